@@ -1,0 +1,175 @@
+"""Pin the CPU oracle (oracle/jitr_oracle.py) against golden vectors produced by
+the real reference (tests/golden/make_golden.py).  CPU only."""
+import numpy as np
+import pytest
+
+from oracle import jitr_oracle as orc
+
+RTOL_S = 1e-11   # oracle vs reference S-matrix (same algorithm, same LAPACK): rounding-level
+RTOL_XS = 1e-10
+
+
+def normerr(a, b):
+    """max-norm relative error (for vectors whose small entries carry no relative accuracy)."""
+    a = np.asarray(a)
+    b = np.asarray(b)
+    return np.max(np.abs(a - b)) / np.max(np.abs(b))
+
+
+def relerr(a, b):
+    a = np.asarray(a)
+    b = np.asarray(b)
+    return np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300))
+
+
+ELASTIC = [
+    ("config1_n208Pb_30MeV", "kduq"), ("config3_p48Ca_30MeV", "kduq"),
+    ("config2_n40Ca_E00", "kduq"), ("config2_n40Ca_E31", "kduq"),
+    ("config2_n208Pb_E06", "kduq"), ("config2_n208Pb_E15", "kduq"),
+    ("chuq_p90Zr_25MeV", "chuq"), ("chuq_n90Zr_12MeV", "chuq"), ("localomp_p54Fe_35MeV", "local"),
+]
+
+
+def _potentials(g, model, p):
+    tgt = tuple(int(v) for v in g["target"])
+    prj = tuple(int(v) for v in g["projectile"])
+    Elab = float(g["kin"][0])
+    r = g["rgrid"]
+    if model == "kduq":
+        return orc.kduq_potentials(r, prj, tgt, Elab, p)
+    if model == "chuq":
+        return orc.chuq_potentials(r, prj, tgt, Elab, p)
+    return orc.local_omp_potentials(r, tgt[0], tgt[1] * prj[1], p)
+
+
+@pytest.mark.parametrize("name,model", ELASTIC)
+def test_elastic_workspace(golden, name, model):
+    g = golden(name)
+    N, lmax = int(g["N"]), int(g["lmax"])
+    kin = tuple(g["kin"])
+    tgt, prj = g["target"], g["projectile"]
+    # kinematics restatement
+    kin2 = orc.semi_relativistic_kinematics(g["masses"][0], g["masses"][1], kin[0], int(tgt[1] * prj[1]))
+    np.testing.assert_allclose(kin2, kin, rtol=1e-14)
+    ws = orc.ElasticWorkspace(N, lmax, float(g["Rch"]), kin, g["angles"], int(tgt[1] * prj[1]))
+    # setup tables
+    assert relerr(ws.asym, g["asym"]) < 1e-13
+    np.testing.assert_allclose(ws.rgrid, g["rgrid"], rtol=1e-14)
+    np.testing.assert_allclose(ws.free[0], g["free0"], rtol=1e-13)
+    np.testing.assert_allclose(ws.free[3], g["free3"], rtol=1e-13)
+    np.testing.assert_allclose(ws.b, g["basis_boundary"], rtol=1e-13)
+    np.testing.assert_allclose(ws.P, g["P"], rtol=1e-13, atol=1e-15)
+    np.testing.assert_allclose(ws.f_c, g["f_c"], rtol=1e-13)
+    nsamp = min(len(g["params"]), 6)
+    for i in range(nsamp):
+        c, so, co = _potentials(g, model, g["params"][i])
+        np.testing.assert_allclose(c, g["central"][i], rtol=1e-13, atol=1e-300)
+        np.testing.assert_allclose(so, g["so"][i], rtol=1e-13, atol=1e-300)
+        np.testing.assert_allclose(co, g["coul"][i], rtol=1e-13, atol=1e-300)
+        sp, sm = ws.smatrix(c, so, co)
+        nl = int(g["nl"][i])
+        assert len(sp) == nl
+        assert relerr(sp, g["splus"][i, :nl]) < RTOL_S
+        assert relerr(sm[1:], g["sminus"][i, 1:nl]) < RTOL_S
+        dsdo, Ay, Q, tot, rxn = ws.xs(c, so, co)
+        assert relerr(dsdo, g["dsdo"][i]) < RTOL_XS
+        np.testing.assert_allclose(Ay, g["Ay"][i], rtol=1e-8, atol=1e-10)
+        np.testing.assert_allclose(Q, g["Q"][i], rtol=1e-8, atol=1e-10)
+        assert abs(tot - g["tot"][i]) / g["tot"][i] < RTOL_XS
+        assert abs(rxn - g["rxn"][i]) / g["rxn"][i] < RTOL_XS
+
+
+def test_kduq_shape_params(golden):
+    g = golden("kduq_shape_params")
+    P = golden("kduq_params")
+    for key in g.files:
+        tag, A, Z, E = key.split("_")
+        prj = (1, 0) if tag == "n" else (1, 1)
+        samples = P["federal_n"] if tag == "n" else P["federal_p"]
+        for i in range(0, 416, 7):
+            with np.errstate(over="ignore"):
+                c, s, co = orc.kduq_shape_params(prj, (int(A), int(Z)), float(E), samples[i])
+            np.testing.assert_allclose(list(c) + list(s) + list(co), g[key][i], rtol=1e-14)
+
+
+def test_local_rk_case(golden):
+    """restated tests/test_local.py: N=70, a=10 pi, WS+Coulomb, l = 0..2 x 10 energies."""
+    g = golden("test_local")
+    N, a = int(g["N"]), float(g["a"])
+    for i in range(10):
+        Elab, Ecm, mu, k, eta = g["kin"][i]
+        for l in range(3):
+            asym = tuple(np.array([v]) for v in orc.coulomb_hankel(l, eta, a))
+            assert relerr(np.array(asym).ravel(), g["asym"][i, l]) < 1e-13
+            R, S, u = orc.solver_solve(N, a, [l], [Ecm], [k], [mu], asym, local_potential=g["pot"][i])
+            assert relerr(S[0, 0], g["S"][i, l]) < RTOL_S
+            assert relerr(R[0, 0], g["R"][i, l]) < 1e-10
+            assert relerr(u[0], g["uext"][i, l]) < 1e-10
+
+
+def test_wavefunction_case(golden):
+    g = golden("test_wavefunction")
+    N, a = int(g["N"]), float(g["a"])
+    Elab, Ecm, mu, k, eta = g["kin"]
+    for l in (0, 1, 4):
+        asym = tuple(np.array([v]) for v in g[f"asym{l}"])
+        R, S, x, u = orc.solver_solve(N, a, [l], [Ecm], [k], [mu], asym, local_potential=g[f"pot{l}"], wavefunction=True)
+        # N=100, strongly absorbed (|S| ~ 1e-2): the reference's own inverse-vs-solve noise floor is ~1e-10 here
+        assert relerr(S, g[f"S{l}"]) < 1e-9
+        assert np.max(np.abs(S - g[f"S{l}"])) < 1e-11
+        assert normerr(x, g[f"x{l}"]) < 1e-10
+        uint = sum(x[0, n] / a * orc.basis_function(N, n + 1, a, g["svals"]) for n in range(N))
+        assert normerr(uint, g[f"uint{l}"]) < 1e-10
+
+
+def test_coupled_config5(golden):
+    g = golden("config5_coupled")
+    for N in (40, 50):
+        for l in range(4):
+            asym = tuple(g[f"l{l}_asym"])
+            R, S, x, u = orc.solver_solve(N, float(g["a"]), [l] * 3, g["E"], g["k"], g["mu"], asym,
+                                          local_potential=g[f"N{N}_l{l}_V"], wavefunction=True)
+            assert relerr(S, g[f"N{N}_l{l}_S"]) < 1e-10
+            assert relerr(R, g[f"N{N}_l{l}_R"]) < 1e-9
+            assert normerr(x, g[f"N{N}_l{l}_x"]) < 1e-10
+
+
+def test_coupled_single(golden):
+    g = golden("test_coupled_single")
+    Elab, Ecm, mu, k, eta = g["kin"]
+    asym = tuple(g["asym"])
+    Rm, Sm, um = orc.solver_solve(40, float(g["a"]), [0, 0], [Ecm] * 2, [k] * 2, [mu] * 2, asym, local_potential=g["V2"])
+    assert np.max(np.abs(Sm - g["Sm"])) < 1e-11
+    asym1 = tuple(v[:1] for v in asym)
+    R1, S1, u1 = orc.solver_solve(40, float(g["a"]), [0], [Ecm], [k], [mu], asym1, local_potential=g["V1"])
+    assert relerr(S1, g["S1"]) < RTOL_S
+    np.testing.assert_almost_equal(Sm[0, 0], S1[0, 0])
+
+
+def test_nonlocal(golden):
+    g = golden("nonlocal_yamaguchi")
+    Elab, Ecm, mu, k, eta = g["kin"]
+    asym = tuple(np.array([v]) for v in g["yam_asym"])
+    for N in (20, 40):
+        R, S, u = orc.solver_solve(N, float(g["a"]), [0], [Ecm], [k], [mu], asym, nonlocal_potential=g[f"yam{N}_V"])
+        assert relerr(S, g[f"yam{N}_S"]) < RTOL_S
+    delta = np.rad2deg(np.real(np.log(S[0, 0]) / 2j))
+    assert abs(delta - (-66.98635852)) < 1e-6  # SURVEY appendix B (mesh value, not the analytic one)
+    g = golden("config4_nonlocal")
+    Elab, Ecm, mu, k, eta = g["kin"]
+    for l in (0, 3):
+        asym = tuple(np.array([v]) for v in g[f"l{l}_asym"])
+        R, S, u = orc.solver_solve(60, float(g["a"]), [l], [Ecm], [k], [mu], asym, nonlocal_potential=g[f"s0_l{l}_U"])
+        assert relerr(S, g[f"s0_l{l}_S"]) < RTOL_S
+
+
+def test_survey_anchor_values(golden):
+    """SURVEY.md appendix B sanity anchors (captured independently in the survey session)."""
+    g = golden("config1_n208Pb_30MeV")
+    assert int(g["nl"][0]) == 21
+    assert abs(g["splus"][0, 0] - (-0.4133998941888191 + 0.08618832270068263j)) < 1e-12
+    assert abs(g["tot"][0] - 5045.3932311612) < 1e-6
+    assert abs(g["rxn"][0] - 2418.2642857019428) < 1e-6
+    assert abs(g["dsdo"][0][90] - 8.6793242520790077) < 1e-8
+    g = golden("nb_kduq_uq_demo")
+    assert round(float(g["pct84_idx9"]), 6) == 1.163423  # kduq_uq_demo.ipynb cell 20
