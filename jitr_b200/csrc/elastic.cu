@@ -1,0 +1,256 @@
+// C-ABI entry points of the elastic path: the sweep dispatcher (kernel template in
+// elastic_sweep.cuh, one translation unit per nbasis) and the observable kernel
+// (xs/elastic.py:310-381).  See include/jitr_b200.h for the contract of each entry point.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+
+#include "common.cuh"
+#include "jitr_b200.h"
+#include "lu_warp.cuh"
+#include "potentials.cuh"
+#include "sweep_decl.cuh"
+
+namespace jitr {
+
+// ---------------------------------------------------------------------------------------------
+// observables: one CTA per (energy, sample chunk); Legendre tables of that energy staged in
+// shared memory once, then every sample of the chunk streams S in and dsdo/Ay/Q out, coalesced.
+// ---------------------------------------------------------------------------------------------
+struct ObsArgs {
+    int lmax, n_angles, n_energies, chunk;
+    long long n_samples;
+    const double2* S;
+    const int* nl;
+    const double* P;
+    const double* P1;
+    const double2* phase;
+    const double2* f_c;
+    const double* kvec;
+    double* dsdo;
+    double* Ay;
+    double* Q;
+    double* tot_rxn;
+};
+
+__global__ void __launch_bounds__(256) elastic_observables_kernel(const ObsArgs A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int L1 = A.lmax + 1, NA = A.n_angles;
+    double* Ps = reinterpret_cast<double*>(smem_raw);  // [L1][NA]
+    double* P1s = Ps + (size_t)L1 * NA;                 // [L1][NA]
+    double2* ca = reinterpret_cast<double2*>(P1s + (size_t)L1 * NA);  // [L1] coefficient of P_l
+    double2* cb = ca + L1;                                            // [L1] coefficient of P^1_l
+    double* red = reinterpret_cast<double*>(cb + L1);                 // [2]
+    const int e = blockIdx.y;
+    const double* Pg = A.P + (size_t)e * L1 * NA;
+    const double* P1g = A.P1 + (size_t)e * L1 * NA;
+    for (int i = threadIdx.x; i < L1 * NA; i += blockDim.x) {
+        Ps[i] = Pg[i];
+        P1s[i] = P1g[i];
+    }
+    const double k = A.kvec[e];
+    const long long s_begin = (long long)blockIdx.x * A.chunk;
+    long long s_end = s_begin + A.chunk;
+    if (s_end > A.n_samples) s_end = A.n_samples;
+    for (long long s = s_begin; s < s_end; ++s) {
+        const long long pair = s * A.n_energies + e;
+        const int nl = A.nl[pair];
+        const double2* Sp = A.S + (size_t)pair * 2 * L1;
+        const double2* Sm = Sp + L1;
+        __syncthreads();  // tables loaded / previous sample's coefficients consumed
+        if (threadIdx.x < ((L1 + 31) & ~31)) {  // whole warps, so the shuffles below are well defined
+            const int l = threadIdx.x;
+            double2 a_l = make_double2(0.0, 0.0), b_l = make_double2(0.0, 0.0);
+            double rx = 0.0, tt = 0.0;
+            if (l < nl) {
+                const double2 sp = Sp[l], sm = Sm[l], ph = A.phase[(size_t)e * L1 + l];
+                // (l+1)(S+ - 1) + l (S- - 1) ;  S+ - S-     (xs/elastic.py:357-362)
+                const double2 wa = make_double2((l + 1) * (sp.x - 1.0) + l * (sm.x - 1.0), (l + 1) * sp.y + l * sm.y);
+                const double2 wb = make_double2(sp.x - sm.x, sp.y - sm.y);
+                a_l = cmul(ph, wa);
+                b_l = cmul(ph, wb);
+                rx = (l + 1) * (1.0 - (sp.x * sp.x + sp.y * sp.y)) + l * (1.0 - (sm.x * sm.x + sm.y * sm.y));
+                tt = (l + 1) * (1.0 - sp.x) + l * (1.0 - sm.x);
+            }
+            if (l < L1) {
+                ca[l] = a_l;
+                cb[l] = b_l;
+            }
+            for (int o = 16; o > 0; o >>= 1) {
+                rx += __shfl_down_sync(0xffffffffu, rx, o);
+                tt += __shfl_down_sync(0xffffffffu, tt, o);
+            }
+            if ((threadIdx.x & 31) == 0) {
+                red[2 * (threadIdx.x >> 5)] = tt;
+                red[2 * (threadIdx.x >> 5) + 1] = rx;
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double tt = 0.0, rx = 0.0;
+            for (int w = 0; w < (L1 + 31) / 32; ++w) {
+                tt += red[2 * w];
+                rx += red[2 * w + 1];
+            }
+            A.tot_rxn[2 * pair] = tt * (10.0 * 2.0 * M_PI / (k * k));
+            A.tot_rxn[2 * pair + 1] = rx * (10.0 * M_PI / (k * k));
+        }
+        for (int t = threadIdx.x; t < NA; t += blockDim.x) {
+            double2 fa = A.f_c[(size_t)e * NA + t];
+            double2 fb = make_double2(0.0, 0.0);
+            for (int l = 0; l < nl; ++l) {
+                const double pl = Ps[l * NA + t], p1 = P1s[l * NA + t];
+                const double2 al = ca[l], bl = cb[l];
+                fa.x = fma(pl, al.x, fa.x);
+                fa.y = fma(pl, al.y, fa.y);
+                fb.x = fma(p1, bl.x, fb.x);
+                fb.y = fma(p1, bl.y, fb.y);
+            }
+            const double d0 = fa.x * fa.x + fa.y * fa.y + fb.x * fb.x + fb.y * fb.y;
+            const double den = fmax(d0, 1e-30);
+            // conj(a) b = (a.x - i a.y)(b.x + i b.y)
+            const double re = fa.x * fb.x + fa.y * fb.y, im = fa.x * fb.y - fa.y * fb.x;
+            const size_t o = (size_t)pair * NA + t;
+            A.dsdo[o] = d0 * 10.0;
+            if (A.Ay) A.Ay[o] = 2.0 * im / den;
+            if (A.Q) A.Q[o] = 2.0 * re / den;
+        }
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// stand-alone evaluation of the built-in potential forms on the mesh (same device code as the
+// fused sweep): SingleChannelOpticalModel.evaluate, omp.py:26-43 / kduq.py:541-559
+// ---------------------------------------------------------------------------------------------
+__global__ void eval_potentials_kernel(int N, int model, long long n_pairs, int n_energies, const double* mesh_x,
+                                       const double* etab, const double* params, int n_params, double2* central,
+                                       double2* spin_orbit, double* coulomb) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_pairs * N) return;
+    const long long pair = idx / N;
+    const int n = (int)(idx - pair * N);
+    const long long smp = pair / n_energies;
+    const int e = (int)(pair - smp * n_energies);
+    const double* et = etab + (size_t)e * JITR_B200_ET_STRIDE;
+    const Shape sh = shape_from_model(model, params + (size_t)smp * n_params, et);
+    double2 vc, vs;
+    double co;
+    eval_shape(sh, mesh_x[n] * et[JITR_B200_ET_RCH], vc, vs, co);
+    central[idx] = vc;
+    spin_orbit[idx] = vs;
+    coulomb[idx] = co;
+}
+
+template <bool PARAMS>
+static int dispatch_sweep(int nbasis, const SweepArgs& a, cudaStream_t st) {
+    switch (nbasis) {
+#define JITR_CASE(NN) \
+    case NN:          \
+        return launch_sweep<NN, PARAMS>(a, st);
+        JITR_SWEEP_SIZES(JITR_CASE)
+#undef JITR_CASE
+        default:
+            return set_error(JITR_B200_ERR_UNSUPPORTED, "elastic sweep: nbasis not in the compiled set");
+    }
+}
+
+}  // namespace jitr
+
+using namespace jitr;
+
+extern "C" int jitr_b200_elastic_sweep_params(int nbasis, int lmax, int model, long long n_samples, int n_energies,
+                                              const double* That, const double* mesh_x, const double* bvec,
+                                              const double* etab, const double* asym, const double* params,
+                                              int n_params, double tol, double* S_out, int* nl_out, int* status,
+                                              void* stream) {
+    if (lmax < 0 || n_samples < 0 || n_energies < 1 || !That || !mesh_x || !bvec || !etab || !asym || !params ||
+        !S_out || !nl_out || !status)
+        return set_error(JITR_B200_ERR_BAD_ARG, "elastic_sweep_params: null pointer or bad size");
+    const int need = model == JITR_B200_MODEL_KDUQ ? 40 : model == JITR_B200_MODEL_CHUQ ? 22 : model == JITR_B200_MODEL_LOCAL ? 15 : 17;
+    if (model < 0 || model > 3 || n_params < need)
+        return set_error(JITR_B200_ERR_BAD_ARG, "elastic_sweep_params: model / n_params mismatch");
+    SweepArgs a{};
+    a.lmax = lmax; a.model = model; a.n_energies = n_energies; a.n_params = n_params;
+    a.n_pairs = n_samples * n_energies;
+    a.That = That; a.mesh_x = mesh_x; a.bvec = bvec; a.etab = etab;
+    a.asym = reinterpret_cast<const double2*>(asym);
+    a.params = params; a.tol = tol;
+    a.S_out = reinterpret_cast<double2*>(S_out); a.nl_out = nl_out; a.status = status;
+    return dispatch_sweep<true>(nbasis, a, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int jitr_b200_elastic_sweep_tensors(int nbasis, int lmax, long long n_samples, int n_energies,
+                                               const double* That, const double* mesh_x, const double* bvec,
+                                               const double* etab, const double* asym, const double* central,
+                                               const double* spin_orbit, const double* coulomb, double tol,
+                                               double* S_out, int* nl_out, int* status, void* stream) {
+    if (lmax < 0 || n_samples < 0 || n_energies < 1 || !That || !mesh_x || !bvec || !etab || !asym || !central ||
+        !S_out || !nl_out || !status)
+        return set_error(JITR_B200_ERR_BAD_ARG, "elastic_sweep_tensors: null pointer or bad size");
+    SweepArgs a{};
+    a.lmax = lmax; a.model = 0; a.n_energies = n_energies; a.n_params = 0;
+    a.n_pairs = n_samples * n_energies;
+    a.That = That; a.mesh_x = mesh_x; a.bvec = bvec; a.etab = etab;
+    a.asym = reinterpret_cast<const double2*>(asym);
+    a.central = reinterpret_cast<const double2*>(central);
+    a.spin_orbit = reinterpret_cast<const double2*>(spin_orbit);
+    a.coulomb = reinterpret_cast<const double2*>(coulomb);
+    a.tol = tol;
+    a.S_out = reinterpret_cast<double2*>(S_out); a.nl_out = nl_out; a.status = status;
+    return dispatch_sweep<false>(nbasis, a, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int jitr_b200_elastic_observables(int lmax, int n_angles, long long n_samples, int n_energies,
+                                             const double* S, const int* nl, const double* P, const double* P1,
+                                             const double* phase, const double* f_c, const double* kvec,
+                                             double* dsdo, double* Ay, double* Q, double* tot_rxn, void* stream) {
+    if (lmax < 0 || lmax > 255 || n_angles < 1 || n_samples < 0 || n_energies < 1 || !S || !nl || !P || !P1 || !phase ||
+        !f_c || !kvec || !dsdo || !tot_rxn)
+        return set_error(JITR_B200_ERR_BAD_ARG, "elastic_observables: null pointer or bad size");
+    if (n_samples == 0) return JITR_B200_OK;
+    ObsArgs a{};
+    a.lmax = lmax; a.n_angles = n_angles; a.n_energies = n_energies; a.n_samples = n_samples;
+    a.S = reinterpret_cast<const double2*>(S); a.nl = nl; a.P = P; a.P1 = P1;
+    a.phase = reinterpret_cast<const double2*>(phase);
+    a.f_c = reinterpret_cast<const double2*>(f_c);
+    a.kvec = kvec; a.dsdo = dsdo; a.Ay = Ay; a.Q = Q; a.tot_rxn = tot_rxn;
+    const int L1 = lmax + 1;
+    const size_t smem = (size_t)2 * L1 * n_angles * 8 + (size_t)2 * L1 * 16 + 2 * 8 * 8;
+    if (smem > 232448) return set_error(JITR_B200_ERR_UNSUPPORTED, "elastic_observables: (lmax+1)*n_angles tables exceed shared memory");
+    static size_t configured = 0;
+    if (smem > configured) {
+        if (cudaFuncSetAttribute(elastic_observables_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return set_cuda_error("cudaFuncSetAttribute(observables)");
+        configured = smem;
+    }
+    // chunk the sample axis so that the grid is a few waves of the SM count
+    const int sms = sm_count();
+    long long target_blocks_x = (4LL * sms + n_energies - 1) / n_energies;
+    if (target_blocks_x < 1) target_blocks_x = 1;
+    long long chunk = (n_samples + target_blocks_x - 1) / target_blocks_x;
+    if (chunk < 1) chunk = 1;
+    a.chunk = (int)(chunk > (1 << 30) ? (1 << 30) : chunk);
+    dim3 grid((unsigned)((n_samples + a.chunk - 1) / a.chunk), (unsigned)n_energies);
+    elastic_observables_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(a);
+    count_launch();
+    if (cudaGetLastError() != cudaSuccess) return set_cuda_error("elastic_observables launch");
+    return JITR_B200_OK;
+}
+
+extern "C" int jitr_b200_eval_potentials(int nbasis, int model, long long n_samples, int n_energies, const double* mesh_x,
+                                         const double* etab, const double* params, int n_params, double* central,
+                                         double* spin_orbit, double* coulomb, void* stream) {
+    if (nbasis < 1 || n_samples < 0 || n_energies < 1 || !mesh_x || !etab || !params || !central || !spin_orbit || !coulomb)
+        return set_error(JITR_B200_ERR_BAD_ARG, "eval_potentials: null pointer or bad size");
+    const int need = model == JITR_B200_MODEL_KDUQ ? 40 : model == JITR_B200_MODEL_CHUQ ? 22 : model == JITR_B200_MODEL_LOCAL ? 15 : 17;
+    if (model < 0 || model > 3 || n_params < need) return set_error(JITR_B200_ERR_BAD_ARG, "eval_potentials: model / n_params mismatch");
+    const long long total = n_samples * n_energies * nbasis;
+    if (total == 0) return JITR_B200_OK;
+    eval_potentials_kernel<<<(unsigned)((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        nbasis, model, n_samples * n_energies, n_energies, mesh_x, etab, params, n_params,
+        reinterpret_cast<double2*>(central), reinterpret_cast<double2*>(spin_orbit), coulomb);
+    count_launch();
+    if (cudaGetLastError() != cudaSuccess) return set_cuda_error("eval_potentials launch");
+    return JITR_B200_OK;
+}

@@ -1,0 +1,180 @@
+// Built-in optical-potential forms and global-parameter maps, evaluated on the mesh inside the
+// fused solve kernel.  Reference: optical_potentials/potential_forms.py:11,40-88,134-153 (forms),
+// kduq.py:100-131,370-528 (KDUQ map), chuq.py:140-227 (CHUQ map), omp.py:54-149 (Local).
+#pragma once
+#include <cuda_runtime.h>
+#include "jitr_b200.h"
+
+namespace jitr {
+
+#define ET_A13 JITR_B200_ET_A13
+#define ET_AM13 JITR_B200_ET_AM13
+#define ET_AM23 JITR_B200_ET_AM23
+#define ET_AM53 JITR_B200_ET_AM53
+
+constexpr double kHbarc = 197.3269804;          // utils/constants.py:5
+constexpr double kAlpha = 1.0 / 137.0359991;    // utils/constants.py:6
+constexpr double kKappa2 = 0.5000000000000001;  // WAVENUMBER_PION**2 = sqrt(1/2)**2 (constants.py:7)
+constexpr double kMaxArg = 36.841361487904734;  // log(1/1e-16), potential_forms.py:11
+
+// canonical shape vector:
+//  V_c  = -Vv f(Rv,av) - i Wv f(Rw,aw) + 4 ad (Vd + i Wd) f'(Rd,ad)
+//  V_so = Vso g(Rso,aso) + i Wso g(Rwso,awso)        (Vso, Wso already include 1/kappa^2 or 2)
+//  V_C  = Zz alpha hbarc * (r <= RC ? (3 - (r/RC)^2)/(2 RC) : 1/r)
+struct Shape {
+    double Vv, Rv, av, Wv, Rw, aw, Vd, Wd, Rd, ad, Vso, Rso, aso, Wso, Rwso, awso, RC, Zz;
+};
+
+__device__ __forceinline__ void ws_forms(double r, double R, double a, double& f, double& fp) {
+    // woods_saxon_safe / woods_saxon_prime_safe (potential_forms.py:40-67): exactly 0 beyond MAX_ARG
+    double x = (r - R) / a;
+    if (x <= kMaxArg) {
+        double e = exp(x);
+        double d = 1.0 + e;
+        f = 1.0 / d;
+        fp = -e / (a * (d * d));
+    } else {
+        f = 0.0;
+        fp = 0.0;
+    }
+}
+
+__device__ __forceinline__ void eval_shape(const Shape& s, double r, double2& vc, double2& vso, double& vcoul) {
+    double f, fp;
+    ws_forms(r, s.Rv, s.av, f, fp);
+    double re = -s.Vv * f;
+    ws_forms(r, s.Rw, s.aw, f, fp);
+    double im = -s.Wv * f;
+    ws_forms(r, s.Rd, s.ad, f, fp);
+    // - (-4 ad) Vd f'  - i (-4 ad) Wd f'   (omp.py:68-73, kduq.py:163-167)
+    re -= (-4.0 * s.ad) * s.Vd * fp;
+    im -= (-4.0 * s.ad) * s.Wd * fp;
+    vc = make_double2(re, im);
+    // thomas_safe = (1/r) f'  (potential_forms.py:70-88)
+    double y = 1.0 / r;
+    ws_forms(r, s.Rso, s.aso, f, fp);
+    double sre = s.Vso * (y * fp);
+    ws_forms(r, s.Rwso, s.awso, f, fp);
+    double sim = s.Wso * (y * fp);
+    vso = make_double2(sre, sim);
+    if (s.Zz == 0.0) {
+        vcoul = 0.0;
+    } else {
+        double inv = (r <= s.RC) ? 1.0 / (2.0 * s.RC) * (3.0 - (r / s.RC) * (r / s.RC)) : 1.0 / r;
+        vcoul = s.Zz * kAlpha * kHbarc * inv;
+    }
+}
+
+// ---- global parameter maps -------------------------------------------------------------------
+__device__ __forceinline__ Shape shape_from_canonical(const double* __restrict__ p, const double* __restrict__ et) {
+    Shape s;
+    s.Vv = p[0]; s.Rv = p[1]; s.av = p[2]; s.Wv = p[3]; s.Rw = p[4]; s.aw = p[5];
+    s.Vd = p[6]; s.Wd = p[7]; s.Rd = p[8]; s.ad = p[9];
+    s.Vso = p[10]; s.Rso = p[11]; s.aso = p[12]; s.Wso = p[13]; s.Rwso = p[14]; s.awso = p[15];
+    s.RC = p[16];
+    s.Zz = et[JITR_B200_ET_ZT] * et[JITR_B200_ET_ZP];
+    return s;
+}
+
+// kduq.calculate_params, kduq.py:438-528 ; p has 40 entries (neutron rows padded with zeros)
+__device__ __forceinline__ Shape shape_from_kduq(const double* __restrict__ p, const double* __restrict__ et) {
+    const double A = et[JITR_B200_ET_AT], Z = et[JITR_B200_ET_ZT], Zp = et[JITR_B200_ET_ZP];
+    const double Elab = et[JITR_B200_ET_ELAB];
+    const double A13 = et[ET_A13], Am13 = et[ET_AM13], Am23 = et[ET_AM23], Am53 = et[ET_AM53];
+    double asym = (A - 2.0 * Z) / A;
+    const double factor = (Zp == 1.0) ? 1.0 : -1.0;  // (-1)**(Zp+1)
+    asym *= factor;
+    const double Ef = p[0] + p[1] * A;
+    const double v1 = p[2] + p[3] * asym - p[4] * A;
+    const double v2 = p[5] + p[6] * A * factor;
+    const double v3 = p[7] + p[8] * A * factor;
+    const double v4 = p[9];
+    const double dE = Elab - Ef;
+    double vv = v1 * (1.0 - v2 * dE + v3 * (dE * dE) - v4 * (dE * dE * dE));
+    const double rv = p[10] - p[11] * Am13;
+    const double av = p[12] - p[13] * A;
+    const double w1 = p[14] + p[15] * A;
+    const double w2 = p[16] + p[17] * A;
+    const double wv = w1 * (dE * dE) / (dE * dE + w2 * w2);
+    const double d1 = p[18] + p[19] * asym;
+    const double d2 = p[20] + p[21] / (1.0 + exp((A - p[23]) / p[22]));  // inf -> 0 like numpy (kduq.py:470)
+    const double d3 = p[24];
+    const double wd = d1 * (dE * dE) / (dE * dE + d3 * d3) * exp(-d2 * dE);
+    const double rd = p[25] - p[26] * A13;
+    const double ad = p[27] + p[28] * A * factor;
+    const double vso1 = p[29] + p[30] * A;
+    const double vso = vso1 * exp(-p[31] * dE);
+    const double wso = p[32] * (dE * dE) / (dE * dE + p[33] * p[33]);
+    const double rso = p[34] - p[35] * Am13;
+    const double aso = p[36];
+    double RC = rv * A13;
+    if (Zp == 1.0) {
+        const double rc0 = p[37] + p[38] * Am23 + p[39] * Am53;
+        RC = rc0 * A13;
+        const double Vcbar = 1.73 / rc0 * Z * Am13;
+        vv += v1 * Vcbar * (v2 - 2.0 * v3 * dE + 3.0 * v4 * (dE * dE));
+    }
+    Shape s;
+    s.Vv = vv; s.Rv = rv * A13; s.av = av;
+    s.Wv = wv; s.Rw = rv * A13; s.aw = av;
+    s.Vd = 0.0; s.Wd = wd; s.Rd = rd * A13; s.ad = ad;
+    s.Vso = vso / kKappa2; s.Rso = rso * A13; s.aso = aso;
+    s.Wso = wso / kKappa2; s.Rwso = rso * A13; s.awso = aso;
+    s.RC = RC;
+    s.Zz = Z * Zp;
+    return s;
+}
+
+// chuq.calculate_params, chuq.py:140-227 ; 22 entries
+__device__ __forceinline__ Shape shape_from_chuq(const double* __restrict__ p, const double* __restrict__ et) {
+    const double A = et[JITR_B200_ET_AT], Z = et[JITR_B200_ET_ZT], Zp = et[JITR_B200_ET_ZP];
+    const double Elab = et[JITR_B200_ET_ELAB];
+    const double A13 = et[ET_A13];
+    const bool is_p = (Zp == 1.0);
+    const double alpha = ((A - Z) - Z) / A;
+    const double asym = (is_p ? 1.0 : -1.0) * alpha;
+    const double R0 = p[3] * A13 + p[4];
+    const double Rw = p[9] * A13 + p[10];
+    const double Rso = p[17] * A13 + p[18];
+    const double RC = p[20] * A13 + p[21];
+    const double Ec = is_p ? 6.0 * Z * kAlpha * kHbarc / (5.0 * RC) : 0.0;
+    const double dE = Elab - Ec;
+    const double V = p[0] + p[1] * dE + asym * p[2];
+    const double Wv = p[6] / (1.0 + exp((p[7] - dE) / p[8]));
+    const double Ws = (p[12] + asym * p[13]) / (1.0 + exp((dE - p[14]) / p[15]));
+    Shape s;
+    s.Vv = V; s.Rv = R0; s.av = p[5];
+    s.Wv = Wv; s.Rw = Rw; s.aw = p[11];
+    s.Vd = 0.0; s.Wd = Ws; s.Rd = Rw; s.ad = p[11];
+    s.Vso = 2.0 * p[16]; s.Rso = Rso; s.aso = p[19];
+    s.Wso = 0.0; s.Rwso = Rso; s.awso = p[19];
+    s.RC = RC;
+    s.Zz = Z * Zp;
+    return s;
+}
+
+// LocalOpticalPotential.evaluate, omp.py:115-149 ; 15 entries, radius factor from the energy table
+__device__ __forceinline__ Shape shape_from_local(const double* __restrict__ p, const double* __restrict__ et) {
+    const double rf = et[JITR_B200_ET_RSCALE];
+    Shape s;
+    s.Vv = p[0]; s.Rv = p[1] * rf; s.av = p[2];
+    s.Wv = p[3]; s.Rw = p[4] * rf; s.aw = p[5];
+    s.Wd = p[6]; s.Vd = p[7]; s.Rd = p[8] * rf; s.ad = p[9];
+    // (Vso + i Wso)/kappa^2 * thomas(Rso, aso)  (omp.py:79-81)
+    s.Vso = p[10] / kKappa2; s.Rso = p[12] * rf; s.aso = p[13];
+    s.Wso = p[11] / kKappa2; s.Rwso = p[12] * rf; s.awso = p[13];
+    s.RC = p[14] * rf;
+    s.Zz = et[JITR_B200_ET_ZT] * et[JITR_B200_ET_ZP];
+    return s;
+}
+
+__device__ __forceinline__ Shape shape_from_model(int model, const double* __restrict__ p, const double* __restrict__ et) {
+    switch (model) {
+        case JITR_B200_MODEL_KDUQ: return shape_from_kduq(p, et);
+        case JITR_B200_MODEL_CHUQ: return shape_from_chuq(p, et);
+        case JITR_B200_MODEL_LOCAL: return shape_from_local(p, et);
+        default: return shape_from_canonical(p, et);
+    }
+}
+
+}  // namespace jitr

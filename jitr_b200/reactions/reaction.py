@@ -1,0 +1,58 @@
+"""Minimal reaction descriptors.
+
+The reference's ``reactions/reaction.py`` (957 lines: mass tables, Q-values, EXFOR strings) is
+host bookkeeping outside the hot path.  The path only consumes
+``reaction.target.{A, Z, m0}``, ``reaction.projectile.{A, Z, m0}``, ``reaction.process`` and
+``reaction.kinematics(Elab)`` (xs/elastic.py:52-70, kduq.py:548-553), so these light classes keep
+exactly that surface; rest masses are given explicitly (MeV/c^2) instead of looked up.  Any
+object with the same attributes -- including the reference's own ``Reaction`` -- works as well.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+from ..constants import AMU, MASS_N, MASS_P
+from ..utils.kinematics import semi_relativistic_kinematics
+
+
+@dataclass(frozen=True)
+class Particle:
+    A: int
+    Z: int
+    m0: float
+
+
+def _particle(p, mass):
+    if isinstance(p, Particle):
+        return p
+    A, Z = p
+    if mass is None:
+        if (A, Z) == (1, 0):
+            mass = MASS_N
+        elif (A, Z) == (1, 1):
+            mass = MASS_P
+        else:
+            mass = A * AMU  # crude default; pass mass_target= for a tabulated value
+    return Particle(int(A), int(Z), float(mass))
+
+
+class Reaction:
+    """Two-body entrance channel: ``target`` + ``projectile`` (reactions/reaction.py:343-556)."""
+
+    def __init__(self, target, projectile, process=None, mass_target=None, mass_projectile=None):
+        self.target = _particle(target, mass_target)
+        self.projectile = _particle(projectile, mass_projectile)
+        self.process = process
+
+    def kinematics(self, Elab):
+        """reactions/reaction.py:540-556."""
+        return semi_relativistic_kinematics(
+            self.target.m0, self.projectile.m0, Elab, Zz=self.target.Z * self.projectile.Z
+        )
+
+
+class ElasticReaction(Reaction):
+    """reactions/reaction.py:715-738."""
+
+    def __init__(self, target, projectile, mass_target=None, mass_projectile=None):
+        super().__init__(target, projectile, process="el", mass_target=mass_target, mass_projectile=mass_projectile)

@@ -1,0 +1,328 @@
+"""GPU parity tests: the CUDA path (through the C ABI / jitr_b200 API) vs the golden vectors of
+the real reference and vs the CPU oracle on the same seeded inputs.
+
+Tolerances (BASELINE.json north_star): 1e-10 relative on S-matrix elements, 1e-8 relative on
+cross sections.
+"""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+import jitr_b200  # noqa: E402
+from jitr_b200 import _cabi  # noqa: E402
+from jitr_b200.optical_potentials import LocalOpticalPotential, ShapeModel, chuq, kduq  # noqa: E402
+from jitr_b200.reactions import ElasticReaction, ProjectileTargetSystem  # noqa: E402
+from oracle import jitr_oracle as orc  # noqa: E402
+
+RTOL_S = 1e-10
+RTOL_XS = 1e-8
+
+
+def relerr(a, b, floor=0.0):
+    a, b = np.asarray(a), np.asarray(b)
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), floor + 1e-300)))
+
+
+def normerr(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    return float(np.max(np.abs(a - b)) / np.max(np.abs(b)))
+
+
+def make_ws(g):
+    rx = ElasticReaction(tuple(int(v) for v in g["target"]), tuple(int(v) for v in g["projectile"]),
+                         mass_target=float(g["masses"][0]), mass_projectile=float(g["masses"][1]))
+    kin = rx.kinematics(float(g["kin"][0]))
+    solver = jitr_b200.Solver(int(g["N"]))
+    ws = jitr_b200.DifferentialWorkspace.build_from_system(rx, kin, float(g["Rch"]), solver, int(g["lmax"]), g["angles"])
+    return rx, kin, ws
+
+
+def model_for(name, g):
+    if name.startswith("chuq"):
+        return chuq.CHUQ()
+    if name.startswith("localomp"):
+        return LocalOpticalPotential()
+    return kduq.KDUQ(tuple(int(v) for v in g["projectile"]))
+
+
+def check_xs_against_golden(x, S, nl, g, idx):
+    """x: ElasticXS of tensors with leading sample axis; compare rows idx with the golden arrays."""
+    S = S.cpu().numpy()
+    nl = nl.cpu().numpy()
+    for row, i in enumerate(idx):
+        L = int(g["nl"][i])
+        assert int(nl[row]) == L
+        assert relerr(S[row, 0, :L], g["splus"][i, :L]) < RTOL_S
+        assert relerr(S[row, 1, 1:L], g["sminus"][i, 1:L]) < RTOL_S
+        assert np.all(S[row, :, L:] == 0)
+        assert relerr(x.dsdo[row].cpu().numpy(), g["dsdo"][i]) < RTOL_XS
+        np.testing.assert_allclose(x.Ay[row].cpu().numpy(), g["Ay"][i], rtol=RTOL_XS, atol=1e-10)
+        np.testing.assert_allclose(x.Q[row].cpu().numpy(), g["Q"][i], rtol=RTOL_XS, atol=1e-10)
+        assert abs(float(x.t[row]) - g["tot"][i]) / g["tot"][i] < RTOL_XS
+        assert abs(float(x.rxn[row]) - g["rxn"][i]) / g["rxn"][i] < RTOL_XS
+
+
+ELASTIC = [
+    "config1_n208Pb_30MeV", "config3_p48Ca_30MeV",
+    "config2_n40Ca_E00", "config2_n40Ca_E06", "config2_n40Ca_E15", "config2_n40Ca_E31",
+    "config2_n208Pb_E00", "config2_n208Pb_E06", "config2_n208Pb_E15", "config2_n208Pb_E31",
+    "chuq_p90Zr_25MeV", "chuq_n90Zr_12MeV", "localomp_p54Fe_35MeV",
+]
+
+
+@pytest.mark.parametrize("name", ELASTIC)
+def test_fused_params_sweep_vs_reference_golden(golden, name):
+    """Built-in potentials evaluated in the fused kernel from parameter rows (north_star kernel 1+2+3)."""
+    g = golden(name)
+    rx, kin, ws = make_ws(g)
+    model = model_for(name, g)
+    params = torch.tensor(g["params"], dtype=torch.float64, device="cuda")
+    S, nl, status = ws.integral_workspace.smatrix_params(model, params)
+    assert int(status.abs().sum()) == 0
+    x = ws.xs_params(model, params)
+    check_xs_against_golden(x, S, nl, g, range(len(g["params"])))
+
+
+@pytest.mark.parametrize("name", ["config1_n208Pb_30MeV", "config3_p48Ca_30MeV", "chuq_p90Zr_25MeV"])
+def test_tensor_sweep_vs_reference_golden(golden, name):
+    """User potentials as device tensors of mesh values (reference's DifferentialWorkspace.xs inputs)."""
+    g = golden(name)
+    rx, kin, ws = make_ws(g)
+    c = torch.tensor(g["central"], dtype=torch.complex128, device="cuda")
+    so = torch.tensor(g["so"], dtype=torch.complex128, device="cuda")
+    co = torch.tensor(g["coul"].astype(np.complex128), dtype=torch.complex128, device="cuda")
+    S, nl, status = ws.integral_workspace.smatrix_batch(c, so, co)
+    assert int(status.abs().sum()) == 0
+    x = ws.xs_batch(c, so, co)
+    check_xs_against_golden(x, S, nl, g, range(c.shape[0]))
+    # single-sample reference API (numpy in / numpy out)
+    one = ws.xs(g["central"][0], g["so"][0], g["coul"][0])
+    assert relerr(one.dsdo, g["dsdo"][0]) < RTOL_XS
+    assert abs(one.t - g["tot"][0]) / g["tot"][0] < RTOL_XS
+    sp, sm = ws.integral_workspace.smatrix(g["central"][0], g["so"][0], g["coul"][0])
+    assert len(sp) == int(g["nl"][0]) and relerr(sp, g["splus"][0, : len(sp)]) < RTOL_S
+    tot, rxn = ws.integral_workspace.xs(g["central"][0], g["so"][0], g["coul"][0])
+    assert abs(rxn - g["rxn"][0]) / g["rxn"][0] < RTOL_XS
+    tp, tm = ws.integral_workspace.transmission_coefficients(g["central"][0], g["so"][0], g["coul"][0])
+    np.testing.assert_allclose(tp, 1 - np.abs(g["splus"][0, : len(tp)]) ** 2, rtol=1e-8, atol=1e-12)
+
+
+def test_optional_spin_orbit_equals_zeros(golden):
+    """restated tests/test_xs_optional_spin_orbit.py: omitted spin-orbit == explicit zeros."""
+    g = golden("config1_n208Pb_30MeV")
+    rx, kin, ws = make_ws(g)
+    c = g["central"][0]
+    a = ws.xs(c)
+    b = ws.xs(c, np.zeros_like(c))
+    np.testing.assert_allclose(a.dsdo, b.dsdo, rtol=1e-12)
+    np.testing.assert_allclose(a.Ay, b.Ay, rtol=1e-7, atol=1e-12)
+    assert a.t == b.t and a.rxn == b.rxn
+    sp0, sm0 = ws.integral_workspace.smatrix(c)
+    sp1, sm1 = ws.integral_workspace.smatrix(c, np.zeros_like(c))
+    np.testing.assert_allclose(sp0, sp1, rtol=1e-12)
+    with pytest.raises(ValueError):
+        ws.xs(c[:-1])
+
+
+def test_device_potential_forms_vs_reference(golden):
+    """SingleChannelOpticalModel.evaluate: device forms vs the reference's numpy forms (golden) to ~1 ulp."""
+    for name in ("config1_n208Pb_30MeV", "config3_p48Ca_30MeV", "chuq_p90Zr_25MeV", "chuq_n90Zr_12MeV", "localomp_p54Fe_35MeV"):
+        g = golden(name)
+        rx, kin, ws = make_ws(g)
+        model = model_for(name, g)
+        for i in range(min(4, len(g["params"]))):
+            c, so, co = model(ws.radial_grid(), rx, kin, *g["params"][i])
+            np.testing.assert_allclose(c, g["central"][i], rtol=1e-13, atol=1e-300)
+            np.testing.assert_allclose(so, g["so"][i], rtol=1e-13, atol=1e-300)
+            np.testing.assert_allclose(co, g["coul"][i], rtol=1e-13, atol=1e-300)
+
+
+def test_kduq_uq_demo_notebook_golden(golden):
+    """examples/notebooks/kduq_uq_demo.ipynb cell 20: 84th percentile of dsdo/ruth at angle index 9
+    over the 416 federal proton samples prints 1.163423."""
+    g = golden("nb_kduq_uq_demo")
+    P = golden("kduq_params")["federal_p"]
+    rx = ElasticReaction((54, 26), (1, 1), mass_target=float(g["masses"][0]), mass_projectile=float(g["masses"][1]))
+    kin = rx.kinematics(35.0)
+    ang = np.linspace(0.1, np.pi, 180)
+    ws = jitr_b200.DifferentialWorkspace.build_from_system(rx, kin, float(g["Rch"]), jitr_b200.Solver(40), 50, ang)
+    x = ws.xs_params(kduq.KDUQ((1, 1)), torch.tensor(P, dtype=torch.float64, device="cuda"))
+    ratio = x.dsdo.cpu().numpy() / ws.rutherford
+    assert relerr(ratio, g["ratio"]) < RTOL_XS
+    assert round(float(np.percentile(ratio, 84, axis=0)[9]), 6) == 1.163423
+
+
+def test_fused_sweep_vs_oracle_random_shapes():
+    """Seeded random canonical shape parameters, several energies in one launch, vs the CPU oracle."""
+    rng = np.random.default_rng(7)
+    N, lmax = 30, 12
+    rx = ElasticReaction((90, 40), (1, 1), mass_target=83725.25, mass_projectile=938.271653086152)
+    energies = [8.0, 21.5, 40.0]
+    ang = np.linspace(0.2, 3.0, 37)
+    solver = jitr_b200.Solver(N)
+    wss = [jitr_b200.DifferentialWorkspace.build_from_system(rx, rx.kinematics(E), 11.0, solver, lmax, ang) for E in energies]
+    sweep = jitr_b200.ElasticSweep(wss)
+    B = 5
+    p = np.zeros((B, 17))
+    p[:, 0] = rng.uniform(40, 60, B); p[:, 1] = rng.uniform(5, 6, B); p[:, 2] = rng.uniform(0.5, 0.8, B)
+    p[:, 3] = rng.uniform(1, 8, B); p[:, 4] = rng.uniform(5, 6, B); p[:, 5] = rng.uniform(0.5, 0.8, B)
+    p[:, 6] = rng.uniform(0, 2, B); p[:, 7] = rng.uniform(2, 9, B); p[:, 8] = rng.uniform(5, 6.5, B); p[:, 9] = rng.uniform(0.4, 0.7, B)
+    p[:, 10] = rng.uniform(8, 13, B); p[:, 11] = rng.uniform(4.5, 5.5, B); p[:, 12] = rng.uniform(0.5, 0.7, B)
+    p[:, 13] = rng.uniform(-1, 1, B); p[:, 14] = rng.uniform(4.5, 5.5, B); p[:, 15] = rng.uniform(0.5, 0.7, B)
+    p[:, 16] = rng.uniform(5, 6, B)
+    x, status = sweep.xs_params(ShapeModel(), torch.tensor(p, device="cuda"), return_status=True)
+    assert int(status.abs().sum()) == 0
+    for ie, E in enumerate(energies):
+        kin = tuple(rx.kinematics(E))
+        ow = orc.ElasticWorkspace(N, lmax, 11.0, kin, ang, 40)
+        r = ow.rgrid
+        for s in range(B):
+            q = p[s]
+            c = (-q[0] * orc.woods_saxon_safe(r, q[1], q[2]) - 1j * q[3] * orc.woods_saxon_safe(r, q[4], q[5])
+                 + 4 * q[9] * (q[6] + 1j * q[7]) * orc.woods_saxon_prime_safe(r, q[8], q[9]))
+            so = q[10] * orc.thomas_safe(r, q[11], q[12]) + 1j * q[13] * orc.thomas_safe(r, q[14], q[15])
+            co = orc.coulomb_charged_sphere(r, 40, q[16])
+            dsdo, Ay, Q, tot, rxn = ow.xs(c, so, co)
+            assert relerr(x.dsdo[s, ie].cpu().numpy(), dsdo) < RTOL_XS
+            np.testing.assert_allclose(x.Ay[s, ie].cpu().numpy(), Ay, rtol=RTOL_XS, atol=1e-10)
+            assert abs(float(x.rxn[s, ie]) - rxn) / rxn < RTOL_XS
+
+
+def test_no_early_break_and_size_independent_properties():
+    """tol <= 0 issues every (l, j); for a REAL potential |S| = 1 (unitarity) for every partial wave
+    and sigma_rxn = 0 -- a size-independent property checked on a larger batch."""
+    N, lmax = 40, 30
+    rx = ElasticReaction((208, 82), (1, 0), mass_target=193687.12278341982, mass_projectile=939.5654983938299)
+    kin = rx.kinematics(30.0)
+    ws = jitr_b200.IntegralWorkspace(rx, kin, 12.0, jitr_b200.Solver(N), lmax, smatrix_abs_tol=0.0)
+    B = 2048
+    rng = np.random.default_rng(3)
+    p = np.zeros((B, 17))
+    p[:, 0] = rng.uniform(30, 60, B); p[:, 1] = rng.uniform(6.5, 7.5, B); p[:, 2] = rng.uniform(0.5, 0.8, B)
+    p[:, 4] = 7.0; p[:, 5] = 0.6; p[:, 8] = 7.0; p[:, 9] = 0.6
+    p[:, 10] = rng.uniform(5, 12, B); p[:, 11] = 6.8; p[:, 12] = 0.6; p[:, 14] = 6.8; p[:, 15] = 0.6; p[:, 16] = 7.0
+    S, nl, status = ws.smatrix_params(ShapeModel(), torch.tensor(p, device="cuda"))
+    assert int(status.abs().sum()) == 0
+    assert int((nl != lmax + 1).sum()) == 0
+    mod = S.abs()
+    assert float((mod[:, 0, :] - 1).abs().max()) < 1e-9
+    assert float((mod[:, 1, 1:] - 1).abs().max()) < 1e-9
+    assert float(S[:, 1, 0].abs().max()) == 0.0
+
+
+# ------------------------------------------------------------------ general Solver.solve path
+def test_solver_solve_local_rk_case(golden):
+    """restated tests/test_local.py (the RK45 cross-check case) against the reference's own S."""
+    g = golden("test_local")
+    N, a = int(g["N"]), float(g["a"])
+    solver = jitr_b200.Solver(N)
+    sysl = ProjectileTargetSystem(channel_radius=a, lmax=2, mass_target=g["masses"][0], mass_projectile=g["masses"][1], Ztarget=20, Zproj=1)
+    free = solver.free_matrix(a, sysl.l, coupled=False)
+    bb = solver.precompute_boundaries(a)
+    for i in (0, 4, 9):
+        channels, asym = sysl.get_partial_wave_channels(*g["kin"][i])
+        for l in range(3):
+            R, S, u = solver.solve(channels[l], asym[l], local_potential=g["pot"][i], basis_boundary=bb, free_matrix=free[l])
+            assert R.shape == (1, 1) and S.shape == (1, 1) and u.shape == (1,)
+            assert relerr(S[0, 0], g["S"][i, l]) < RTOL_S
+            assert relerr(R[0, 0], g["R"][i, l]) < 1e-9
+            assert relerr(u[0], g["uext"][i, l]) < 1e-9
+
+
+def test_solver_solve_wavefunction(golden):
+    """restated tests/test_wavefunction.py: N = 100, wavefunction=True, u_int(s)."""
+    g = golden("test_wavefunction")
+    N, a = int(g["N"]), float(g["a"])
+    solver = jitr_b200.Solver(N)
+    sysw = ProjectileTargetSystem(channel_radius=a, lmax=10, mass_target=44657.26581995028, mass_projectile=938.271653086152, Ztarget=20, Zproj=1)
+    channels, asym = sysw.get_partial_wave_channels(*g["kin"])
+    for l in (0, 1, 4):
+        R, S, x, u = solver.solve(channels[l], asym[l], wavefunction=True, local_potential=g[f"pot{l}"])
+        assert x.shape == (1, N)
+        assert np.max(np.abs(S - g[f"S{l}"])) < 1e-11
+        assert normerr(x, g[f"x{l}"]) < 1e-9
+        uint = jitr_b200.reactions.Wavefunctions(solver, x, S, u, channels[l]).uint()[0](g["svals"])
+        assert normerr(uint, g[f"uint{l}"]) < 1e-9
+
+
+def test_solver_solve_coupled_config5(golden):
+    """BASELINE config 5 (examples/coupled.py geometry): 3 channels x N = 40/50."""
+    g = golden("config5_coupled")
+    cm = g["coupling"]
+    for N in (40, 50):
+        solver = jitr_b200.Solver(N)
+        sysc = ProjectileTargetSystem(channel_radius=float(g["a"]), lmax=3, Ztarget=20, Zproj=1,
+                                      channel_levels=np.array([0, 2.3, 3.1]), coupling=lambda l: cm)
+        channels, asym = sysc.get_partial_wave_channels(5.0, g["E"], g["mu"], g["k"], g["eta"])
+        for l in range(4):
+            R, S, x, u = solver.solve(channels[l], asym[l], local_potential=g[f"N{N}_l{l}_V"], wavefunction=True)
+            assert relerr(S, g[f"N{N}_l{l}_S"]) < 1e-9 and np.max(np.abs(S - g[f"N{N}_l{l}_S"])) < RTOL_S
+            assert normerr(R, g[f"N{N}_l{l}_R"]) < 1e-9
+            assert normerr(x, g[f"N{N}_l{l}_x"]) < 1e-9
+            assert normerr(u, g[f"N{N}_l{l}_u"]) < 1e-9
+            np.testing.assert_allclose(S.conj().T @ S, np.eye(3), atol=1e-9)  # real potential: unitary
+
+
+def test_solver_solve_coupled_vs_single(golden):
+    """restated tests/test_coupled_single_dwba.py: zero coupling reproduces single-channel solves."""
+    g = golden("test_coupled_single")
+    solver = jitr_b200.Solver(40)
+    sys2 = ProjectileTargetSystem(channel_radius=float(g["a"]), lmax=2, mass_target=44657, mass_projectile=938.3, Ztarget=20, Zproj=1,
+                                  coupling=lambda l: np.array([[1, 0], [0, 1]]))
+    channels, asym = sys2.get_partial_wave_channels(*g["kin"])
+    Rm, Sm, um = solver.solve(channels[0], asym[0], local_potential=g["V2"])
+    ch0, as0 = channels[0].decouple()[0], asym[0].decouple()[0]
+    R1, S1, u1 = solver.solve(ch0, as0, local_potential=g["V1"])
+    np.testing.assert_almost_equal(Sm[1, 0], 0)
+    np.testing.assert_almost_equal(Rm[0, 1], 0)
+    np.testing.assert_almost_equal(Sm[1, 1], S1[0, 0])
+    np.testing.assert_almost_equal(Sm[0, 0], S1[0, 0])
+    np.testing.assert_almost_equal(Rm[0, 0], R1[0, 0])
+    assert np.max(np.abs(Sm - g["Sm"])) < RTOL_S
+    assert relerr(S1, g["S1"]) < RTOL_S
+    with pytest.raises(ValueError):
+        solver.solve(channels[0], asym[0], local_potential=g["V1"])  # 1D potential with 2 channels
+
+
+def test_solver_solve_nonlocal(golden):
+    """nonlocal branch: Yamaguchi (examples/nonlocal.py) and the config-4 Perey-Buck-style kernel."""
+    g = golden("nonlocal_yamaguchi")
+    Elab, Ecm, mu, k, eta = g["kin"]
+    sysn = ProjectileTargetSystem(channel_radius=30.0, lmax=5)
+    channels, asym = sysn.get_partial_wave_channels(Ecm, Ecm, mu, k, eta)
+    for N in (20, 40):
+        solver = jitr_b200.Solver(N)
+        R, S, u = solver.solve(channels[0], asym[0], nonlocal_potential=g[f"yam{N}_V"])
+        assert relerr(S, g[f"yam{N}_S"]) < RTOL_S
+    delta = np.rad2deg(np.real(np.log(S[0, 0]) / 2j))
+    assert abs(delta - (-66.98635852)) < 1e-6
+    g = golden("config4_nonlocal")
+    solver = jitr_b200.Solver(60)
+    sys4 = ProjectileTargetSystem(float(g["a"]), 6, Ztarget=82, Zproj=0)
+    channels, asym = sys4.get_partial_wave_channels(*g["kin"])
+    for l in (0, 3):
+        R, S, u = solver.solve(channels[l], asym[l], nonlocal_potential=g[f"s0_l{l}_U"])
+        assert relerr(S, g[f"s0_l{l}_S"]) < RTOL_S
+    # batched form: the two l = 0 kernels of the two samples in one launch
+    U = torch.tensor(np.stack([g["s0_l0_U"], g["s1_l0_U"]]), dtype=torch.complex128, device="cuda")
+    Elab, Ecm, mu, k, eta = g["kin"]
+    free = torch.tensor(solver.free_matrix(float(g["a"]), [0], [Ecm], [mu]), device="cuda")
+    a0 = asym[0]
+    out = solver.solve_batch(float(g["a"]), Ecm, k, 1, free, torch.tensor(np.stack([a0.Hp, a0.Hm, a0.Hpp, a0.Hmp]), device="cuda"),
+                             nonlocal_potential=U)
+    assert relerr(out["S"][0].cpu().numpy(), g["s0_l0_S"]) < RTOL_S
+    assert relerr(out["S"][1].cpu().numpy(), g["s1_l0_S"]) < RTOL_S
+
+
+def test_singular_system_reports_status():
+    """An all-NaN potential must flag the system instead of crashing or hanging (numba raises LinAlgError)."""
+    rx = ElasticReaction((40, 20), (1, 0), mass_target=37214.7)
+    ws = jitr_b200.IntegralWorkspace(rx, rx.kinematics(10.0), 10.0, jitr_b200.Solver(20), 4)
+    c = torch.full((2, 20), float("nan"), dtype=torch.complex128, device="cuda")
+    c[1] = -40.0
+    S, nl, status = ws.smatrix_batch(c)
+    assert int(status[0]) != _cabi.STATUS_OK and int(status[1]) == _cabi.STATUS_OK
+    with pytest.raises(np.linalg.LinAlgError):
+        ws.smatrix(np.full(20, np.nan, dtype=complex))

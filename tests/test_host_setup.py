@@ -1,0 +1,119 @@
+"""Host-side mirror of the reference interface (setup math, classes, error behaviour) vs golden vectors.  CPU only."""
+import numpy as np
+import pytest
+
+import jitr_b200
+from jitr_b200 import reactions, utils
+from jitr_b200.free_solutions import coulomb_hankel_table
+from jitr_b200.optical_potentials import chuq, kduq
+from jitr_b200.reactions import ElasticReaction, ProjectileTargetSystem
+
+
+def test_kinematics_and_tables(golden):
+    for name in ("config1_n208Pb_30MeV", "config3_p48Ca_30MeV"):
+        g = golden(name)
+        rx = ElasticReaction(tuple(g["target"]), tuple(g["projectile"]), mass_target=g["masses"][0], mass_projectile=g["masses"][1])
+        kin = rx.kinematics(float(g["kin"][0]))
+        np.testing.assert_allclose(list(kin), g["kin"], rtol=1e-15)
+        N, lmax = int(g["N"]), int(g["lmax"])
+        solver = jitr_b200.Solver(N)
+        ws = jitr_b200.DifferentialWorkspace.build_from_system(rx, kin, float(g["Rch"]), solver, lmax, g["angles"])
+        iw = ws.integral_workspace
+        np.testing.assert_allclose(ws.radial_grid(), g["rgrid"], rtol=1e-15)
+        np.testing.assert_allclose(iw.free_matrices[0], g["free0"], rtol=1e-13)
+        np.testing.assert_allclose(iw.free_matrices[3], g["free3"], rtol=1e-13)
+        np.testing.assert_allclose(iw.basis_boundary, g["basis_boundary"], rtol=1e-14)
+        assert np.max(np.abs(iw._asym_table - g["asym"]) / np.abs(g["asym"])) < 1e-13
+        np.testing.assert_allclose(ws.P_l_costheta, g["P"], rtol=1e-15, atol=0)
+        np.testing.assert_allclose(ws.P_1_l_costheta, g["P1"], rtol=1e-15, atol=0)
+        np.testing.assert_allclose(ws.sigma_l, g["sigma_l"], rtol=1e-15)
+        np.testing.assert_allclose(ws.f_c, g["f_c"], rtol=1e-14)
+        if ws.rutherford is not None:
+            np.testing.assert_allclose(ws.rutherford, g["rutherford"], rtol=1e-14)
+        # channel objects keep the reference fields
+        ch = iw.channels[3][1]
+        assert ch.size == 1 and ch.l[0] == 3 and ch.couplings[0, 0] == -4.0
+        assert iw.l_dot_s.shape == (lmax, 2)
+
+
+def test_system_classes(golden):
+    g = golden("config5_coupled")
+    cm = g["coupling"]
+    sysc = ProjectileTargetSystem(
+        channel_radius=float(g["a"]), lmax=3, mass_target=1.0, mass_projectile=1.0, Ztarget=20, Zproj=1,
+        channel_levels=np.array([0, 2.3, 3.1]), coupling=lambda l: cm,
+    )
+    channels, asym = sysc.get_partial_wave_channels(5.0, g["E"], g["mu"], g["k"], g["eta"])
+    for l in range(4):
+        ref = g[f"l{l}_asym"]
+        got = np.array([asym[l].Hp, asym[l].Hm, asym[l].Hpp, asym[l].Hmp])
+        assert np.max(np.abs(got - ref) / np.abs(ref)) < 1e-13
+        assert channels[l].size == 3 and channels[l].num_channels == 3
+    with pytest.raises(AssertionError):
+        reactions.Channels(np.ones(2), np.ones(2), np.ones(2), np.ones(2), 1.0, np.ones(2), np.eye(3))
+
+
+def test_solver_host_helpers_and_errors():
+    s = jitr_b200.Solver(12)
+    F = s.free_matrix(7.0, [0, 2], E=[5.0, 3.0], mu=[900.0, 910.0])
+    assert F.shape == (24, 24)
+    np.testing.assert_allclose(s.get_channel_block(F, 0, 1), 0)
+    np.testing.assert_allclose(s.get_channel_block(F, 1), s.kernel.quadrature.kinetic_matrix(7.0, 2) * 900.0 / 910.0 - np.eye(12) * 3.0 / 5.0)
+    # element-wise definition agrees with the vectorised That
+    q = s.kernel.quadrature
+    T = q.kinetic_matrix(7.0, 2)
+    for n, m in ((1, 1), (2, 5), (12, 3)):
+        assert abs(T[n - 1, m - 1] - q.kinetic_operator_element(n, m, 7.0, 2)) < 1e-12 * abs(T[n - 1, m - 1])
+    with pytest.raises(ValueError):
+        s.interaction_matrix(1.0, 1.0, 7.0, 2, local_potential=np.zeros(12))
+    with pytest.raises(ValueError):
+        s.interaction_matrix(1.0, 1.0, 7.0, 1, local_potential=np.zeros(11))
+    with pytest.raises(ValueError):
+        s.interaction_matrix(1.0, 1.0, 7.0, 1, nonlocal_potential=np.zeros((12, 11)))
+    with pytest.raises(NotImplementedError):
+        jitr_b200.Solver(10, "Laguerre")
+    with pytest.raises(ValueError):
+        jitr_b200.xs.elastic.check_angles(np.array([[0.1, 0.2]]))
+    with pytest.raises(ValueError):
+        jitr_b200.IntegralWorkspace(reactions.Reaction((40, 20), (1, 0), process="abs"), None, 10.0, s, 3)
+
+
+def test_interaction_matrix_matches_oracle():
+    from oracle import jitr_oracle as orc
+
+    s = jitr_b200.Solver(10)
+    rng = np.random.default_rng(1)
+    loc = rng.standard_normal((2, 2, 10)) + 1j * rng.standard_normal((2, 2, 10))
+    nl = rng.standard_normal((2, 2, 10, 10)) + 1j * rng.standard_normal((2, 2, 10, 10))
+    got = s.interaction_matrix(1.3, 12.0, 9.0, 2, local_potential=loc, nonlocal_potential=nl)
+    ref = orc.interaction_matrix(10, 1.3, 12.0, 9.0, 2, loc, nl)
+    np.testing.assert_allclose(got, ref, rtol=1e-14)
+
+
+def test_param_vectors(golden):
+    g = golden("kduq_params")
+    np.testing.assert_array_equal(kduq.get_kd03((1, 0)), g["kd03_n"])
+    np.testing.assert_array_equal(kduq.get_kd03((1, 1)), g["kd03_p"])
+    assert kduq.get_param_names((1, 0)) == list(g["names_n"])
+    assert kduq.get_param_names((1, 1)) == list(g["names_p"])
+    c = golden("chuq_params")
+    np.testing.assert_array_equal(chuq.get_ch89(), c["ch89"])
+    assert chuq.get_param_names() == list(c["names"])
+    with pytest.raises(RuntimeError):
+        kduq.KDUQ((4, 2))
+
+
+def test_neutral_asymptotics_closed_form_matches_mpmath():
+    from oracle import jitr_oracle as orc
+
+    for a in (3.3, 14.481215395437799, 31.4):
+        tab = coulomb_hankel_table(12, 0.0, a)
+        ref = np.array([orc.coulomb_hankel(l, 0.0, a) for l in range(13)])
+        assert np.max(np.abs(tab - ref) / np.abs(ref)) < 5e-13
+
+
+def test_utils():
+    assert utils.suggested_basis_size(10 * np.pi) == 50
+    assert abs(utils.interaction_range(208) - 1.2 * 208 ** (1 / 3)) < 1e-15
+    k = utils.classical_kinematics(44657.0, 938.3, 42.1, 20)
+    assert abs(k.Ecm - 44657.0 / (44657.0 + 938.3) * 42.1) < 1e-12
