@@ -2,8 +2,7 @@
 
     python -m jitr_b200._build [--force]
 
-The fused sweep kernel is fully unrolled per nbasis, so each size is its own translation unit
-(sweep_inst.cu compiled with -DJITR_SWEEP_N=<N>) and all units are compiled in parallel.
+All translation units are compiled in parallel; objects are cached by content hash.
 """
 from __future__ import annotations
 
@@ -29,17 +28,8 @@ FLAGS = [
 ]
 
 
-def sweep_sizes():
-    txt = open(os.path.join(CSRC, "common.cuh")).read()
-    m = re.search(r"#define JITR_SWEEP_SIZES\(X\)(.*)", txt)
-    return [int(v) for v in re.findall(r"X\((\d+)\)", m.group(1))]
-
-
 def _units():
-    units = [(name, os.path.join(CSRC, name + ".cu"), []) for name in ("api", "probe", "elastic", "general")]
-    for n in sweep_sizes():
-        units.append((f"sweep_{n}", os.path.join(CSRC, "sweep_inst.cu"), [f"-DJITR_SWEEP_N={n}"]))
-    return units
+    return [(name, os.path.join(CSRC, name + ".cu"), []) for name in ("api", "probe", "elastic", "general")]
 
 
 def _deps(src, seen=None):
@@ -96,7 +86,7 @@ def build(force=False, verbose=True):
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
     if verbose:
-        print(f"[jitr_b200] built {LIB} ({sum(c for _, c in res)} units recompiled, sizes={sweep_sizes()})")
+        print(f"[jitr_b200] built {LIB} ({sum(c for _, c in res)} units recompiled)")
     return LIB
 
 

@@ -9,7 +9,7 @@
 #include "jitr_b200.h"
 #include "lu_warp.cuh"
 #include "potentials.cuh"
-#include "sweep_decl.cuh"
+#include "elastic_sweep.cuh"
 
 namespace jitr {
 
@@ -142,19 +142,6 @@ __global__ void eval_potentials_kernel(int N, int model, long long n_pairs, int 
     coulomb[idx] = co;
 }
 
-template <bool PARAMS>
-static int dispatch_sweep(int nbasis, const SweepArgs& a, cudaStream_t st) {
-    switch (nbasis) {
-#define JITR_CASE(NN) \
-    case NN:          \
-        return launch_sweep<NN, PARAMS>(a, st);
-        JITR_SWEEP_SIZES(JITR_CASE)
-#undef JITR_CASE
-        default:
-            return set_error(JITR_B200_ERR_UNSUPPORTED, "elastic sweep: nbasis not in the compiled set");
-    }
-}
-
 }  // namespace jitr
 
 using namespace jitr;
@@ -177,7 +164,8 @@ extern "C" int jitr_b200_elastic_sweep_params(int nbasis, int lmax, int model, l
     a.asym = reinterpret_cast<const double2*>(asym);
     a.params = params; a.tol = tol;
     a.S_out = reinterpret_cast<double2*>(S_out); a.nl_out = nl_out; a.status = status;
-    return dispatch_sweep<true>(nbasis, a, static_cast<cudaStream_t>(stream));
+    a.N = nbasis;
+    return launch_sweep<true>(a, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int jitr_b200_elastic_sweep_tensors(int nbasis, int lmax, long long n_samples, int n_energies,
@@ -198,7 +186,8 @@ extern "C" int jitr_b200_elastic_sweep_tensors(int nbasis, int lmax, long long n
     a.coulomb = reinterpret_cast<const double2*>(coulomb);
     a.tol = tol;
     a.S_out = reinterpret_cast<double2*>(S_out); a.nl_out = nl_out; a.status = status;
-    return dispatch_sweep<false>(nbasis, a, static_cast<cudaStream_t>(stream));
+    a.N = nbasis;
+    return launch_sweep<false>(a, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int jitr_b200_elastic_observables(int lmax, int n_angles, long long n_samples, int n_energies,

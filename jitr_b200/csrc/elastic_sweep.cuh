@@ -1,7 +1,7 @@
-// Fused spin-1/2 elastic sweep kernel (template on nbasis); instantiated per N in sweep_inst.cu.
+// Fused spin-1/2 elastic sweep kernel:
 // potential evaluation -> system assembly -> bordered LU -> R -> S, one WARP per (sample, energy)
 // pair walking l = 0..lmax, j = l +- 1/2 with the reference's data-dependent early break
-// (xs/elastic.py:104-183).
+// (xs/elastic.py:104-183).  nbasis is a runtime value (<= 63: at most two row slots per lane).
 #pragma once
 #include <cuda_runtime.h>
 #include <math.h>
@@ -14,27 +14,40 @@
 
 namespace jitr {
 
-template <int N>
-struct SweepCfg {
-    static constexpr int MSZ = (N + 1) * (N + 1);  // double2 elements of one bordered system
-    static constexpr int MAXS = 232448;            // max dynamic shared memory per block on sm_100
-    static constexpr int WFIT = (MAXS - N * N * 8) / (MSZ * 16);
-    static constexpr int WARPS = WFIT > 8 ? 8 : WFIT;
-    static constexpr int SMEM = WARPS * MSZ * 16 + N * N * 8;
-    static_assert(WARPS >= 1, "system does not fit in shared memory");
+constexpr int kSweepMaxSmem = 232448;  // max dynamic shared memory per block on sm_100
+constexpr int kSweepMaxWarps = 8;
+
+// shared-memory plan for a given nbasis: `warps` bordered systems of (P+1)^2 complex + That (N^2 real)
+struct SweepPlan {
+    int P, LD, msz, warps, smem;
 };
+inline SweepPlan sweep_plan(int N) {
+    SweepPlan p;
+    p.P = (N + 7) & ~7;
+    p.LD = p.P + 1;
+    p.msz = p.LD * p.LD;
+    const int fit = (kSweepMaxSmem - N * N * 8) / (p.msz * 16);
+    p.warps = fit > kSweepMaxWarps ? kSweepMaxWarps : fit;
+    p.smem = p.warps * p.msz * 16 + N * N * 8;
+    return p;
+}
 
 // PARAMS: built-in potential forms from parameter rows; otherwise mesh values from tensors.
-template <int N, bool PARAMS>
-__global__ void __launch_bounds__(SweepCfg<N>::WARPS * 32, 1) elastic_sweep_kernel(const SweepArgs A) {
-    using Cfg = SweepCfg<N>;
-    constexpr int LD = N + 1;
+template <bool PARAMS>
+__global__ void __launch_bounds__(kSweepMaxWarps * 32, 1) elastic_sweep_kernel(const SweepArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int N = A.N;
+    LuGeom g;
+    g.N = N;
+    g.P = (N + 7) & ~7;
+    g.LD = g.P + 1;
+    const int P = g.P, LD = g.LD, msz = LD * LD;
+    const int nwarps = blockDim.x >> 5;
     double2* Mall = reinterpret_cast<double2*>(smem_raw);
-    double* Ts = reinterpret_cast<double*>(smem_raw + (size_t)Cfg::WARPS * Cfg::MSZ * 16);
+    double* Ts = reinterpret_cast<double*>(smem_raw + (size_t)nwarps * msz * 16);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double2* M = Mall + (size_t)warp * Cfg::MSZ;
+    double2* M = Mall + (size_t)warp * msz;
 
     for (int i = threadIdx.x; i < N * N; i += blockDim.x) Ts[i] = A.That[i];
     __syncthreads();
@@ -48,9 +61,10 @@ __global__ void __launch_bounds__(SweepCfg<N>::WARPS * 32, 1) elastic_sweep_kern
     const double t0 = Ts[(v0 ? n0 : 0) * (N + 1)], t1 = Ts[(v1 ? n1 : 0) * (N + 1)];
     const double cent0 = 1.0 / (x0 * x0), cent1 = 1.0 / (x1 * x1);
     const int L1 = A.lmax + 1;
+    const double2 zero2 = make_double2(0.0, 0.0);
 
-    for (long long pair = (long long)blockIdx.x * Cfg::WARPS + warp; pair < A.n_pairs;
-         pair += (long long)gridDim.x * Cfg::WARPS) {
+    for (long long pair = (long long)blockIdx.x * nwarps + warp; pair < A.n_pairs;
+         pair += (long long)gridDim.x * nwarps) {
         const long long smp = pair / A.n_energies;
         const int e = (int)(pair - smp * A.n_energies);
         const double* et = A.etab + (size_t)e * JITR_B200_ET_STRIDE;
@@ -70,7 +84,7 @@ __global__ void __launch_bounds__(SweepCfg<N>::WARPS * 32, 1) elastic_sweep_kern
             const size_t off = (size_t)pair * N;
             vc0 = A.central[off + (v0 ? n0 : 0)];
             vc1 = A.central[off + (v1 ? n1 : 0)];
-            vs0 = vs1 = make_double2(0.0, 0.0);
+            vs0 = vs1 = zero2;
             if (A.spin_orbit) {
                 vs0 = A.spin_orbit[off + (v0 ? n0 : 0)];
                 vs1 = A.spin_orbit[off + (v1 ? n1 : 0)];
@@ -95,31 +109,35 @@ __global__ void __launch_bounds__(SweepCfg<N>::WARPS * 32, 1) elastic_sweep_kern
             const double2* as = A.asym + ((size_t)e * L1 + l) * 4;
             const double2 Hp = as[0], Hm = as[1], Hpp = as[2], Hmp = as[3];
             double2 Sj[2];
-            Sj[1] = make_double2(0.0, 0.0);
+            Sj[1] = zero2;
             const int nj = (l == 0) ? 1 : 2;
             for (int jj = 0; jj < nj; ++jj) {
                 const double ls = (jj == 0) ? (double)l : -(double)(l + 1);
-                // ---- assemble the bordered matrix  [[That + diag, b], [b^T, 0]]
-#pragma unroll 5
-                for (int idx = lane; idx < N * N; idx += 32) {  // copy of the real kinetic matrix
-                    const int i = idx / N, j = idx - i * N;
-                    M[i * LD + j] = make_double2(Ts[idx], 0.0);
+                // ---- assemble the bordered matrix  [[That + diag, 0, b], [0, 0, 0], [b^T, 0, 0]]
+                for (int i = 0; i < N; ++i) {
+                    const double* Trow = Ts + i * N;
+                    double2* Mrow = M + i * LD;
+                    if (lane < P) Mrow[lane] = make_double2(v0 ? Trow[n0] : 0.0, 0.0);
+                    if (n1 < P) Mrow[n1] = make_double2(v1 ? Trow[n1] : 0.0, 0.0);
+                }
+                for (int i = N; i < P; ++i) {  // zero padding rows
+                    for (int j = lane; j < LD; j += 32) M[i * LD + j] = zero2;
                 }
                 __syncwarp();
                 if (v0) {
                     M[n0 * LD + n0] = make_double2(d0.x + ll1 * cent0 + ls * so0.x, d0.y + ls * so0.y);
-                    M[n0 * LD + N] = make_double2(b0, 0.0);
-                    M[N * LD + n0] = make_double2(b0, 0.0);
+                    M[n0 * LD + P] = make_double2(b0, 0.0);
+                    M[P * LD + n0] = make_double2(b0, 0.0);
                 }
                 if (v1) {
                     M[n1 * LD + n1] = make_double2(d1.x + ll1 * cent1 + ls * so1.x, d1.y + ls * so1.y);
-                    M[n1 * LD + N] = make_double2(b1, 0.0);
-                    M[N * LD + n1] = make_double2(b1, 0.0);
+                    M[n1 * LD + P] = make_double2(b1, 0.0);
+                    M[P * LD + n1] = make_double2(b1, 0.0);
                 }
-                if (lane == 0) M[N * LD + N] = make_double2(0.0, 0.0);
+                for (int j = N + lane; j <= P; j += 32) M[P * LD + j] = zero2;  // z row: padding + corner
                 __syncwarp();
                 // ---- factorise; corner = -b^T (a^2 A)^-1 b = -R
-                const double2 corner = bordered_schur<N>(M, lane, singular);
+                const double2 corner = bordered_schur(M, g, lane, singular);
                 __syncwarp();
                 const double2 aR = make_double2(-a * corner.x, -a * corner.y);
                 // S = (H- - a R H-') / (H+ - a R H+')   (rmatrix/core.py:51-56 with nch = 1)
@@ -141,8 +159,8 @@ __global__ void __launch_bounds__(SweepCfg<N>::WARPS * 32, 1) elastic_sweep_kern
             }
         }
         for (int l = nl + lane; l <= A.lmax; l += 32) {
-            Sp_out[l] = make_double2(0.0, 0.0);
-            Sm_out[l] = make_double2(0.0, 0.0);
+            Sp_out[l] = zero2;
+            Sm_out[l] = zero2;
         }
         if (lane == 0) {
             A.nl_out[pair] = nl;
@@ -151,25 +169,26 @@ __global__ void __launch_bounds__(SweepCfg<N>::WARPS * 32, 1) elastic_sweep_kern
     }
 }
 
-template <int N, bool PARAMS>
+template <bool PARAMS>
 int launch_sweep(const SweepArgs& a, cudaStream_t st) {
-    using Cfg = SweepCfg<N>;
-    auto kern = elastic_sweep_kernel<N, PARAMS>;
-    static bool configured = false;
-    if (!configured) {
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM) != cudaSuccess)
+    if (a.N < 1 || a.N > 63) return set_error(JITR_B200_ERR_UNSUPPORTED, "elastic sweep: nbasis must be in 1..63");
+    const SweepPlan plan = sweep_plan(a.N);
+    if (plan.warps < 1) return set_error(JITR_B200_ERR_UNSUPPORTED, "elastic sweep: system does not fit in shared memory");
+    auto kern = elastic_sweep_kernel<PARAMS>;
+    static int configured = 0;
+    if (plan.smem > configured) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem) != cudaSuccess)
             return set_cuda_error("cudaFuncSetAttribute(elastic_sweep)");
-        configured = true;
+        configured = plan.smem;
     }
     const int sms = sm_count();
-    long long blocks = (a.n_pairs + Cfg::WARPS - 1) / Cfg::WARPS;
+    long long blocks = (a.n_pairs + plan.warps - 1) / plan.warps;
     if (blocks > sms) blocks = sms;
     if (blocks < 1) return JITR_B200_OK;
-    kern<<<(unsigned)blocks, Cfg::WARPS * 32, Cfg::SMEM, st>>>(a);
+    kern<<<(unsigned)blocks, plan.warps * 32, plan.smem, st>>>(a);
     count_launch();
     if (cudaGetLastError() != cudaSuccess) return set_cuda_error("elastic_sweep launch");
     return JITR_B200_OK;
 }
-
 
 }  // namespace jitr

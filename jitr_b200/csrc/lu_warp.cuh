@@ -1,25 +1,29 @@
 // Warp-per-system blocked LU (complex128, partial pivoting) of the BORDERED matrix
 //
-//        M = [ A   b ]      (N+1) x (N+1), stored row-major in shared memory with LD = N+1
-//            [ b^T 0 ]
+//        M = [ A   0  b ]     rows 0..N-1   : the system (N = nbasis)
+//            [ 0   0  0 ]     rows N..P-1   : zero padding up to P = 8*ceil(N/8)
+//            [ b^T 0  0 ]     row  P        : the "z" row
 //
-// eliminated on its first N columns with the pivot search restricted to the first N rows; the
-// corner that is left is the Schur complement  -b^T A^-1 b , i.e. minus the (scaled) R-matrix
-// (rmatrix/core.py:7-22 computes the same number through the explicit inverse).  Nothing of L or
-// U is needed afterwards, so no triangular back-substitution is run.
+// stored row-major in shared memory with leading dimension LD = P + 1 (odd: a column walk by the 32
+// lanes is bank-conflict free), column P holding the right-hand side.  The first N columns are
+// eliminated with the pivot search restricted to the first N rows; the corner M[P][P] that is left
+// is the Schur complement  -b^T A^-1 b , i.e. minus the (scaled) R-matrix that rmatrix/core.py:7-22
+// obtains through the explicit inverse.  Neither L nor U is needed afterwards: no back-substitution.
 //
-// One warp owns one system.  Right-looking, panel width NB = 8, three phases per panel:
-//   P  panel factorisation with the panel held in REGISTERS, one matrix row per lane (two row
-//      slots while more than 32 rows are alive): pivot search = REDUX.MAX on the high word of
-//      |a|^2 + ballot, pivot-row broadcast = shuffles, rank-1 updates = DFMA on registers.
-//      Column N (the right-hand side y) rides along as a ninth panel column, row N (z = U^-T b)
-//      as one more row that is never a pivot candidate.  Row interchanges of the trailing columns
-//      are done in shared memory as soon as the pivot is known (lane c always owns column c, so no
-//      barrier is needed and the LDS/STS latency hides under the register updates).
-//   U  U12 = L11^-1 A12: lane c owns trailing column c and runs the 8-step forward substitution
-//      in registers (L11 read as shared-memory broadcasts); the z row is updated here too.
-//   T  A22 -= L21 U12 with 4x4 complex register tiles per lane (8 row groups x 4 column groups,
-//      cyclic, conflict-free for the odd leading dimension LD = N+1).
+// One warp owns one system; right-looking, panel width 8, three phases per panel.  The code is a
+// RUNTIME loop over panels with nbasis a runtime value: the first version of this file unrolled every
+// panel at compile time and ran instruction-fetch bound (400 KB of SASS, I-cache hit rate 38 %, ncu
+// profiles/r01_v1_*); this one is ~1.5k instructions and serves every nbasis <= 60.
+//   P  panel factorisation with the panel in REGISTERS, one matrix row per lane (two row slots while
+//      more than 32 rows are alive): pivot search = REDUX.MAX on the high word of |a|^2 + ballot,
+//      pivot-row broadcast = shuffles, rank-1 updates = DFMA on registers.  Column P (the RHS y) rides
+//      along as a ninth panel column, row P (z = U^-T b) as one more row that is never a pivot
+//      candidate.  Row interchanges of the trailing columns are done in shared memory as soon as the
+//      pivot is known (lane c always owns column c, so no barrier is needed).
+//   U  U12 = L11^-1 A12: lane c owns trailing column c, 8-step forward substitution in registers
+//      (L11 read as shared-memory broadcasts); the z row is updated here too.
+//   T  A22 -= L21 U12 on the FP64 tensor-core path: 8x8 complex tiles, K = 8 = two m8n8k4 DMMA steps,
+//      four real DMMAs per complex step; a warp register-blocks 1x2 tiles.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -45,204 +49,211 @@ __device__ __forceinline__ double2 cdiv(double2 n, double2 d) { return cmul(n, c
 __device__ __forceinline__ double2 shfl2(double2 v, int src) {
     return make_double2(__shfl_sync(kFull, v.x, src), __shfl_sync(kFull, v.y, src));
 }
+__device__ __forceinline__ double dneg(double x) {
+    return __hiloint2double(__double2hiint(x) ^ 0x80000000, __double2loint(x));
+}
+// D(8x8) += A(8x4, row) * B(4x8, col): a = A[lane/4][lane%4], b = B[lane%4][lane/4], c{0,1} = C[lane/4][2(lane%4)+{0,1}]
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
 
-// ---- phase T ------------------------------------------------------------------------------------
-template <int N, int J0, int NBc, int RB, int CB>
-__device__ __forceinline__ void trailing_update(double2* __restrict__ M, int lane) {
-    constexpr int LD = N + 1;
-    constexpr int MT = N - J0 - NBc;
-    constexpr int R0 = J0 + NBc;
-    constexpr int TI = (MT + 7) / 8;
-    constexpr int TJ = (MT + 3) / 4;
-    const int rg = lane & 7, cg = lane >> 3;
-#pragma unroll
-    for (int tj0 = 0; tj0 < TJ; tj0 += CB) {
-#pragma unroll
-        for (int ti0 = 0; ti0 < TI; ti0 += RB) {
-            int rowoff[RB], coloff[CB];
-            bool rok[RB], cok[CB];
-#pragma unroll
-            for (int ti = 0; ti < RB; ++ti) {
-                const int r = rg + 8 * (ti0 + ti);
-                rok[ti] = (8 * (ti0 + ti) + 7 < MT) || (r < MT);
-                rowoff[ti] = (R0 + (rok[ti] ? r : 0)) * LD;
+struct LuGeom {
+    int N;    // nbasis (real rows/columns)
+    int P;    // N rounded up to a multiple of 8; z row = row P, rhs column = column P
+    int LD;   // P + 1
+};
+
+// ---- phase T: A22 -= L21 * U12, 8x8 complex tiles on DMMA --------------------------------------------
+__device__ __forceinline__ void trailing_update_dmma(double2* __restrict__ M, const LuGeom g, int J0, int lane) {
+    const int R0 = J0 + 8;
+    const int nt = (g.P - R0) >> 3;  // tiles per dimension
+    const int LD = g.LD;
+    const int fr = lane >> 2, fk = lane & 3;
+    for (int tr = 0; tr < nt; ++tr) {
+        // A fragments of this tile row (both k-steps): -L and the sign-flipped parts, kept in registers
+        const int arow = (R0 + 8 * tr + fr) * LD + J0 + fk;
+        const double2 l0 = M[arow], l1 = M[arow + 4];
+        const double nl0x = dneg(l0.x), nl0y = dneg(l0.y), nl1x = dneg(l1.x), nl1y = dneg(l1.y);
+        for (int tc = 0; tc < nt; tc += 2) {
+            const bool two = tc + 1 < nt;  // warp-uniform
+            const int bcol = R0 + 8 * tc + fr;
+            const int brow = (J0 + fk) * LD;
+            const double2 u0 = M[brow + bcol], u1 = M[brow + 4 * LD + bcol];
+            const int crow = (R0 + 8 * tr + fr) * LD + R0 + 8 * tc + 2 * fk;
+            double2 ca = M[crow], cb = M[crow + 1];
+            // C_re += (-Lre) Ure + (Lim) Uim ;  C_im += (-Lre) Uim + (-Lim) Ure
+            dmma884(ca.x, cb.x, nl0x, u0.x);
+            dmma884(ca.y, cb.y, nl0x, u0.y);
+            dmma884(ca.x, cb.x, l0.y, u0.y);
+            dmma884(ca.y, cb.y, nl0y, u0.x);
+            dmma884(ca.x, cb.x, nl1x, u1.x);
+            dmma884(ca.y, cb.y, nl1x, u1.y);
+            dmma884(ca.x, cb.x, l1.y, u1.y);
+            dmma884(ca.y, cb.y, nl1y, u1.x);
+            M[crow] = ca;
+            M[crow + 1] = cb;
+            if (two) {
+                const double2 v0 = M[brow + bcol + 8], v1 = M[brow + 4 * LD + bcol + 8];
+                double2 cc = M[crow + 8], cd = M[crow + 9];
+                dmma884(cc.x, cd.x, nl0x, v0.x);
+                dmma884(cc.y, cd.y, nl0x, v0.y);
+                dmma884(cc.x, cd.x, l0.y, v0.y);
+                dmma884(cc.y, cd.y, nl0y, v0.x);
+                dmma884(cc.x, cd.x, nl1x, v1.x);
+                dmma884(cc.y, cd.y, nl1x, v1.y);
+                dmma884(cc.x, cd.x, l1.y, v1.y);
+                dmma884(cc.y, cd.y, nl1y, v1.x);
+                M[crow + 8] = cc;
+                M[crow + 9] = cd;
             }
-#pragma unroll
-            for (int tj = 0; tj < CB; ++tj) {
-                const int c = cg + 4 * (tj0 + tj);
-                cok[tj] = (4 * (tj0 + tj) + 3 < MT) || (c < MT);
-                coloff[tj] = R0 + (cok[tj] ? c : 0);
-            }
-            double2 acc[RB][CB];
-#pragma unroll
-            for (int ti = 0; ti < RB; ++ti)
-#pragma unroll
-                for (int tj = 0; tj < CB; ++tj)
-                    if (ti0 + ti < TI && tj0 + tj < TJ) acc[ti][tj] = M[rowoff[ti] + coloff[tj]];
-#pragma unroll
-            for (int k = 0; k < NBc; ++k) {
-                double2 l[RB], u[CB];
-#pragma unroll
-                for (int ti = 0; ti < RB; ++ti)
-                    if (ti0 + ti < TI) l[ti] = M[rowoff[ti] + J0 + k];
-#pragma unroll
-                for (int tj = 0; tj < CB; ++tj)
-                    if (tj0 + tj < TJ) u[tj] = M[(J0 + k) * LD + coloff[tj]];
-#pragma unroll
-                for (int ti = 0; ti < RB; ++ti)
-#pragma unroll
-                    for (int tj = 0; tj < CB; ++tj)
-                        if (ti0 + ti < TI && tj0 + tj < TJ) cfnma(acc[ti][tj], l[ti], u[tj]);
-            }
-#pragma unroll
-            for (int ti = 0; ti < RB; ++ti)
-#pragma unroll
-                for (int tj = 0; tj < CB; ++tj)
-                    if (ti0 + ti < TI && tj0 + tj < TJ && rok[ti] && cok[tj]) M[rowoff[ti] + coloff[tj]] = acc[ti][tj];
         }
     }
 }
 
-// ---- one panel stage (phases P, U, T), recursing on J0 -------------------------------------------
-template <int N, int J0>
-struct Stage {
-    static constexpr int LD = N + 1;
-    static constexpr int NBc = (N - J0 < 8) ? (N - J0) : 8;
-    static constexpr int ROWS = N - J0 + 1;  // rows J0..N (row N is the z row)
-    static constexpr int SLOTS = (ROWS + 31) / 32;
-    static constexpr int MT = N - J0 - NBc;
-    static constexpr int R0 = J0 + NBc;
-    static_assert(SLOTS <= 2, "warp LU supports N <= 63");
-
-    __device__ __forceinline__ static void run(double2* __restrict__ M, int lane, int& singular, double2& corner) {
+// ---- the whole factorisation; returns the corner -b^T A^-1 b to every lane ---------------------------
+__device__ __forceinline__ double2 bordered_schur(double2* __restrict__ M, const LuGeom g, int lane, int& singular) {
+    const int N = g.N, P = g.P, LD = g.LD;
+    double2 corner = make_double2(0.0, 0.0);
+    for (int J0 = 0; J0 < N; J0 += 8) {
+        const int nreal = N - J0;              // real rows still alive (before this panel)
+        const int nb = nreal < 8 ? nreal : 8;  // panel width
+        const int rows = nreal + 1;            // + z row
+        const bool two = rows > 32;            // warp-uniform: second row slot in use
+        const int MTr = N - J0 - 8;            // real trailing columns (<= 0 on the last panel)
+        const int R0 = J0 + 8;
         // ------------------------------------------------------------------ phase P
-        double2 p[SLOTS][NBc + 1];
-        int pos[SLOTS];
-        bool alive[SLOTS], valid[SLOTS], cand[SLOTS];
+        double2 p[2][9];
+        int pos[2];
+        bool alive[2], cand[2], valid[2];
 #pragma unroll
-        for (int s = 0; s < SLOTS; ++s) {
-            const int row = J0 + 32 * s + lane;
-            valid[s] = (32 * s + 31 < ROWS) || (row <= N);
+        for (int s = 0; s < 2; ++s) {
+            const int i = 32 * s + lane;
+            valid[s] = i < rows;
+            cand[s] = i < nreal;
             alive[s] = valid[s];
-            cand[s] = valid[s] && (row != N);
-            pos[s] = row;
-            const int base = (valid[s] ? row : J0) * LD;
+            pos[s] = cand[s] ? J0 + i : P;  // the z row sits at row P
+            if (s == 0 || two) {
+                const int base = (valid[s] ? pos[s] : J0) * LD;
 #pragma unroll
-            for (int j = 0; j < NBc; ++j) p[s][j] = M[base + J0 + j];
-            p[s][NBc] = M[base + N];
+                for (int j = 0; j < 8; ++j) p[s][j] = M[base + J0 + j];
+                p[s][8] = M[base + P];
+            } else {
+#pragma unroll
+                for (int j = 0; j < 9; ++j) p[s][j] = make_double2(0.0, 0.0);
+            }
         }
 #pragma unroll
-        for (int kk = 0; kk < NBc; ++kk) {
-            double best = -1.0;
-            int bs = 0;
-#pragma unroll
-            for (int s = 0; s < SLOTS; ++s) {
-                const double m = fma(p[s][kk].x, p[s][kk].x, p[s][kk].y * p[s][kk].y);
-                if (cand[s] && alive[s] && m > best) {
-                    best = m;
-                    bs = s;
+        for (int kk = 0; kk < 8; ++kk) {
+            if (kk < nb) {  // warp-uniform
+                double best = -1.0;
+                int bs = 0;
+                {
+                    const double m = fma(p[0][kk].x, p[0][kk].x, p[0][kk].y * p[0][kk].y);
+                    if (cand[0] && alive[0] && m > best) best = m;
                 }
-            }
-            const int key = __double2hiint(best);
-            const int kmax = __reduce_max_sync(kFull, key);
-            const unsigned ball = __ballot_sync(kFull, key == kmax);
-            const int pl = __ffs(ball) - 1;
-            if (kmax <= 0) singular = 1;  // |pivot|^2 is zero/denormal (or no candidate)
-            const int ps = (SLOTS > 1) ? __shfl_sync(kFull, bs, pl) : 0;
-            double2 u[NBc + 1];
+                if (two) {
+                    const double m = fma(p[1][kk].x, p[1][kk].x, p[1][kk].y * p[1][kk].y);
+                    if (cand[1] && alive[1] && m > best) {
+                        best = m;
+                        bs = 1;
+                    }
+                }
+                const int key = __double2hiint(best);
+                const int kmax = __reduce_max_sync(kFull, key);
+                const unsigned ball = __ballot_sync(kFull, key == kmax);
+                const int pl = __ffs(ball) - 1;
+                if (kmax <= 0) singular = 1;  // |pivot|^2 is zero/denormal (or no candidate)
+                const int ps = two ? __shfl_sync(kFull, bs, pl) : 0;
+                double2 u[9];
 #pragma unroll
-            for (int j = kk; j <= NBc; ++j) {
-                double2 src = p[0][j];
-                if (SLOTS > 1 && ps) src = p[SLOTS - 1][j];
-                u[j] = shfl2(src, pl);
-            }
-            int mypos = pos[0];
-            if (SLOTS > 1 && ps) mypos = pos[SLOTS - 1];
-            const int pp = __shfl_sync(kFull, mypos, pl);
-            const int target = J0 + kk;
-            if (MT > 0 && pp != target) {  // warp-uniform: interchange rows `target` and `pp` in the trailing columns
-#pragma unroll
-                for (int c0 = 0; c0 < MT; c0 += 32) {
-                    const int c = c0 + lane;
-                    if ((c0 + 31 < MT) || (c < MT)) {
+                for (int j = kk; j < 9; ++j) {
+                    double2 src = p[0][j];
+                    if (ps) src = p[1][j];
+                    u[j] = shfl2(src, pl);
+                }
+                const int pp = __shfl_sync(kFull, ps ? pos[1] : pos[0], pl);
+                const int target = J0 + kk;
+                if (MTr > 0 && pp != target) {  // interchange rows `target` and `pp` in the trailing columns
+                    for (int c = lane; c < MTr; c += 32) {
                         const double2 t1 = M[target * LD + R0 + c];
                         const double2 t2 = M[pp * LD + R0 + c];
                         M[target * LD + R0 + c] = t2;
                         M[pp * LD + R0 + c] = t1;
                     }
                 }
-            }
 #pragma unroll
-            for (int s = 0; s < SLOTS; ++s)
-                if (pos[s] == target) pos[s] = pp;
-#pragma unroll
-            for (int s = 0; s < SLOTS; ++s)
-                if (lane == pl && s == ps) {
-                    pos[s] = target;
-                    alive[s] = false;
+                for (int s = 0; s < 2; ++s)
+                    if (pos[s] == target) pos[s] = pp;
+                if (lane == pl) {
+                    if (ps) { pos[1] = target; alive[1] = false; }
+                    else    { pos[0] = target; alive[0] = false; }
                 }
-            const double2 rinv = crecip(u[kk]);
+                const double2 rinv = crecip(u[kk]);
+                {
+                    double2 l = make_double2(0.0, 0.0);
+                    if (alive[0]) {
+                        l = cmul(p[0][kk], rinv);
+                        p[0][kk] = l;
+                    }
 #pragma unroll
-            for (int s = 0; s < SLOTS; ++s) {
-                double2 l = make_double2(0.0, 0.0);
-                if (alive[s]) {
-                    l = cmul(p[s][kk], rinv);
-                    p[s][kk] = l;
+                    for (int j = kk + 1; j < 9; ++j) cfnma(p[0][j], l, u[j]);
                 }
+                if (two) {
+                    double2 l = make_double2(0.0, 0.0);
+                    if (alive[1]) {
+                        l = cmul(p[1][kk], rinv);
+                        p[1][kk] = l;
+                    }
 #pragma unroll
-                for (int j = kk + 1; j <= NBc; ++j) cfnma(p[s][j], l, u[j]);
+                    for (int j = kk + 1; j < 9; ++j) cfnma(p[1][j], l, u[j]);
+                }
             }
         }
-        if constexpr (MT == 0) {
-            // last panel: the z row (row N) now holds the corner in its y slot
-            constexpr int zl = (N - J0) % 32, zs = (N - J0) / 32;
-            corner = shfl2(p[zs][NBc], zl);
-        } else {
+        if (MTr <= 0) {
+            // last panel: the z row now holds the corner in its y slot
+            const int zl = nreal & 31, zs = nreal >> 5;
+            corner = shfl2(zs ? p[1][8] : p[0][8], zl);
+            break;
+        }
+        if (valid[0]) {
 #pragma unroll
-        for (int s = 0; s < SLOTS; ++s) {
-            if (valid[s]) {
+            for (int j = 0; j < 8; ++j) M[pos[0] * LD + J0 + j] = p[0][j];
+            M[pos[0] * LD + P] = p[0][8];
+        }
+        if (two && valid[1]) {
 #pragma unroll
-                for (int j = 0; j < NBc; ++j) M[pos[s] * LD + J0 + j] = p[s][j];
-                M[pos[s] * LD + N] = p[s][NBc];
-            }
+            for (int j = 0; j < 8; ++j) M[pos[1] * LD + J0 + j] = p[1][j];
+            M[pos[1] * LD + P] = p[1][8];
         }
         __syncwarp();
         // ------------------------------------------------------------------ phase U
-#pragma unroll
-        for (int c0 = 0; c0 < MT; c0 += 32) {
+        for (int c0 = 0; c0 < MTr; c0 += 32) {
             const int c = c0 + lane;
-            const bool act = (c0 + 31 < MT) || (c < MT);
+            const bool act = c < MTr;
             const int col = R0 + (act ? c : 0);
-            double2 a[NBc];
+            double2 a[8];
 #pragma unroll
-            for (int kk = 0; kk < NBc; ++kk) a[kk] = M[(J0 + kk) * LD + col];
+            for (int kk = 0; kk < 8; ++kk) a[kk] = M[(J0 + kk) * LD + col];
 #pragma unroll
-            for (int kk = 1; kk < NBc; ++kk)
+            for (int kk = 1; kk < 8; ++kk)
 #pragma unroll
                 for (int k2 = 0; k2 < kk; ++k2) cfnma(a[kk], M[(J0 + kk) * LD + J0 + k2], a[k2]);
-            double2 z = M[N * LD + col];
+            double2 z = M[P * LD + col];
 #pragma unroll
-            for (int kk = 0; kk < NBc; ++kk) cfnma(z, M[N * LD + J0 + kk], a[kk]);
+            for (int kk = 0; kk < 8; ++kk) cfnma(z, M[P * LD + J0 + kk], a[kk]);
             if (act) {
 #pragma unroll
-                for (int kk = 0; kk < NBc; ++kk) M[(J0 + kk) * LD + col] = a[kk];
-                M[N * LD + col] = z;
+                for (int kk = 0; kk < 8; ++kk) M[(J0 + kk) * LD + col] = a[kk];
+                M[P * LD + col] = z;
             }
         }
         __syncwarp();
         // ------------------------------------------------------------------ phase T
-        trailing_update<N, J0, NBc, 4, 4>(M, lane);
+        trailing_update_dmma(M, g, J0, lane);
         __syncwarp();
-        Stage<N, R0>::run(M, lane, singular, corner);
-        }
     }
-};
-
-// -b^T A^-1 b for the bordered matrix held in M (destroyed).  All lanes get the result.
-template <int N>
-__device__ __forceinline__ double2 bordered_schur(double2* __restrict__ M, int lane, int& singular) {
-    double2 corner = make_double2(0.0, 0.0);
-    Stage<N, 0>::run(M, lane, singular, corner);
     return corner;
 }
 

@@ -5,7 +5,7 @@
 namespace jitr {
 
 struct SweepArgs {
-    int lmax, model, n_energies, n_params;
+    int N, lmax, model, n_energies, n_params;
     long long n_pairs;
     const double* That;
     const double* mesh_x;
@@ -22,7 +22,7 @@ struct SweepArgs {
     int* status;
 };
 
-template <int N, bool PARAMS>
+template <bool PARAMS>
 int launch_sweep(const SweepArgs& a, cudaStream_t st);
 
 }  // namespace jitr

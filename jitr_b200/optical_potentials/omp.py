@@ -35,9 +35,11 @@ class SingleChannelOpticalModel:
             p = torch.tensor(np.atleast_2d(np.asarray(params, dtype=np.float64)), device=device or "cuda")
         if p.dim() == 1:
             p = p.unsqueeze(0)
+        need = _cabi.MODEL_NPARAMS[self.model_id]
+        if p.shape[1] == need and p.is_contiguous():
+            return p  # already in the kernel's padded row layout
         if p.shape[1] != self.n_params:
             raise ValueError(f"expected {self.n_params} parameters per row, got {p.shape[1]}")
-        need = _cabi.MODEL_NPARAMS[self.model_id]
         if p.shape[1] < need:
             p = torch.nn.functional.pad(p, (0, need - p.shape[1]))
         return p.contiguous()

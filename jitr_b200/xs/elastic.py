@@ -329,8 +329,9 @@ class ElasticSweep:
         import torch
 
         params = model.pack(params, self.device)
-        if hasattr(model, "radius_factor"):
+        if hasattr(model, "radius_factor") and getattr(self, "_rf_model", None) is not model:
             self.set_radius_factor(model)
+            self._rf_model = model
         B = params.shape[0]
         S, nl, status = self._alloc_S(B) if out is None else out
         rc = _cabi.lib().jitr_b200_elastic_sweep_params(
@@ -388,6 +389,50 @@ class ElasticSweep:
         )
         _cabi.check(rc, "jitr_b200_elastic_observables")
         return ElasticXS(dsdo, Ay, Q, tr[..., 0], tr[..., 1])
+
+    def xs_params_to_host(self, model, params_host, dsdo_host, tr_host, chunk=8192):
+        """End-to-end sweep with HOST buffers: ``params_host`` (B, n_params) pinned float64 ->
+        ``dsdo_host`` (B, E, n_angles) and ``tr_host`` (B, E, 2) pinned float64.  The sample axis is
+        processed in chunks on two device buffer sets so that the device->host copy of chunk i
+        overlaps the solve of chunk i+1 (copy stream + events).  Returns the number of systems solved."""
+        import torch
+
+        B = params_host.shape[0]
+        cur = torch.cuda.current_stream(self.device)
+        if not hasattr(self, "_copy_stream"):
+            self._copy_stream = torch.cuda.Stream(self.device)
+            self._bufs = {}
+        key = (chunk, params_host.shape[1])
+        if key not in self._bufs:
+            mk = lambda *sh, dt=torch.float64: torch.empty(sh, dtype=dt, device=self.device)
+            self._bufs[key] = [
+                dict(p=mk(chunk, params_host.shape[1]), S=self._alloc_S(chunk),
+                     obs=(mk(chunk, self.nE, self.n_angles), None, None, mk(chunk, self.nE, 2)), done=None)
+                for _ in range(2)
+            ]
+        bufs = self._bufs[key]
+        nsolve = torch.zeros((), dtype=torch.int64, device=self.device)
+        for i, s0 in enumerate(range(0, B, chunk)):
+            n = min(chunk, B - s0)
+            b = bufs[i % 2]
+            if b["done"] is not None:
+                cur.wait_event(b["done"])  # previous D2H out of this buffer set has finished
+            b["p"][:n].copy_(params_host[s0 : s0 + n], non_blocking=True)
+            S, nl, status = (t[:n] for t in b["S"])
+            self.smatrix_params(model, b["p"][:n], out=(S, nl, status))
+            dsdo, _, _, tr = b["obs"]
+            self.observables(S, nl, want_Ay=False, want_Q=False, out=(dsdo[:n], None, None, tr[:n]))
+            nsolve += (2 * nl.to(torch.int64) - 1).sum()
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            self._copy_stream.wait_event(ev)
+            with torch.cuda.stream(self._copy_stream):
+                dsdo_host[s0 : s0 + n].copy_(dsdo[:n], non_blocking=True)
+                tr_host[s0 : s0 + n].copy_(tr[:n], non_blocking=True)
+                b["done"] = torch.cuda.Event()
+                b["done"].record(self._copy_stream)
+        cur.wait_stream(self._copy_stream)
+        return nsolve
 
     def xs_params(self, model, params, return_status=False):
         S, nl, status = self.smatrix_params(model, params)

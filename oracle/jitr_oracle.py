@@ -146,24 +146,40 @@ def interaction_matrix(nbasis, k0, E0, a, nch, local_potential=None, nonlocal_po
 # ----------------------------------------------------------------------------
 # the solve  (rmatrix/core.py)
 # ----------------------------------------------------------------------------
-def rmatrix_with_inverse(A, b, nch, nbasis, a):
+def _rmatrix_with_inverse_py(A, b, nch, nbasis, a):
     """R_ij = b^T (A^-1)_ij b / a^2 using the explicit inverse.  rmatrix/core.py:7-22."""
     C = np.linalg.inv(A)
     R = np.zeros((nch, nch), dtype=np.complex128)
     for i in range(nch):
         for j in range(nch):
-            R[i, j] = b @ C[i * nbasis : (i + 1) * nbasis, j * nbasis : (j + 1) * nbasis] @ b
+            Cblock = np.ascontiguousarray(C[i * nbasis : (i + 1) * nbasis, j * nbasis : (j + 1) * nbasis])
+            R[i, j] = b.T @ Cblock @ b
     return R / a**2, C
 
 
-def solve_smatrix(A, b, Hp, Hm, Hpp, Hmp, weights, a, nch, nbasis):
+def _solve_smatrix_py(A, b, Hp, Hm, Hpp, Hmp, weights, a, nch, nbasis):
     """R, S, A^-1 and u'_ext(a).  rmatrix/core.py:25-60."""
     R, Ainv = rmatrix_with_inverse(A, b, nch, nbasis, a)
     Zp = np.diag(Hp) - R @ np.diag(Hpp) * a
     Zm = np.diag(Hm) - R @ np.diag(Hmp) * a
     S = np.linalg.solve(Zp, Zm)
-    uext_prime = 1j / 2 * (Hmp * weights - S @ Hpp)
+    uext_prime = 1j / 2 * (Hmp * weights - S @ np.copy(Hpp))
     return R, S, Ainv, uext_prime
+
+
+# The reference compiles these two functions with numba @njit (np.linalg.inv -> LAPACK zgetrf+zgetri,
+# about 2x faster than numpy's inv).  The CPU baseline must not be slower than the reference for
+# a reason that is not the reference's, so the same decorator is applied when numba is importable.
+try:  # pragma: no cover - depends on the image
+    import numba as _numba
+
+    rmatrix_with_inverse = _numba.njit(_rmatrix_with_inverse_py)
+    solve_smatrix = _numba.njit(_solve_smatrix_py)
+    HAVE_NUMBA = True
+except Exception:  # numba missing: plain numpy (same numbers to rounding)
+    rmatrix_with_inverse = _rmatrix_with_inverse_py
+    solve_smatrix = _solve_smatrix_py
+    HAVE_NUMBA = False
 
 
 def solution_coeffs(Ainv, b, uext_prime, nch, nbasis):
@@ -409,6 +425,8 @@ class ElasticWorkspace:
         if asym_table is None:
             asym_table = np.array([coulomb_hankel(l, eta, self.a) for l in range(lmax + 1)])
         self.asym = asym_table  # (lmax+1, 4): Hp, Hm, Hpp, Hmp
+        self._H = [[np.array([v], dtype=np.complex128) for v in row] for row in self.asym]
+        self._one = np.ones(1, dtype=np.float64)
         self.angles = angles
         ls = np.arange(lmax + 1)[:, None]
         self.P = eval_legendre(ls, np.cos(angles))
@@ -423,11 +441,8 @@ class ElasticWorkspace:
             self.f_c = np.zeros_like(angles)
 
     def _solve(self, A, l):
-        Hp, Hm, Hpp, Hmp = self.asym[l]
-        one = np.ones(1)
-        _, S, _, _ = solve_smatrix(
-            A, self.b, Hp * one, Hm * one, Hpp * one, Hmp * one, one, self.a, 1, self.N
-        )
+        H = self._H[l]
+        _, S, _, _ = solve_smatrix(A, self.b, H[0], H[1], H[2], H[3], self._one, self.a, 1, self.N)
         return S[0, 0]
 
     def smatrix(self, central, spin_orbit=None, coulomb=None, count=None):

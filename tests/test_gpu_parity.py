@@ -18,6 +18,9 @@ from oracle import jitr_oracle as orc  # noqa: E402
 
 RTOL_S = 1e-10
 RTOL_XS = 1e-8
+# Ay and Q are bounded ratios in [-1, 1] that cross zero: near a crossing only the ABSOLUTE error is
+# meaningful (2 Im/Re(a* b) cancels), so they are checked to 1e-8 relative OR 1e-9 absolute.
+ATOL_POL = 1e-9
 
 
 def relerr(a, b, floor=0.0):
@@ -58,8 +61,8 @@ def check_xs_against_golden(x, S, nl, g, idx):
         assert relerr(S[row, 1, 1:L], g["sminus"][i, 1:L]) < RTOL_S
         assert np.all(S[row, :, L:] == 0)
         assert relerr(x.dsdo[row].cpu().numpy(), g["dsdo"][i]) < RTOL_XS
-        np.testing.assert_allclose(x.Ay[row].cpu().numpy(), g["Ay"][i], rtol=RTOL_XS, atol=1e-10)
-        np.testing.assert_allclose(x.Q[row].cpu().numpy(), g["Q"][i], rtol=RTOL_XS, atol=1e-10)
+        np.testing.assert_allclose(x.Ay[row].cpu().numpy(), g["Ay"][i], rtol=RTOL_XS, atol=ATOL_POL)
+        np.testing.assert_allclose(x.Q[row].cpu().numpy(), g["Q"][i], rtol=RTOL_XS, atol=ATOL_POL)
         assert abs(float(x.t[row]) - g["tot"][i]) / g["tot"][i] < RTOL_XS
         assert abs(float(x.rxn[row]) - g["rxn"][i]) / g["rxn"][i] < RTOL_XS
 
@@ -186,7 +189,7 @@ def test_fused_sweep_vs_oracle_random_shapes():
             co = orc.coulomb_charged_sphere(r, 40, q[16])
             dsdo, Ay, Q, tot, rxn = ow.xs(c, so, co)
             assert relerr(x.dsdo[s, ie].cpu().numpy(), dsdo) < RTOL_XS
-            np.testing.assert_allclose(x.Ay[s, ie].cpu().numpy(), Ay, rtol=RTOL_XS, atol=1e-10)
+            np.testing.assert_allclose(x.Ay[s, ie].cpu().numpy(), Ay, rtol=RTOL_XS, atol=ATOL_POL)
             assert abs(float(x.rxn[s, ie]) - rxn) / rxn < RTOL_XS
 
 
