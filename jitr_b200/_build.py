@@ -28,8 +28,17 @@ FLAGS = [
 ]
 
 
+def sweep_modes():
+    txt = open(os.path.join(CSRC, "sweep_decl.cuh")).read()
+    m = re.search(r"#define JITR_SWEEP_MODES\(X\)(.*)", txt)
+    return [int(v) for v in re.findall(r"X\((-?\d+)\)", m.group(1))]
+
+
 def _units():
-    return [(name, os.path.join(CSRC, name + ".cu"), []) for name in ("api", "probe", "elastic", "general")]
+    units = [(name, os.path.join(CSRC, name + ".cu"), []) for name in ("api", "probe", "elastic", "general")]
+    for mode in sweep_modes():
+        units.append((f"sweep_{mode}".replace("-", "g"), os.path.join(CSRC, "sweep_inst.cu"), [f"-DJITR_SWEEP_MODE={mode}"]))
+    return units
 
 
 def _deps(src, seen=None):

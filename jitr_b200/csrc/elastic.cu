@@ -9,7 +9,7 @@
 #include "jitr_b200.h"
 #include "lu_warp.cuh"
 #include "potentials.cuh"
-#include "elastic_sweep.cuh"
+#include "sweep_decl.cuh"
 
 namespace jitr {
 
@@ -140,6 +140,23 @@ __global__ void eval_potentials_kernel(int N, int model, long long n_pairs, int 
     central[idx] = vc;
     spin_orbit[idx] = vs;
     coulomb[idx] = co;
+}
+
+// pick the solver mode for nbasis: fast path when P <= 40, generic otherwise
+template <bool PARAMS>
+static int launch_sweep(const SweepArgs& a, cudaStream_t st) {
+    const int N = a.N;
+    if (N < 1 || N > 64) return set_error(JITR_B200_ERR_UNSUPPORTED, "elastic sweep: nbasis must be in 1..64");
+    const int P = (N + 7) & ~7;
+    switch (P) {
+        case 16: return launch_sweep_mode<PARAMS, 16>(a, st);
+        case 24: return launch_sweep_mode<PARAMS, 24>(a, st);
+        case 32: return launch_sweep_mode<PARAMS, 32>(a, st);
+        case 40: return launch_sweep_mode<PARAMS, 40>(a, st);
+        default: break;
+    }
+    if (P + 1 <= 64) return launch_sweep_mode<PARAMS, -2>(a, st);
+    return launch_sweep_mode<PARAMS, -3>(a, st);
 }
 
 }  // namespace jitr

@@ -1,13 +1,15 @@
 // Fused spin-1/2 elastic sweep kernel:
 // potential evaluation -> system assembly -> bordered LU -> R -> S, one WARP per (sample, energy)
 // pair walking l = 0..lmax, j = l +- 1/2 with the reference's data-dependent early break
-// (xs/elastic.py:104-183).  nbasis is a runtime value (<= 63: at most two row slots per lane).
+// (xs/elastic.py:104-183).  nbasis is a runtime value (<= 64); the kernel is instantiated per solver MODE
+// (fast paths for P = 8 ceil(N/8) <= 40, generic paths above), one translation unit per MODE.
 #pragma once
 #include <cuda_runtime.h>
 #include <math.h>
 
 #include "common.cuh"
 #include "jitr_b200.h"
+#include "lu_fast.cuh"
 #include "lu_warp.cuh"
 #include "potentials.cuh"
 #include "sweep_decl.cuh"
@@ -15,50 +17,169 @@
 namespace jitr {
 
 constexpr int kSweepMaxSmem = 232448;  // max dynamic shared memory per block on sm_100
-constexpr int kSweepMaxWarps = 8;
 
-// shared-memory plan for a given nbasis: `warps` bordered systems of (P+1)^2 complex + That (N^2 real)
-struct SweepPlan {
-    int P, LD, msz, warps, smem;
+// ---------------------------------------------------------------------------------------------
+// Per-warp solver of one system  a^2 A = That + diag(d):  returns -b^T (a^2 A)^-1 b.
+// MODE > 0: fast path for P = MODE (lu_fast.cuh, the system never exists as a whole; 12 warps per
+//           SM for P = 40).   MODE = -2 / -3: generic path, the bordered matrix is assembled in the
+//           warp's shared-memory region (lu_warp.cuh) with at most 2 / 3 row slots per lane.
+// ---------------------------------------------------------------------------------------------
+template <int MODE>
+struct WarpSolver;
+
+template <int MODE>
+struct SweepPlan;
+
+template <int MAXNS>
+struct GenericPlan {
+    static constexpr int kMaxWarps = 8;
+    static constexpr int kThreads = kMaxWarps * 32;
+    static bool supports(int N) { return N >= 1 && ((N + 7) & ~7) + 1 <= 32 * MAXNS && N <= 64; }
+    static int warps(int N) {
+        const int P = (N + 7) & ~7, msz = (P + 1) * (P + 1);
+        const int fit = (kSweepMaxSmem - N * N * 8 - N * 8) / (msz * 16);
+        return fit > kMaxWarps ? kMaxWarps : fit;
+    }
+    static int smem(int N, int w) {
+        const int P = (N + 7) & ~7, msz = (P + 1) * (P + 1);
+        return w * msz * 16 + N * N * 8 + N * 8;
+    }
 };
-inline SweepPlan sweep_plan(int N) {
-    SweepPlan p;
-    p.P = (N + 7) & ~7;
-    p.LD = p.P + 1;
-    p.msz = p.LD * p.LD;
-    const int fit = (kSweepMaxSmem - N * N * 8) / (p.msz * 16);
-    p.warps = fit > kSweepMaxWarps ? kSweepMaxWarps : fit;
-    p.smem = p.warps * p.msz * 16 + N * N * 8;
-    return p;
-}
+template <>
+struct SweepPlan<-2> : GenericPlan<2> {};
+template <>
+struct SweepPlan<-3> : GenericPlan<3> {};
+
+template <int MAXNS>
+struct GenericSolver {
+    double2* M;
+    const double* Ts;
+    const double* bs;
+    LuGeom g;
+    int N, lane;
+    __device__ __forceinline__ void init(unsigned char* smem, const double* That, const double* bvec, int N_, int nwarps,
+                                         int warp, int lane_) {
+        N = N_;
+        lane = lane_;
+        g.N = N;
+        g.P = (N + 7) & ~7;
+        g.LD = g.P + 1;
+        const int msz = g.LD * g.LD;
+        M = reinterpret_cast<double2*>(smem) + (size_t)warp * msz;
+        double* T = reinterpret_cast<double*>(smem + (size_t)nwarps * msz * 16);
+        double* b = T + N * N;
+        for (int i = threadIdx.x; i < N * N; i += blockDim.x) T[i] = That[i];
+        for (int i = threadIdx.x; i < N; i += blockDim.x) b[i] = bvec[i];
+        Ts = T;
+        bs = b;
+    }
+    // d0, d1: diagonal entries of rows lane and lane + 32
+    __device__ __forceinline__ double2 solve(const double2 d0, const double2 d1, int& singular) {
+        const int P = g.P, LD = g.LD;
+        const int n0 = lane, n1 = lane + 32;
+        const bool v0 = n0 < N, v1 = n1 < N;
+        const double2 zero2 = make_double2(0.0, 0.0);
+        // ---- assemble the bordered matrix  [[That + diag, 0, b], [0, I, 0], [b^T, 0, 0]]
+        for (int i = 0; i < N; ++i) {
+            const double* Trow = Ts + i * N;
+            double2* Mrow = M + i * LD;
+            if (lane < P) Mrow[lane] = make_double2(v0 ? Trow[n0] : 0.0, 0.0);
+            if (n1 < P) Mrow[n1] = make_double2(v1 ? Trow[n1] : 0.0, 0.0);
+        }
+        for (int i = N; i < P; ++i)  // identity padding rows
+            for (int j = lane; j < LD; j += 32) M[i * LD + j] = make_double2(i == j ? 1.0 : 0.0, 0.0);
+        __syncwarp();
+        if (v0) {
+            const double2 bb = make_double2(bs[n0], 0.0);
+            M[n0 * LD + n0] = d0;
+            M[n0 * LD + P] = bb;
+            M[P * LD + n0] = bb;
+        }
+        if (v1) {
+            const double2 bb = make_double2(bs[n1], 0.0);
+            M[n1 * LD + n1] = d1;
+            M[n1 * LD + P] = bb;
+            M[P * LD + n1] = bb;
+        }
+        for (int j = N + lane; j <= P; j += 32) M[P * LD + j] = zero2;  // z row: padding + corner
+        __syncwarp();
+        const double2 corner = bordered_schur<MAXNS>(M, g, lane, singular);
+        __syncwarp();
+        return corner;
+    }
+};
+template <>
+struct WarpSolver<-2> : GenericSolver<2> {};
+template <>
+struct WarpSolver<-3> : GenericSolver<3> {};
+
+template <int PT>
+struct SweepPlan {
+    using G = FastGeom<PT>;
+    static constexpr int kShared = (PT * PT + PT) * 8;
+    static constexpr int kFit = (kSweepMaxSmem - kShared) / G::WARP_BYTES;
+    static constexpr int kMaxWarps = kFit > 16 ? 16 : kFit;
+    static constexpr int kThreads = kMaxWarps * 32;
+    static bool supports(int N) { return N > PT - 8 && N <= PT; }
+    static int warps(int) { return kMaxWarps; }
+    static int smem(int, int w) { return kShared + w * G::WARP_BYTES; }
+};
+
+template <int PT>
+struct WarpSolver {
+    using G = FastGeom<PT>;
+    double2* W;
+    double2* dvec;
+    unsigned char* origv;
+    const double* Tp;
+    const double* bsh;
+    int N, lane;
+    __device__ __forceinline__ void init(unsigned char* smem, const double* That, const double* bvec, int N_, int nwarps,
+                                         int warp, int lane_) {
+        N = N_;
+        lane = lane_;
+        double* T = reinterpret_cast<double*>(smem);
+        double* b = T + PT * PT;
+        unsigned char* wbase = smem + SweepPlan<PT>::kShared + (size_t)warp * G::WARP_BYTES;
+        W = reinterpret_cast<double2*>(wbase);
+        dvec = W + G::WALLOC;
+        origv = reinterpret_cast<unsigned char*>(dvec + PT);
+        for (int i = threadIdx.x; i < PT * PT; i += blockDim.x) {  // That padded with the identity
+            const int r = i / PT, c = i - r * PT;
+            T[i] = (r < N && c < N) ? That[r * N + c] : (r == c ? 1.0 : 0.0);
+        }
+        for (int i = threadIdx.x; i < PT; i += blockDim.x) b[i] = i < N ? bvec[i] : 0.0;
+        Tp = T;
+        bsh = b;
+    }
+    __device__ __forceinline__ double2 solve(const double2 d0, const double2 d1, int& singular) {
+        double2 d[G::NS0];
+        d[0] = lane < N ? d0 : make_double2(1.0, 0.0);
+        if (G::NS0 > 1) d[G::NS0 - 1] = lane + 32 < N ? d1 : make_double2(1.0, 0.0);
+        const double2 corner = fast_schur<PT>(W, dvec, origv, Tp, bsh, d, lane, singular);
+        __syncwarp();
+        return corner;
+    }
+};
 
 // PARAMS: built-in potential forms from parameter rows; otherwise mesh values from tensors.
-template <bool PARAMS>
-__global__ void __launch_bounds__(kSweepMaxWarps * 32, 1) elastic_sweep_kernel(const SweepArgs A) {
+template <bool PARAMS, int MODE>
+__global__ void __launch_bounds__(SweepPlan<MODE>::kThreads, 1) elastic_sweep_kernel(const SweepArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int N = A.N;
-    LuGeom g;
-    g.N = N;
-    g.P = (N + 7) & ~7;
-    g.LD = g.P + 1;
-    const int P = g.P, LD = g.LD, msz = LD * LD;
     const int nwarps = blockDim.x >> 5;
-    double2* Mall = reinterpret_cast<double2*>(smem_raw);
-    double* Ts = reinterpret_cast<double*>(smem_raw + (size_t)nwarps * msz * 16);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double2* M = Mall + (size_t)warp * msz;
-
-    for (int i = threadIdx.x; i < N * N; i += blockDim.x) Ts[i] = A.That[i];
+    // broadcast from lane 0: tells the compiler the warp index (hence the whole work loop) is warp-uniform
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
+    WarpSolver<MODE> solver;
+    solver.init(smem_raw, A.That, A.bvec, N, nwarps, warp, lane);
     __syncthreads();
 
-    // mesh points owned by this lane (two slots, N <= 63)
+    // mesh points owned by this lane (two slots, N <= 64)
     const int n0 = lane, n1 = lane + 32;
     const bool v1 = n1 < N;
     const bool v0 = n0 < N;
     const double x0 = A.mesh_x[v0 ? n0 : 0], x1 = A.mesh_x[v1 ? n1 : 0];
-    const double b0 = A.bvec[v0 ? n0 : 0], b1 = A.bvec[v1 ? n1 : 0];
-    const double t0 = Ts[(v0 ? n0 : 0) * (N + 1)], t1 = Ts[(v1 ? n1 : 0) * (N + 1)];
+    const double t0 = A.That[(v0 ? n0 : 0) * (N + 1)], t1 = A.That[(v1 ? n1 : 0) * (N + 1)];
     const double cent0 = 1.0 / (x0 * x0), cent1 = 1.0 / (x1 * x1);
     const int L1 = A.lmax + 1;
     const double2 zero2 = make_double2(0.0, 0.0);
@@ -104,6 +225,7 @@ __global__ void __launch_bounds__(kSweepMaxWarps * 32, 1) elastic_sweep_kernel(c
         double2* Sp_out = A.S_out + (size_t)pair * 2 * L1;
         double2* Sm_out = Sp_out + L1;
         int nl = 0, singular = 0, nonfinite = 0;
+#pragma unroll 1
         for (int l = 0; l <= A.lmax; ++l) {
             const double ll1 = (double)l * (double)(l + 1);
             const double2* as = A.asym + ((size_t)e * L1 + l) * 4;
@@ -111,34 +233,13 @@ __global__ void __launch_bounds__(kSweepMaxWarps * 32, 1) elastic_sweep_kernel(c
             double2 Sj[2];
             Sj[1] = zero2;
             const int nj = (l == 0) ? 1 : 2;
+#pragma unroll 1
             for (int jj = 0; jj < nj; ++jj) {
                 const double ls = (jj == 0) ? (double)l : -(double)(l + 1);
-                // ---- assemble the bordered matrix  [[That + diag, 0, b], [0, 0, 0], [b^T, 0, 0]]
-                for (int i = 0; i < N; ++i) {
-                    const double* Trow = Ts + i * N;
-                    double2* Mrow = M + i * LD;
-                    if (lane < P) Mrow[lane] = make_double2(v0 ? Trow[n0] : 0.0, 0.0);
-                    if (n1 < P) Mrow[n1] = make_double2(v1 ? Trow[n1] : 0.0, 0.0);
-                }
-                for (int i = N; i < P; ++i) {  // zero padding rows
-                    for (int j = lane; j < LD; j += 32) M[i * LD + j] = zero2;
-                }
-                __syncwarp();
-                if (v0) {
-                    M[n0 * LD + n0] = make_double2(d0.x + ll1 * cent0 + ls * so0.x, d0.y + ls * so0.y);
-                    M[n0 * LD + P] = make_double2(b0, 0.0);
-                    M[P * LD + n0] = make_double2(b0, 0.0);
-                }
-                if (v1) {
-                    M[n1 * LD + n1] = make_double2(d1.x + ll1 * cent1 + ls * so1.x, d1.y + ls * so1.y);
-                    M[n1 * LD + P] = make_double2(b1, 0.0);
-                    M[P * LD + n1] = make_double2(b1, 0.0);
-                }
-                for (int j = N + lane; j <= P; j += 32) M[P * LD + j] = zero2;  // z row: padding + corner
-                __syncwarp();
-                // ---- factorise; corner = -b^T (a^2 A)^-1 b = -R
-                const double2 corner = bordered_schur(M, g, lane, singular);
-                __syncwarp();
+                const double2 dd0 = make_double2(d0.x + ll1 * cent0 + ls * so0.x, d0.y + ls * so0.y);
+                const double2 dd1 = make_double2(d1.x + ll1 * cent1 + ls * so1.x, d1.y + ls * so1.y);
+                // corner = -b^T (a^2 A)^-1 b = -R
+                const double2 corner = solver.solve(dd0, dd1, singular);
                 const double2 aR = make_double2(-a * corner.x, -a * corner.y);
                 // S = (H- - a R H-') / (H+ - a R H+')   (rmatrix/core.py:51-56 with nch = 1)
                 const double2 t_m = cmul(aR, Hmp), t_p = cmul(aR, Hpp);
@@ -169,23 +270,24 @@ __global__ void __launch_bounds__(kSweepMaxWarps * 32, 1) elastic_sweep_kernel(c
     }
 }
 
-template <bool PARAMS>
-int launch_sweep(const SweepArgs& a, cudaStream_t st) {
-    if (a.N < 1 || a.N > 63) return set_error(JITR_B200_ERR_UNSUPPORTED, "elastic sweep: nbasis must be in 1..63");
-    const SweepPlan plan = sweep_plan(a.N);
-    if (plan.warps < 1) return set_error(JITR_B200_ERR_UNSUPPORTED, "elastic sweep: system does not fit in shared memory");
-    auto kern = elastic_sweep_kernel<PARAMS>;
+template <bool PARAMS, int MODE>
+int launch_sweep_mode(const SweepArgs& a, cudaStream_t st) {
+    using Plan = SweepPlan<MODE>;
+    const int warps = Plan::warps(a.N);
+    if (warps < 1) return set_error(JITR_B200_ERR_UNSUPPORTED, "elastic sweep: system does not fit in shared memory");
+    const int smem = Plan::smem(a.N, warps);
+    auto kern = elastic_sweep_kernel<PARAMS, MODE>;
     static int configured = 0;
-    if (plan.smem > configured) {
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem) != cudaSuccess)
+    if (smem > configured) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
             return set_cuda_error("cudaFuncSetAttribute(elastic_sweep)");
-        configured = plan.smem;
+        configured = smem;
     }
     const int sms = sm_count();
-    long long blocks = (a.n_pairs + plan.warps - 1) / plan.warps;
+    long long blocks = (a.n_pairs + warps - 1) / warps;
     if (blocks > sms) blocks = sms;
     if (blocks < 1) return JITR_B200_OK;
-    kern<<<(unsigned)blocks, plan.warps * 32, plan.smem, st>>>(a);
+    kern<<<(unsigned)blocks, warps * 32, smem, st>>>(a);
     count_launch();
     if (cudaGetLastError() != cudaSuccess) return set_cuda_error("elastic_sweep launch");
     return JITR_B200_OK;

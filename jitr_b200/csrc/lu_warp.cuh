@@ -1,31 +1,39 @@
 // Warp-per-system blocked LU (complex128, partial pivoting) of the BORDERED matrix
 //
 //        M = [ A   0  b ]     rows 0..N-1   : the system (N = nbasis)
-//            [ 0   0  0 ]     rows N..P-1   : zero padding up to P = 8*ceil(N/8)
+//            [ 0   I  0 ]     rows N..P-1   : identity padding up to P = 8*ceil(N/8)
 //            [ b^T 0  0 ]     row  P        : the "z" row
 //
 // stored row-major in shared memory with leading dimension LD = P + 1 (odd: a column walk by the 32
 // lanes is bank-conflict free), column P holding the right-hand side.  The first N columns are
-// eliminated with the pivot search restricted to the first N rows; the corner M[P][P] that is left
+// eliminated with the pivot search restricted to the first P rows (the identity padding makes every
+// panel a full 8 columns and changes nothing else); the corner M[P][P] that is left
 // is the Schur complement  -b^T A^-1 b , i.e. minus the (scaled) R-matrix that rmatrix/core.py:7-22
 // obtains through the explicit inverse.  Neither L nor U is needed afterwards: no back-substitution.
 //
-// One warp owns one system; right-looking, panel width 8, three phases per panel.  The code is a
-// RUNTIME loop over panels with nbasis a runtime value: the first version of this file unrolled every
-// panel at compile time and ran instruction-fetch bound (400 KB of SASS, I-cache hit rate 38 %, ncu
-// profiles/r01_v1_*); this one is ~1.5k instructions and serves every nbasis <= 60.
-//   P  panel factorisation with the panel in REGISTERS, one matrix row per lane (two row slots while
-//      more than 32 rows are alive): pivot search = REDUX.MAX on the high word of |a|^2 + ballot,
-//      pivot-row broadcast = shuffles, rank-1 updates = DFMA on registers.  Column P (the RHS y) rides
-//      along as a ninth panel column, row P (z = U^-T b) as one more row that is never a pivot
-//      candidate.  Row interchanges of the trailing columns are done in shared memory as soon as the
-//      pivot is known (lane c always owns column c, so no barrier is needed).
+// One warp owns one system; right-looking, panel width 8, three phases per panel, nbasis a runtime
+// value (P + 1 <= 96 rows: up to three row slots per lane).
+//   P  panel factorisation with the panel in REGISTERS, one matrix row per lane (a second row slot
+//      while more than 32 rows are alive).  Pivot search: |re|+|im| (LAPACK izamax), REDUX.MAX on the
+//      high word + ballot; pivot-row broadcast by SHFL (measured on B200: a shared-memory store costs
+//      4 SM-cycles per 128-bit instruction whatever the number of active lanes, a SHFL 1).  Column P
+//      (the RHS y) rides along as a ninth panel column, row P (z = U^-T b) as one more row that is
+//      never a pivot candidate.  Row interchanges of the trailing columns are done in shared memory
+//      as soon as the pivot is known (lane c always owns column c, so no barrier is needed).
 //   U  U12 = L11^-1 A12: lane c owns trailing column c, 8-step forward substitution in registers
 //      (L11 read as shared-memory broadcasts); the z row is updated here too.
-//   T  A22 -= L21 U12 on the FP64 tensor-core path: 8x8 complex tiles, K = 8 = two m8n8k4 DMMA steps,
-//      four real DMMAs per complex step; a warp register-blocks 1x2 tiles.
+//   T  A22 -= L21 U12 on the FP64 tensor-core path (DMMA m8n8k4) in the REAL representation of the
+//      complex product: an 8 x 4 complex half-tile of C is an 8 x 8 real tile whose accumulator
+//      fragment (c0, c1) is exactly one interleaved complex number, so C moves between shared memory
+//      and the accumulators with one 128-bit access and no register shuffling; the 8 complex = 16
+//      real contraction indices take four DMMAs.
 #pragma once
 #include <cuda_runtime.h>
+
+#ifndef JITR_PH
+#define JITR_PH_INIT
+#define JITR_PH(k)
+#endif
 
 namespace jitr {
 
@@ -43,6 +51,19 @@ __device__ __forceinline__ void cfnma(double2& acc, double2 a, double2 b) {
 }
 __device__ __forceinline__ double2 crecip(double2 a) {
     double d = 1.0 / fma(a.x, a.x, a.y * a.y);
+    return make_double2(a.x * d, -a.y * d);
+}
+// 1/x to ~1 ulp without the slow-path code of the IEEE division: MUFU.RCP64H seed (2^-23) + two
+// Newton steps.  x must be finite, normal and non-zero (callers flag zero pivots separately).
+__device__ __forceinline__ double rcp_newton(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = fma(fma(-x, r, 1.0), r, r);
+    r = fma(fma(-x, r, 1.0), r, r);
+    return r;
+}
+__device__ __forceinline__ double2 crecip_fast(double2 a) {
+    const double d = rcp_newton(fma(a.x, a.x, a.y * a.y));
     return make_double2(a.x * d, -a.y * d);
 }
 __device__ __forceinline__ double2 cdiv(double2 n, double2 d) { return cmul(n, crecip(d)); }
@@ -65,194 +86,275 @@ struct LuGeom {
     int LD;   // P + 1
 };
 
-// ---- phase T: A22 -= L21 * U12, 8x8 complex tiles on DMMA --------------------------------------------
+// ---- phase P: factorise eight panel columns (+ the RHS column) held in registers -------------------
+// p[s][0..7] panel columns and p[s][8] the RHS of the row in slot s of this lane; pos[s] the row's
+// current position (LAPACK-style interchanges are applied to positions); cand[s] whether the row is
+// still a pivot candidate.  On return p[s][k] (k < 8) holds the row's multipliers, p[s][8] its updated
+// RHS; a row that became pivot kk has pos = `first` + kk and keeps its multipliers p[0..kk-1].
+// swap (warp-uniform): also interchange the trailing columns (R0.. R0+MTr-1) of the two rows in shared memory.
+template <int NS>
+__device__ __forceinline__ void panel_eliminate(double2 (&p)[NS][9], int (&pos)[NS], bool (&cand)[NS],
+                                                double2* __restrict__ M, const int LD, const int first, const int R0,
+                                                const int MTr, const bool swap, const int lane, int& singular) {
+#pragma unroll
+    for (int kk = 0; kk < 8; ++kk) {
+        // pivot search over the candidate rows: max |re| + |im|
+        double best = -1.0;
+        int bs = 0;
+        double2 cbest = p[0][kk];
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            const double m = fabs(p[s][kk].x) + fabs(p[s][kk].y);
+            if (cand[s] && m > best) {
+                best = m;
+                bs = s;
+                cbest = p[s][kk];
+            }
+        }
+        // speculative reciprocal of this lane's own candidate: runs beside the search instead of
+        // after the broadcast (it is the longest dependent chain of the step)
+        const double2 myrinv = crecip_fast(cbest);
+        const int key = __double2hiint(best);
+        const int kmax = __reduce_max_sync(kFull, key);
+        const int pl = __ffs(__ballot_sync(kFull, key == kmax)) - 1;
+        if (kmax <= 0) singular = 1;  // pivot is zero/denormal (or there is no finite candidate)
+        // (slot, position) of the pivot row, one shuffle
+        int mypk = pos[0];
+#pragma unroll
+        for (int s = 1; s < NS; ++s)
+            if (bs == s) mypk = pos[s] | (s << 8);
+        const int pk = __shfl_sync(kFull, mypk, pl);
+        const int ps = pk >> 8;  // warp-uniform
+        const int pp = pk & 0xff;
+        const int target = first + kk;
+        // broadcast 1/pivot and the pivot row (columns kk+1.. and the RHS); the row is final from now on
+        const double2 rinv = shfl2(myrinv, pl);
+        double2 u[9];
+#pragma unroll
+        for (int j = kk + 1; j < 9; ++j) {
+            double2 src = p[0][j];
+#pragma unroll
+            for (int s = 1; s < NS; ++s)
+                if (ps == s) src = p[s][j];
+            u[j] = shfl2(src, pl);
+        }
+        if (lane == pl) {  // the pivot row leaves the candidate set and is parked at `target`
+#pragma unroll
+            for (int s = 0; s < NS; ++s)
+                if (ps == s) {
+                    cand[s] = false;
+                    pos[s] = -1;
+                }
+        }
+        if (swap && pp != target) {  // interchange rows `target` and `pp` in the trailing columns
+            for (int c = lane; c < MTr; c += 32) {
+                const double2 t1 = M[target * LD + R0 + c];
+                const double2 t2 = M[pp * LD + R0 + c];
+                M[target * LD + R0 + c] = t2;
+                M[pp * LD + R0 + c] = t1;
+            }
+        }
+#pragma unroll
+        for (int s = 0; s < NS; ++s)
+            if (pos[s] == target) pos[s] = pp;  // whoever lived at `target` moves to the pivot's old home
+        if (lane == pl) {
+#pragma unroll
+            for (int s = 0; s < NS; ++s)
+                if (ps == s) pos[s] = target;
+        }
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            // A row that already is a pivot keeps its multipliers p[0..own kk-1] (all that phase U
+            // needs from it); what it computes from here on is never used.
+            const double2 l = cmul(p[s][kk], rinv);
+            p[s][kk] = l;
+#pragma unroll
+            for (int j = kk + 1; j < 9; ++j) cfnma(p[s][j], l, u[j]);
+        }
+    }
+}
+
+// Panel J0 of the matrix in shared memory.  NS = number of row slots per lane (rows alive, z row
+// included, <= 32 NS).  Returns true when this was the last panel; `corner` then holds -b^T A^-1 b.
+template <int NS>
+__device__ __forceinline__ void panel_load(double2 (&p)[NS][9], int (&pos)[NS], bool (&cand)[NS], bool (&wb)[NS],
+                                           const double2* __restrict__ M, const LuGeom g, const int J0, const int lane) {
+    const int P = g.P, LD = g.LD;
+    const int nreal = P - J0;
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+        const int i = 32 * s + lane;
+        cand[s] = i < nreal;
+        wb[s] = i <= nreal;              // row exists: real rows + the z row (i == nreal)
+        pos[s] = cand[s] ? J0 + i : P;   // the z row sits at row P
+        const int base = (wb[s] ? pos[s] : J0) * LD;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) p[s][j] = M[base + J0 + j];
+        p[s][8] = M[base + P];
+    }
+}
+template <int NS>
+__device__ __forceinline__ void panel_store(const double2 (&p)[NS][9], const int (&pos)[NS], const bool (&wb)[NS],
+                                            double2* __restrict__ M, const LuGeom g, const int J0) {
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+        if (wb[s]) {
+            double2* dst = M + pos[s] * g.LD;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dst[J0 + j] = p[s][j];
+            dst[g.P] = p[s][8];
+        }
+    }
+}
+template <int NS>
+__device__ __forceinline__ bool panel_phase(double2* __restrict__ M, const LuGeom g, const int J0, const int lane,
+                                            int& singular, double2& corner) {
+    const int nreal = g.P - J0;  // candidate rows still alive (before this panel), a multiple of 8
+    const int MTr = nreal - 8;   // trailing columns (0 on the last panel)
+    double2 p[NS][9];
+    int pos[NS];
+    bool cand[NS], wb[NS];
+    panel_load<NS>(p, pos, cand, wb, M, g, J0, lane);
+    panel_eliminate<NS>(p, pos, cand, M, g.LD, J0, J0 + 8, MTr, MTr > 0, lane, singular);
+    if (MTr <= 0) {
+        // last panel: the z row (slot 0 of lane 8) now holds the corner in its y slot
+        corner = shfl2(p[0][8], nreal & 31);
+        return true;
+    }
+    panel_store<NS>(p, pos, wb, M, g, J0);
+    return false;
+}
+
+// ---- phase U: U12 = L11^-1 A12 and the z row --------------------------------------------------------
+__device__ __forceinline__ void upper_phase(double2* __restrict__ M, const LuGeom g, const int J0, const int lane) {
+    const int P = g.P, LD = g.LD;
+    const int MTr = P - J0 - 8;
+    const int R0 = J0 + 8;
+#pragma unroll 1
+    for (int c0 = 0; c0 < MTr; c0 += 32) {
+        const int c = c0 + lane;
+        const bool act = c < MTr;
+        const int col = R0 + (act ? c : 0);
+        double2 a[8];
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) a[kk] = M[(J0 + kk) * LD + col];
+#pragma unroll
+        for (int kk = 1; kk < 8; ++kk)
+#pragma unroll
+            for (int k2 = 0; k2 < kk; ++k2) cfnma(a[kk], M[(J0 + kk) * LD + J0 + k2], a[k2]);
+        double2 z = M[P * LD + col];
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) cfnma(z, M[P * LD + J0 + kk], a[kk]);
+        if (act) {
+#pragma unroll
+            for (int kk = 1; kk < 8; ++kk) M[(J0 + kk) * LD + col] = a[kk];
+            M[P * LD + col] = z;
+        }
+    }
+}
+
+// ---- phase T: A22 -= L21 * U12 on DMMA, real representation of the complex product -------------------
+// Fragment <-> matrix mapping (lane = 4 fr + fk):
+//   C  8 rows x 4 complex columns: row rho(fr) = (fr >> 1) + 4 (fr & 1), complex column fk; the accumulator
+//      pair (c0, c1) is (re, im).  rho puts the two rows of a quarter-warp 4 rows apart, which makes the
+//      128-bit accesses conflict free with the odd leading dimension.
+//   contraction index of step s (0..3): complex k = s + 4 (fk >> 1), part = fk & 1 (0 re, 1 im)
+//   A  -L[row rho(fr)][k].part
+//   B  column n = fr -> complex column fr >> 1, pn = fr & 1:  component (part ^ pn) of U[k][col],
+//      negated when part = 1 and pn = 0      ( [re im] += [Lre Lim] [[Ure Uim], [-Uim Ure]] )
+struct TFrag {
+    int a_off, b_off, bflip, c_off;
+};
+// NQ tile columns starting at tile column tc0, all nt tile rows
+template <int NQ>
+__device__ __forceinline__ void trailing_block(double2* __restrict__ M, const TFrag f, const int LD, const int J0,
+                                               const int nt, const int tc0) {
+    const int R0 = J0 + 8;
+    const double* Md = reinterpret_cast<const double*>(M);
+    // B fragments of the NQ tile columns (2 half-tiles x 4 steps each), kept in registers over the tile rows
+    double b[NQ][2][4];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q)
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+                const double v = Md[f.b_off + 2 * (s * LD + R0 + 8 * (tc0 + q) + 4 * h)];
+                b[q][h][s] = __hiloint2double(__double2hiint(v) ^ f.bflip, __double2loint(v));
+            }
+#pragma unroll 1
+    for (int tr = 0; tr < nt; ++tr) {
+        const int rbase = (R0 + 8 * tr) * LD;
+        double a[4];
+#pragma unroll
+        for (int s = 0; s < 4; ++s) a[s] = dneg(Md[f.a_off + 2 * (rbase + s)]);
+        double2* Crow = M + rbase + f.c_off + 8 * tc0;
+        double2 c[NQ][2];
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            c[q][0] = Crow[8 * q];
+            c[q][1] = Crow[8 * q + 4];
+        }
+#pragma unroll
+        for (int s = 0; s < 4; ++s)
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                dmma884(c[q][0].x, c[q][0].y, a[s], b[q][0][s]);
+                dmma884(c[q][1].x, c[q][1].y, a[s], b[q][1][s]);
+            }
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            Crow[8 * q] = c[q][0];
+            Crow[8 * q + 4] = c[q][1];
+        }
+    }
+}
+
 __device__ __forceinline__ void trailing_update_dmma(double2* __restrict__ M, const LuGeom g, int J0, int lane) {
     const int R0 = J0 + 8;
     const int nt = (g.P - R0) >> 3;  // tiles per dimension
     const int LD = g.LD;
     const int fr = lane >> 2, fk = lane & 3;
-    for (int tr = 0; tr < nt; ++tr) {
-        // A fragments of this tile row (both k-steps): -L and the sign-flipped parts, kept in registers
-        const int arow = (R0 + 8 * tr + fr) * LD + J0 + fk;
-        const double2 l0 = M[arow], l1 = M[arow + 4];
-        const double nl0x = dneg(l0.x), nl0y = dneg(l0.y), nl1x = dneg(l1.x), nl1y = dneg(l1.y);
-        for (int tc = 0; tc < nt; tc += 2) {
-            const bool two = tc + 1 < nt;  // warp-uniform
-            const int bcol = R0 + 8 * tc + fr;
-            const int brow = (J0 + fk) * LD;
-            const double2 u0 = M[brow + bcol], u1 = M[brow + 4 * LD + bcol];
-            const int crow = (R0 + 8 * tr + fr) * LD + R0 + 8 * tc + 2 * fk;
-            double2 ca = M[crow], cb = M[crow + 1];
-            // C_re += (-Lre) Ure + (Lim) Uim ;  C_im += (-Lre) Uim + (-Lim) Ure
-            dmma884(ca.x, cb.x, nl0x, u0.x);
-            dmma884(ca.y, cb.y, nl0x, u0.y);
-            dmma884(ca.x, cb.x, l0.y, u0.y);
-            dmma884(ca.y, cb.y, nl0y, u0.x);
-            dmma884(ca.x, cb.x, nl1x, u1.x);
-            dmma884(ca.y, cb.y, nl1x, u1.y);
-            dmma884(ca.x, cb.x, l1.y, u1.y);
-            dmma884(ca.y, cb.y, nl1y, u1.x);
-            M[crow] = ca;
-            M[crow + 1] = cb;
-            if (two) {
-                const double2 v0 = M[brow + bcol + 8], v1 = M[brow + 4 * LD + bcol + 8];
-                double2 cc = M[crow + 8], cd = M[crow + 9];
-                dmma884(cc.x, cd.x, nl0x, v0.x);
-                dmma884(cc.y, cd.y, nl0x, v0.y);
-                dmma884(cc.x, cd.x, l0.y, v0.y);
-                dmma884(cc.y, cd.y, nl0y, v0.x);
-                dmma884(cc.x, cd.x, nl1x, v1.x);
-                dmma884(cc.y, cd.y, nl1x, v1.y);
-                dmma884(cc.x, cd.x, l1.y, v1.y);
-                dmma884(cc.y, cd.y, nl1y, v1.x);
-                M[crow + 8] = cc;
-                M[crow + 9] = cd;
-            }
-        }
-    }
+    const int rho = (fr >> 1) + 4 * (fr & 1);
+    const int part = fk & 1, pn = fr & 1;
+    TFrag f;
+    // per-lane element offsets (in doubles) of the A and B operands of step s = 0 (then + 2 s / + 2 s LD)
+    f.a_off = 2 * (rho * LD + J0 + 4 * (fk >> 1)) + part;
+    f.b_off = 2 * ((J0 + 4 * (fk >> 1)) * LD + (fr >> 1)) + (part ^ pn);
+    f.bflip = (part & (pn ^ 1)) ? 0x80000000 : 0;
+    f.c_off = rho * LD + R0 + fk;
+    int tc0 = 0;
+#pragma unroll 1
+    for (; tc0 + 4 <= nt; tc0 += 4) trailing_block<4>(M, f, LD, J0, nt, tc0);
+    const int rem = nt - tc0;  // warp-uniform
+    if (rem == 3) trailing_block<3>(M, f, LD, J0, nt, tc0);
+    else if (rem == 2) trailing_block<2>(M, f, LD, J0, nt, tc0);
+    else if (rem == 1) trailing_block<1>(M, f, LD, J0, nt, tc0);
 }
 
 // ---- the whole factorisation; returns the corner -b^T A^-1 b to every lane ---------------------------
-__device__ __forceinline__ double2 bordered_schur(double2* __restrict__ M, const LuGeom g, int lane, int& singular) {
-    const int N = g.N, P = g.P, LD = g.LD;
+// MAXNS: largest number of row slots the instantiation supports (P + 1 <= 32 MAXNS).
+template <int MAXNS>
+__device__ __forceinline__ double2 bordered_schur(double2* __restrict__ M, const LuGeom g, int lane, int& singular,
+                                                  const int J0start = 0) {
     double2 corner = make_double2(0.0, 0.0);
-    for (int J0 = 0; J0 < N; J0 += 8) {
-        const int nreal = N - J0;              // real rows still alive (before this panel)
-        const int nb = nreal < 8 ? nreal : 8;  // panel width
-        const int rows = nreal + 1;            // + z row
-        const bool two = rows > 32;            // warp-uniform: second row slot in use
-        const int MTr = N - J0 - 8;            // real trailing columns (<= 0 on the last panel)
-        const int R0 = J0 + 8;
-        // ------------------------------------------------------------------ phase P
-        double2 p[2][9];
-        int pos[2];
-        bool alive[2], cand[2], valid[2];
-#pragma unroll
-        for (int s = 0; s < 2; ++s) {
-            const int i = 32 * s + lane;
-            valid[s] = i < rows;
-            cand[s] = i < nreal;
-            alive[s] = valid[s];
-            pos[s] = cand[s] ? J0 + i : P;  // the z row sits at row P
-            if (s == 0 || two) {
-                const int base = (valid[s] ? pos[s] : J0) * LD;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) p[s][j] = M[base + J0 + j];
-                p[s][8] = M[base + P];
-            } else {
-#pragma unroll
-                for (int j = 0; j < 9; ++j) p[s][j] = make_double2(0.0, 0.0);
-            }
-        }
-#pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {
-            if (kk < nb) {  // warp-uniform
-                double best = -1.0;
-                int bs = 0;
-                {
-                    const double m = fma(p[0][kk].x, p[0][kk].x, p[0][kk].y * p[0][kk].y);
-                    if (cand[0] && alive[0] && m > best) best = m;
-                }
-                if (two) {
-                    const double m = fma(p[1][kk].x, p[1][kk].x, p[1][kk].y * p[1][kk].y);
-                    if (cand[1] && alive[1] && m > best) {
-                        best = m;
-                        bs = 1;
-                    }
-                }
-                const int key = __double2hiint(best);
-                const int kmax = __reduce_max_sync(kFull, key);
-                const unsigned ball = __ballot_sync(kFull, key == kmax);
-                const int pl = __ffs(ball) - 1;
-                if (kmax <= 0) singular = 1;  // |pivot|^2 is zero/denormal (or no candidate)
-                const int ps = two ? __shfl_sync(kFull, bs, pl) : 0;
-                double2 u[9];
-#pragma unroll
-                for (int j = kk; j < 9; ++j) {
-                    double2 src = p[0][j];
-                    if (ps) src = p[1][j];
-                    u[j] = shfl2(src, pl);
-                }
-                const int pp = __shfl_sync(kFull, ps ? pos[1] : pos[0], pl);
-                const int target = J0 + kk;
-                if (MTr > 0 && pp != target) {  // interchange rows `target` and `pp` in the trailing columns
-                    for (int c = lane; c < MTr; c += 32) {
-                        const double2 t1 = M[target * LD + R0 + c];
-                        const double2 t2 = M[pp * LD + R0 + c];
-                        M[target * LD + R0 + c] = t2;
-                        M[pp * LD + R0 + c] = t1;
-                    }
-                }
-#pragma unroll
-                for (int s = 0; s < 2; ++s)
-                    if (pos[s] == target) pos[s] = pp;
-                if (lane == pl) {
-                    if (ps) { pos[1] = target; alive[1] = false; }
-                    else    { pos[0] = target; alive[0] = false; }
-                }
-                const double2 rinv = crecip(u[kk]);
-                {
-                    double2 l = make_double2(0.0, 0.0);
-                    if (alive[0]) {
-                        l = cmul(p[0][kk], rinv);
-                        p[0][kk] = l;
-                    }
-#pragma unroll
-                    for (int j = kk + 1; j < 9; ++j) cfnma(p[0][j], l, u[j]);
-                }
-                if (two) {
-                    double2 l = make_double2(0.0, 0.0);
-                    if (alive[1]) {
-                        l = cmul(p[1][kk], rinv);
-                        p[1][kk] = l;
-                    }
-#pragma unroll
-                    for (int j = kk + 1; j < 9; ++j) cfnma(p[1][j], l, u[j]);
-                }
-            }
-        }
-        if (MTr <= 0) {
-            // last panel: the z row now holds the corner in its y slot
-            const int zl = nreal & 31, zs = nreal >> 5;
-            corner = shfl2(zs ? p[1][8] : p[0][8], zl);
-            break;
-        }
-        if (valid[0]) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) M[pos[0] * LD + J0 + j] = p[0][j];
-            M[pos[0] * LD + P] = p[0][8];
-        }
-        if (two && valid[1]) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) M[pos[1] * LD + J0 + j] = p[1][j];
-            M[pos[1] * LD + P] = p[1][8];
-        }
+    JITR_PH_INIT
+#pragma unroll 1
+    for (int J0 = J0start; J0 < g.P; J0 += 8) {
+        const int rows = g.P - J0 + 1;
+        bool last;
+        if (MAXNS >= 3 && rows > 64) last = panel_phase<(MAXNS >= 3 ? 3 : 1)>(M, g, J0, lane, singular, corner);
+        else if (MAXNS >= 2 && rows > 32) last = panel_phase<(MAXNS >= 2 ? 2 : 1)>(M, g, J0, lane, singular, corner);
+        else last = panel_phase<1>(M, g, J0, lane, singular, corner);
+        JITR_PH(0)
+        if (last) break;
         __syncwarp();
-        // ------------------------------------------------------------------ phase U
-        for (int c0 = 0; c0 < MTr; c0 += 32) {
-            const int c = c0 + lane;
-            const bool act = c < MTr;
-            const int col = R0 + (act ? c : 0);
-            double2 a[8];
-#pragma unroll
-            for (int kk = 0; kk < 8; ++kk) a[kk] = M[(J0 + kk) * LD + col];
-#pragma unroll
-            for (int kk = 1; kk < 8; ++kk)
-#pragma unroll
-                for (int k2 = 0; k2 < kk; ++k2) cfnma(a[kk], M[(J0 + kk) * LD + J0 + k2], a[k2]);
-            double2 z = M[P * LD + col];
-#pragma unroll
-            for (int kk = 0; kk < 8; ++kk) cfnma(z, M[P * LD + J0 + kk], a[kk]);
-            if (act) {
-#pragma unroll
-                for (int kk = 0; kk < 8; ++kk) M[(J0 + kk) * LD + col] = a[kk];
-                M[P * LD + col] = z;
-            }
-        }
+        upper_phase(M, g, J0, lane);
         __syncwarp();
-        // ------------------------------------------------------------------ phase T
+        JITR_PH(1)
         trailing_update_dmma(M, g, J0, lane);
         __syncwarp();
+        JITR_PH(2)
     }
     return corner;
 }

@@ -22,7 +22,11 @@ struct SweepArgs {
     int* status;
 };
 
-template <bool PARAMS>
-int launch_sweep(const SweepArgs& a, cudaStream_t st);
+// one instantiation per solver MODE (elastic_sweep.cuh); defined in sweep_inst.cu compiled with -DJITR_SWEEP_MODE
+template <bool PARAMS, int MODE>
+int launch_sweep_mode(const SweepArgs& a, cudaStream_t st);
+
+// solver modes compiled into the library: fast paths (P = MODE) and generic paths (-2, -3 row slots)
+#define JITR_SWEEP_MODES(X) X(16) X(24) X(32) X(40) X(-2) X(-3)
 
 }  // namespace jitr
