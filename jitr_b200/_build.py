@@ -17,15 +17,17 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 INCLUDE = os.path.join(ROOT, "include")
-LIBDIR = os.path.join(PKG, "_lib")
-OBJDIR = os.path.join(ROOT, "build", "obj")
+# JITR_B200_VARIANT=<name> + JITR_B200_NVCC_FLAGS="-D..." build a tuning variant into build/variants/<name>/
+VARIANT = os.environ.get("JITR_B200_VARIANT", "")
+LIBDIR = os.path.join(ROOT, "build", "variants", VARIANT) if VARIANT else os.path.join(PKG, "_lib")
+OBJDIR = os.path.join(ROOT, "build", "obj_" + VARIANT if VARIANT else "obj")
 LIB = os.path.join(LIBDIR, "libjitr_b200.so")
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-std=c++17", "-O3", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
     "-Xcompiler", "-fPIC", "-I", INCLUDE, "-I", CSRC,
-]
+] + os.environ.get("JITR_B200_NVCC_FLAGS", "").split()
 
 
 def sweep_modes():

@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_lib", "libjitr_b200.so")
+# JITR_B200_LIB: load another build of the same library (kernel tuning experiments)
+LIB_PATH = os.environ.get("JITR_B200_LIB") or os.path.join(_HERE, "_lib", "libjitr_b200.so")
 
 OK, ERR_BAD_ARG, ERR_UNSUPPORTED, ERR_CUDA = 0, 1, 2, 3
 STATUS_OK, STATUS_NONFINITE, STATUS_SINGULAR = 0, 1, 2

@@ -118,7 +118,10 @@ struct SweepPlan {
     using G = FastGeom<PT>;
     static constexpr int kShared = (PT * PT + PT) * 8;
     static constexpr int kFit = (kSweepMaxSmem - kShared) / G::WARP_BYTES;
-    static constexpr int kMaxWarps = kFit > 16 ? 16 : kFit;
+#ifndef JITR_FAST_WARPS
+#define JITR_FAST_WARPS 16
+#endif
+    static constexpr int kMaxWarps = kFit > JITR_FAST_WARPS ? JITR_FAST_WARPS : kFit;
     static constexpr int kThreads = kMaxWarps * 32;
     static bool supports(int N) { return N > PT - 8 && N <= PT; }
     static int warps(int) { return kMaxWarps; }
@@ -162,6 +165,29 @@ struct WarpSolver {
     }
 };
 
+// Built-in potential forms at this lane's two mesh points.  Deliberately NOT inlined: it runs once per
+// (sample, energy) pair, its code is large (parameter maps of four models, ten exponentials), and
+// inlined into the solve loop it evicted the LU code from the instruction cache (ncu: 2.7
+// no-instruction stall cycles per issued instruction, profiles/r01_sweep_v4_icache.txt).
+struct PairPotentials {
+    double2 vc0, vs0, vc1, vs1;
+};
+static __device__ __noinline__ PairPotentials eval_pair_potentials(int model, const double* __restrict__ prow,
+                                                            const double* __restrict__ et, double r0, double r1) {
+    const Shape sh = shape_from_model(model, prow, et);
+    PairPotentials o;
+    double co;
+    const double rr[2] = {r0, r1};
+    double2 vc[2], vs[2];
+#pragma unroll 1
+    for (int s = 0; s < 2; ++s) {
+        eval_shape(sh, rr[s], vc[s], vs[s], co);
+        vc[s].x += co;
+    }
+    o.vc0 = vc[0]; o.vs0 = vs[0]; o.vc1 = vc[1]; o.vs1 = vs[1];
+    return o;
+}
+
 // PARAMS: built-in potential forms from parameter rows; otherwise mesh values from tensors.
 template <bool PARAMS, int MODE>
 __global__ void __launch_bounds__(SweepPlan<MODE>::kThreads, 1) elastic_sweep_kernel(const SweepArgs A) {
@@ -195,12 +221,9 @@ __global__ void __launch_bounds__(SweepPlan<MODE>::kThreads, 1) elastic_sweep_ke
         // ---- potentials on this lane's mesh points, in the a^2-scaled form of the diagonal
         double2 vc0, vs0, vc1, vs1;
         if (PARAMS) {
-            const Shape sh = shape_from_model(A.model, A.params + (size_t)smp * A.n_params, et);
-            double co0, co1;
-            eval_shape(sh, x0 * radius, vc0, vs0, co0);
-            eval_shape(sh, x1 * radius, vc1, vs1, co1);
-            vc0.x += co0;
-            vc1.x += co1;
+            const PairPotentials pp =
+                eval_pair_potentials(A.model, A.params + (size_t)smp * A.n_params, et, x0 * radius, x1 * radius);
+            vc0 = pp.vc0; vs0 = pp.vs0; vc1 = pp.vc1; vs1 = pp.vs1;
         } else {
             const size_t off = (size_t)pair * N;
             vc0 = A.central[off + (v0 ? n0 : 0)];
@@ -228,8 +251,6 @@ __global__ void __launch_bounds__(SweepPlan<MODE>::kThreads, 1) elastic_sweep_ke
 #pragma unroll 1
         for (int l = 0; l <= A.lmax; ++l) {
             const double ll1 = (double)l * (double)(l + 1);
-            const double2* as = A.asym + ((size_t)e * L1 + l) * 4;
-            const double2 Hp = as[0], Hm = as[1], Hpp = as[2], Hmp = as[3];
             double2 Sj[2];
             Sj[1] = zero2;
             const int nj = (l == 0) ? 1 : 2;
@@ -240,6 +261,8 @@ __global__ void __launch_bounds__(SweepPlan<MODE>::kThreads, 1) elastic_sweep_ke
                 const double2 dd1 = make_double2(d1.x + ll1 * cent1 + ls * so1.x, d1.y + ls * so1.y);
                 // corner = -b^T (a^2 A)^-1 b = -R
                 const double2 corner = solver.solve(dd0, dd1, singular);
+                const double2* as = A.asym + ((size_t)e * L1 + l) * 4;  // (after the solve: fewer live registers)
+                const double2 Hp = as[0], Hm = as[1], Hpp = as[2], Hmp = as[3];
                 const double2 aR = make_double2(-a * corner.x, -a * corner.y);
                 // S = (H- - a R H-') / (H+ - a R H+')   (rmatrix/core.py:51-56 with nch = 1)
                 const double2 t_m = cmul(aR, Hmp), t_p = cmul(aR, Hpp);
@@ -256,7 +279,9 @@ __global__ void __launch_bounds__(SweepPlan<MODE>::kThreads, 1) elastic_sweep_ke
             nl = l + 1;
             if (l >= 1 && A.tol > 0.0) {
                 const double dp = hypot(1.0 - Sj[0].x, Sj[0].y), dm = hypot(1.0 - Sj[1].x, Sj[1].y);
-                if (dp < A.tol && dm < A.tol) break;
+                // (a vote makes the exit provably warp-uniform for the compiler: the warp-collective
+                // instructions of the solve are then emitted without divergence guards)
+                if (__all_sync(0xffffffffu, dp < A.tol && dm < A.tol)) break;
             }
         }
         for (int l = nl + lane; l <= A.lmax; l += 32) {
