@@ -268,7 +268,7 @@ __global__ void __launch_bounds__(SweepPlan<MODE>::kThreads, 1) elastic_sweep_ke
                 const double2 t_m = cmul(aR, Hmp), t_p = cmul(aR, Hpp);
                 const double2 num = make_double2(Hm.x - t_m.x, Hm.y - t_m.y);
                 const double2 den = make_double2(Hp.x - t_p.x, Hp.y - t_p.y);
-                const double2 S = cdiv(num, den);
+                const double2 S = cmul(num, crecip_fast(den));
                 Sj[jj] = S;
                 if (!(isfinite(S.x) && isfinite(S.y))) nonfinite = 1;
             }
@@ -278,10 +278,12 @@ __global__ void __launch_bounds__(SweepPlan<MODE>::kThreads, 1) elastic_sweep_ke
             }
             nl = l + 1;
             if (l >= 1 && A.tol > 0.0) {
-                const double dp = hypot(1.0 - Sj[0].x, Sj[0].y), dm = hypot(1.0 - Sj[1].x, Sj[1].y);
+                // |1 - S| < tol for both j  (xs/elastic.py:178-181), compared in squares
+                const double ep = 1.0 - Sj[0].x, em = 1.0 - Sj[1].x, tol2 = A.tol * A.tol;
+                const bool small = fma(ep, ep, Sj[0].y * Sj[0].y) < tol2 && fma(em, em, Sj[1].y * Sj[1].y) < tol2;
                 // (a vote makes the exit provably warp-uniform for the compiler: the warp-collective
                 // instructions of the solve are then emitted without divergence guards)
-                if (__all_sync(0xffffffffu, dp < A.tol && dm < A.tol)) break;
+                if (__all_sync(0xffffffffu, small)) break;
             }
         }
         for (int l = nl + lane; l <= A.lmax; l += 32) {
