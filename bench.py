@@ -8,9 +8,11 @@ One "step" = one pass of the hot path over the whole synthetic sweep: S KDUQ par
 (416 real federal posterior rows + multivariate-normal draws fitted to them, seed 20241019) x
 {n+40Ca, n+208Pb} x 32 energies linspace(5, 67, 32) MeV, N = 40, lmax = 30, 180 angles:
 fused potential evaluation + assembly + LU + R -> S (kernel 1/2) and elastic observables (kernel 3).
-For N > 1 (torchrun, one rank per GPU) the sample axis is sharded (strong scaling of the fixed
-S-sample sweep), no traffic during the solve, one NCCL gather of d sigma/d Omega to rank 0.
-Prints ONE JSON line on rank 0.
+For N > 1 (torchrun, one rank per GPU) the sample axis is sharded: every rank solves its own block of
+S samples (weak scaling: per-GPU work fixed, the job is N x S samples), no traffic during the
+solve, one NCCL gather of sigma_tot / sigma_rxn to rank 0 per step (the full d sigma/d Omega block of
+a rank stays in its HBM / goes to its own pinned host buffer in the e2e leg; `--gather-dsdo` also
+gathers it).  Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
 
@@ -34,19 +36,22 @@ E_GRID = np.linspace(5.0, 67.0, 32)
 FLOPS_PER_SOLVE = 8 * N_BASIS**3 / 3 + 8 * N_BASIS**2  # complex LU + one RHS = 183 467
 
 
-def synthetic_kduq_samples(n):
-    """rows 0..415: KDUQ federal neutron posterior; the rest: MVN fitted to them."""
+def synthetic_kduq_samples(n, block=0):
+    """rows 0..415: KDUQ federal neutron posterior; the rest: MVN fitted to them.
+    ``block`` > 0 (ranks > 0 of a multi-GPU run) gives an independent block of draws only."""
     g = np.load(os.path.join(ROOT, "tests", "golden", "kduq_params.npz"))
     real = g["federal_n"]
-    if n <= len(real):
+    if block == 0 and n <= len(real):
         return real[:n].copy()
     vary = [i for i in range(real.shape[1]) if np.std(real[:, i]) > 0]
     mean = real[:, vary].mean(axis=0)
     cov = np.cov(real[:, vary], rowvar=False)
-    rng = np.random.default_rng(20241019)
+    rng = np.random.default_rng(20241019 + block)
     out = np.tile(real[0], (n, 1))
-    out[: len(real)] = real
-    filled = len(real)
+    filled = 0
+    if block == 0:
+        out[: len(real)] = real
+        filled = len(real)
     while filled < n:
         draw = rng.multivariate_normal(mean, cov, size=2 * (n - filled), method="cholesky", check_valid="ignore") \
             if np.all(np.linalg.eigvalsh(cov) > 0) else rng.multivariate_normal(mean, cov, size=2 * (n - filled))
@@ -142,8 +147,8 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": "partial-wave R-matrix solves/sec (KDUQ elastic sweep)", "value": v, "unit": "solves/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "complex128 (f64)", "data": "synthetic",
-        "config": workload_config(args.samples),
+        "scaling": "weak", "vs_baseline": None, "dtype": "complex128 (f64)", "data": "synthetic",
+        "config": workload_config(args.samples, args.gpus),
         "cpu_baseline": {"value": v, "unit": "solves/s", "cores": procs, "kind": "port", "sample": sample,
                          "samples_per_s": float(np.mean([r["samples_per_s"] for r in vals]))},
         "e2e": {"value": v, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -151,11 +156,12 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-def workload_config(samples):
+def workload_config(samples, world=1):
     return {
-        "workload": f"configs[1] KDUQ posterior sweep: {samples} samples x (n+40Ca, n+208Pb) x 32 energies 5-67 MeV, "
+        "workload": f"configs[1] KDUQ posterior sweep: {samples} samples per GPU x (n+40Ca, n+208Pb) x 32 energies 5-67 MeV, "
                     f"nbasis={N_BASIS}, lmax={LMAX}, {N_ANGLES} angles, elastic dsigma/dOmega + sigma_rxn, early break tol 1e-6",
-        "samples": samples, "pairs_per_step": samples * 64, "parallelism": "sample axis sharded over ranks",
+        "samples_per_gpu": samples, "samples": samples * world, "pairs_per_step": samples * world * 64,
+        "parallelism": f"dp{world}: sample axis sharded over ranks, no collective during the solve, one NCCL gather of the integral cross sections",
         "l2": "per-step working set (S-matrices + observables, >= 0.5 GB per 10^4 samples) exceeds the 126 MB L2; no flush needed",
     }
 
@@ -165,7 +171,8 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--samples", type=int, default=100000, help="total KDUQ samples of the sweep (sharded over ranks)")
+    ap.add_argument("--samples", type=int, default=100000, help="KDUQ samples per GPU (weak scaling; configs[1] has 10^5)")
+    ap.add_argument("--gather-dsdo", action="store_true", help="also gather the full dsigma/dOmega blocks to rank 0")
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--cpu-pairs", type=int, default=1500, help="(sample, energy) pairs per CPU worker for the CPU baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -204,22 +211,20 @@ def main():
     model = kduq.KDUQ((1, 0))
     nE = sweep.nE
 
-    # ---- inputs: this rank's shard of the sample axis
-    S_total = args.samples
-    lo, hi = rank * S_total // world, (rank + 1) * S_total // world
-    rows_all = synthetic_kduq_samples(S_total)
+    # ---- inputs: this rank's block of the sample axis (rank 0 holds the real posterior rows)
+    from jitr_b200.sharding import gather_to_root, shard_bounds
+
+    S_total = args.samples * world
+    lo, hi = shard_bounds(S_total, world, rank)
+    rows_all = synthetic_kduq_samples(hi - lo, block=rank)
     rows = np.zeros((hi - lo, 40))
-    rows[:, :37] = rows_all[lo:hi]
+    rows[:, :37] = rows_all
     B = hi - lo
     params_host = torch.from_numpy(rows).pin_memory()
     params_dev = params_host.to(dev)
     Sbuf = sweep._alloc_S(B)
     dsdo = torch.empty((B, nE, N_ANGLES), dtype=torch.float64, device=dev)
     tr = torch.empty((B, nE, 2), dtype=torch.float64, device=dev)
-    gather_list = None
-    if world > 1 and rank == 0:
-        sizes = [(r + 1) * S_total // world - r * S_total // world for r in range(world)]
-        gather_list = [torch.empty((sz, nE, N_ANGLES), dtype=torch.float64, device=dev) for sz in sizes]
 
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
 
@@ -231,11 +236,9 @@ def main():
         sweep.observables(Sbuf[0], Sbuf[1], want_Ay=False, want_Q=False, out=(dsdo, None, None, tr))
         ev[2].record()
         if world > 1:
-            # uneven shards are handled by gather of equal-size padded views only when sizes match
-            if len({g.shape[0] for g in gather_list} if rank == 0 else {0}) <= 1:
-                dist.gather(dsdo, gather_list if rank == 0 else None, dst=0)
-            else:
-                dist.gather(dsdo[: S_total // world].contiguous(), [g[: S_total // world] for g in gather_list] if rank == 0 else None, dst=0)
+            gather_to_root(tr, S_total, dst=0)
+            if args.gather_dsdo:
+                gather_to_root(dsdo, S_total, dst=0)
         ev[3].record()
 
     def sync_all():
@@ -321,7 +324,7 @@ def main():
     sweep_ms = t_sweep / args.steps
     achieved = my_solves * FLOPS_PER_SOLVE / (sweep_ms * 1e-3) / 1e12
     roofline = {
-        "bound": "fp64", "kernel": "elastic_sweep_kernel<40,true>", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+        "bound": "fp64", "kernel": "elastic_sweep_kernel<PARAMS=true, MODE=40> (fused potentials + assembly-free LU + R->S)", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
         "frac": achieved / peak, "traffic": None,
         "peak_source": "measured live: FP64 pipe micro-benchmark in this library (max of DFMA and DMMA m8n8k4 issue-bound loops); "
                        "MEASURED_PEAKS.json has no FP64 entry; nominal 37.2",
@@ -350,8 +353,8 @@ def main():
     line = {
         "metric": "partial-wave R-matrix solves/sec (KDUQ elastic sweep)", "value": value, "unit": "solves/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "complex128 (f64)", "data": "synthetic",
-        "config": workload_config(S_total),
+        "scaling": "weak", "vs_baseline": None, "dtype": "complex128 (f64)", "data": "synthetic",
+        "config": workload_config(args.samples, world),
         "samples_per_s": S_total * nE / (ms_per_step * 1e-3),
         "solves_per_pair": all_solves / (S_total * nE),
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu_baseline,

@@ -76,7 +76,7 @@ int jitr_b200_device_ok(void);
  *   optical_potentials/potential_forms.py:40-153, kduq.py:100-197,370-559, chuq.py:92-227,
  *   omp.py:54-149           evaluation of (central, spin_orbit, coulomb) on the mesh
  *
- *   nbasis      N, number of Lagrange-Legendre functions (compiled set: JITR_SWEEP_SIZES in csrc/common.cuh)
+ *   nbasis      N, number of Lagrange-Legendre functions, 1..64 (N <= 40 takes the assembly-free fast path)
  *   That        [N][N] real: a-independent kinetic+Bloch matrix (quadrature.py:197-218 with a=1,l=0)
  *   mesh_x      [N] abscissae on (0,1);  bvec [N] basis functions at the boundary (rmatrix.py:36-42)
  *   etab        [n_energies][JITR_B200_ET_STRIDE]

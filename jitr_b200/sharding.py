@@ -1,0 +1,47 @@
+"""Sample-axis sharding of a UQ sweep over ranks (one process per GPU).
+
+Every (sample, energy, l, j) system is independent: rank r owns a contiguous block of
+samples, all energies and partial waves stay local, nothing is exchanged during the solve, and the
+observables are gathered to the root rank ONCE at the end with a single ``torch.distributed.gather``
+(NCCL over NVLink on the GPU box, gloo in the CPU tests).  The reference has no counterpart: its user
+loop over samples is serial (examples/notebooks/kduq_uq_demo.ipynb cell 16).
+"""
+from __future__ import annotations
+
+
+def shard_bounds(n_samples: int, world: int, rank: int):
+    """[lo, hi) of rank's contiguous block; blocks differ by at most one sample and cover 0..n_samples."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError("need 0 <= rank < world")
+    if n_samples < 0:
+        raise ValueError("n_samples must be >= 0")
+    return rank * n_samples // world, (rank + 1) * n_samples // world
+
+
+def gather_to_root(shard, n_samples: int, dst: int = 0, group=None):
+    """Gather the per-rank blocks ``shard`` (leading axis = this rank's samples, as cut by
+    ``shard_bounds(n_samples, world, rank)``) into one tensor of leading size ``n_samples`` on rank
+    ``dst``; returns None on the other ranks.  One collective; uneven blocks are padded to the
+    largest block for the transfer and trimmed on the root."""
+    import torch
+    import torch.distributed as dist
+
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return shard
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    sizes = [shard_bounds(n_samples, world, r) for r in range(world)]
+    mx = max(hi - lo for lo, hi in sizes)
+    lo, hi = sizes[rank]
+    if shard.shape[0] != hi - lo:
+        raise ValueError(f"rank {rank}: shard has {shard.shape[0]} samples, expected {hi - lo}")
+    send = shard.contiguous()
+    if hi - lo < mx:
+        pad = torch.zeros((mx - (hi - lo),) + tuple(shard.shape[1:]), dtype=shard.dtype, device=shard.device)
+        send = torch.cat([send, pad], dim=0)
+    bufs = None
+    if rank == dst:
+        bufs = [torch.empty_like(send) for _ in range(world)]
+    dist.gather(send, bufs, dst=dst, group=group)
+    if rank != dst:
+        return None
+    return torch.cat([b[: h - l] for b, (l, h) in zip(bufs, sizes)], dim=0)

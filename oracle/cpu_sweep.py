@@ -37,6 +37,11 @@ def _work(job):
     wss = []
     for (tgt, Elab, Rch, kin) in energies:
         wss.append((tgt, Elab, orc.ElasticWorkspace(N, lmax, Rch, kin, angles, 0)))
+    # untimed warm-up: numba compiles the njit core on the first call in every fresh process (the
+    # reference's users pay this once per session, not per sample)
+    with np.errstate(over="ignore"):
+        c, so, co = orc.kduq_potentials(wss[0][2].rgrid, (1, 0), wss[0][0], wss[0][1], rows[0])
+    wss[0][2].xs(c, so, co)
     setup = time.perf_counter() - t0
     count = [0]
     npairs = 0
