@@ -210,89 +210,113 @@ __global__ void __launch_bounds__(SweepPlan<MODE>::kThreads, 1) elastic_sweep_ke
     const int L1 = A.lmax + 1;
     const double2 zero2 = make_double2(0.0, 0.0);
 
-    for (long long pair = (long long)blockIdx.x * nwarps + warp; pair < A.n_pairs;
-         pair += (long long)gridDim.x * nwarps) {
-        const long long smp = pair / A.n_energies;
-        const int e = (int)(pair - smp * A.n_energies);
-        const double* et = A.etab + (size_t)e * JITR_B200_ET_STRIDE;
-        const double a = et[JITR_B200_ET_A], E0 = et[JITR_B200_ET_ECM], radius = et[JITR_B200_ET_RCH];
-        const double a2 = a * a;
-
-        // ---- potentials on this lane's mesh points, in the a^2-scaled form of the diagonal
-        double2 vc0, vs0, vc1, vs1;
-        if (PARAMS) {
-            const PairPotentials pp =
-                eval_pair_potentials(A.model, A.params + (size_t)smp * A.n_params, et, x0 * radius, x1 * radius);
-            vc0 = pp.vc0; vs0 = pp.vs0; vc1 = pp.vc1; vs1 = pp.vs1;
-        } else {
-            const size_t off = (size_t)pair * N;
-            vc0 = A.central[off + (v0 ? n0 : 0)];
-            vc1 = A.central[off + (v1 ? n1 : 0)];
-            vs0 = vs1 = zero2;
-            if (A.spin_orbit) {
-                vs0 = A.spin_orbit[off + (v0 ? n0 : 0)];
-                vs1 = A.spin_orbit[off + (v1 ? n1 : 0)];
+    // The warps of the CTA advance in lock step, ONE SOLVE PER ITERATION, separated by a CTA barrier
+    // (__syncthreads_or doubles as the termination test).  Every solve executes the same ~55 KB of
+    // unrolled LU code; without the barrier the early break lets the 12 warps drift to unrelated
+    // code regions and the SM's instruction cache thrashes (ncu: 2.5 no-instruction stall cycles per
+    // issued instruction, icc hit rate 63 %); aligned, one warp's fetch serves the other eleven.
+    const long long stride = (long long)gridDim.x * nwarps;
+    long long pair = (long long)blockIdx.x * nwarps + warp;
+    bool active = pair < A.n_pairs;  // warp-uniform
+    bool fresh = true;               // the pair's potentials have not been evaluated yet
+    int e = 0, l = 0, jj = 0, nl = 0, singular = 0, nonfinite = 0;
+    double a = 0.0;
+    double2 d0 = zero2, d1 = zero2, so0 = zero2, so1 = zero2, Splus = zero2;
+    while (__syncthreads_or(active)) {
+        if (!active) continue;
+        if (fresh) {
+            const long long smp = pair / A.n_energies;
+            e = (int)(pair - smp * A.n_energies);
+            const double* et = A.etab + (size_t)e * JITR_B200_ET_STRIDE;
+            a = et[JITR_B200_ET_A];
+            const double E0 = et[JITR_B200_ET_ECM], radius = et[JITR_B200_ET_RCH];
+            const double a2 = a * a;
+            // ---- potentials on this lane's mesh points, in the a^2-scaled form of the diagonal
+            double2 vc0, vs0, vc1, vs1;
+            if (PARAMS) {
+                const PairPotentials pp =
+                    eval_pair_potentials(A.model, A.params + (size_t)smp * A.n_params, et, x0 * radius, x1 * radius);
+                vc0 = pp.vc0; vs0 = pp.vs0; vc1 = pp.vc1; vs1 = pp.vs1;
+            } else {
+                const size_t off = (size_t)pair * N;
+                vc0 = A.central[off + (v0 ? n0 : 0)];
+                vc1 = A.central[off + (v1 ? n1 : 0)];
+                vs0 = vs1 = zero2;
+                if (A.spin_orbit) {
+                    vs0 = A.spin_orbit[off + (v0 ? n0 : 0)];
+                    vs1 = A.spin_orbit[off + (v1 ? n1 : 0)];
+                }
+                if (A.coulomb) {
+                    const double2 c0 = A.coulomb[off + (v0 ? n0 : 0)], c1 = A.coulomb[off + (v1 ? n1 : 0)];
+                    vc0.x += c0.x; vc0.y += c0.y;
+                    vc1.x += c1.x; vc1.y += c1.y;
+                }
             }
-            if (A.coulomb) {
-                const double2 c0 = A.coulomb[off + (v0 ? n0 : 0)], c1 = A.coulomb[off + (v1 ? n1 : 0)];
-                vc0.x += c0.x; vc0.y += c0.y;
-                vc1.x += c1.x; vc1.y += c1.y;
-            }
+            // diag(a^2 A) = That_nn + l(l+1)/x_n^2 + a^2(-1 + V/E0) + (l.s) a^2 Vso/E0
+            d0 = make_double2(t0 + a2 * (vc0.x / E0 - 1.0), a2 * (vc0.y / E0));
+            d1 = make_double2(t1 + a2 * (vc1.x / E0 - 1.0), a2 * (vc1.y / E0));
+            so0 = make_double2(a2 * (vs0.x / E0), a2 * (vs0.y / E0));
+            so1 = make_double2(a2 * (vs1.x / E0), a2 * (vs1.y / E0));
+            l = 0; jj = 0; nl = 0; singular = 0; nonfinite = 0;
+            fresh = false;
         }
-        // diag(a^2 A) = That_nn + l(l+1)/x_n^2 + a^2(-1 + V/E0) + (l.s) a^2 Vso/E0
-        const double2 d0 = make_double2(t0 + a2 * (vc0.x / E0 - 1.0), a2 * (vc0.y / E0));
-        const double2 d1 = make_double2(t1 + a2 * (vc1.x / E0 - 1.0), a2 * (vc1.y / E0));
-        const double2 so0 = make_double2(a2 * (vs0.x / E0), a2 * (vs0.y / E0));
-        const double2 so1 = make_double2(a2 * (vs1.x / E0), a2 * (vs1.y / E0));
-
+        // ---- one system: partial wave l, j = l + 1/2 (jj = 0) or l - 1/2 (jj = 1)
+        const double ll1 = (double)l * (double)(l + 1);
+        const double ls = (jj == 0) ? (double)l : -(double)(l + 1);
+        const double2 dd0 = make_double2(d0.x + ll1 * cent0 + ls * so0.x, d0.y + ls * so0.y);
+        const double2 dd1 = make_double2(d1.x + ll1 * cent1 + ls * so1.x, d1.y + ls * so1.y);
+        // corner = -b^T (a^2 A)^-1 b = -R
+        const double2 corner = solver.solve(dd0, dd1, singular);
+        const double2* as = A.asym + ((size_t)e * L1 + l) * 4;  // (after the solve: fewer live registers)
+        const double2 Hp = as[0], Hm = as[1], Hpp = as[2], Hmp = as[3];
+        const double2 aR = make_double2(-a * corner.x, -a * corner.y);
+        // S = (H- - a R H-') / (H+ - a R H+')   (rmatrix/core.py:51-56 with nch = 1)
+        const double2 t_m = cmul(aR, Hmp), t_p = cmul(aR, Hpp);
+        const double2 num = make_double2(Hm.x - t_m.x, Hm.y - t_m.y);
+        const double2 den = make_double2(Hp.x - t_p.x, Hp.y - t_p.y);
+        const double2 S = cmul(num, crecip_fast(den));
+        if (!(isfinite(S.x) && isfinite(S.y))) nonfinite = 1;
         double2* Sp_out = A.S_out + (size_t)pair * 2 * L1;
         double2* Sm_out = Sp_out + L1;
-        int nl = 0, singular = 0, nonfinite = 0;
-#pragma unroll 1
-        for (int l = 0; l <= A.lmax; ++l) {
-            const double ll1 = (double)l * (double)(l + 1);
-            double2 Sj[2];
-            Sj[1] = zero2;
-            const int nj = (l == 0) ? 1 : 2;
-#pragma unroll 1
-            for (int jj = 0; jj < nj; ++jj) {
-                const double ls = (jj == 0) ? (double)l : -(double)(l + 1);
-                const double2 dd0 = make_double2(d0.x + ll1 * cent0 + ls * so0.x, d0.y + ls * so0.y);
-                const double2 dd1 = make_double2(d1.x + ll1 * cent1 + ls * so1.x, d1.y + ls * so1.y);
-                // corner = -b^T (a^2 A)^-1 b = -R
-                const double2 corner = solver.solve(dd0, dd1, singular);
-                const double2* as = A.asym + ((size_t)e * L1 + l) * 4;  // (after the solve: fewer live registers)
-                const double2 Hp = as[0], Hm = as[1], Hpp = as[2], Hmp = as[3];
-                const double2 aR = make_double2(-a * corner.x, -a * corner.y);
-                // S = (H- - a R H-') / (H+ - a R H+')   (rmatrix/core.py:51-56 with nch = 1)
-                const double2 t_m = cmul(aR, Hmp), t_p = cmul(aR, Hpp);
-                const double2 num = make_double2(Hm.x - t_m.x, Hm.y - t_m.y);
-                const double2 den = make_double2(Hp.x - t_p.x, Hp.y - t_p.y);
-                const double2 S = cmul(num, crecip_fast(den));
-                Sj[jj] = S;
-                if (!(isfinite(S.x) && isfinite(S.y))) nonfinite = 1;
+        bool pair_done = false;
+        if (jj == 0) {
+            Splus = S;
+            if (lane == 0) Sp_out[l] = S;
+            if (l == 0) {  // l = 0 has the single j = 1/2 system; S- [0] = 0 (xs/elastic.py:112,152)
+                if (lane == 0) Sm_out[0] = zero2;
+                nl = 1;
+                pair_done = A.lmax == 0;
+                l = 1;
+            } else {
+                jj = 1;
+            }
+        } else {
+            if (lane == 0) Sm_out[l] = S;
+            nl = l + 1;
+            pair_done = l == A.lmax;
+            if (A.tol > 0.0) {
+                // |1 - S| < tol for both j  (xs/elastic.py:178-181), compared in squares
+                const double ep = 1.0 - Splus.x, em = 1.0 - S.x, tol2 = A.tol * A.tol;
+                const bool small = fma(ep, ep, Splus.y * Splus.y) < tol2 && fma(em, em, S.y * S.y) < tol2;
+                // (the vote keeps every branch of this loop provably warp-uniform for the compiler)
+                if (__all_sync(0xffffffffu, small)) pair_done = true;
+            }
+            l += 1;
+            jj = 0;
+        }
+        if (__any_sync(0xffffffffu, pair_done)) {
+            for (int q = nl + lane; q <= A.lmax; q += 32) {
+                Sp_out[q] = zero2;
+                Sm_out[q] = zero2;
             }
             if (lane == 0) {
-                Sp_out[l] = Sj[0];
-                Sm_out[l] = Sj[1];
+                A.nl_out[pair] = nl;
+                A.status[pair] =
+                    nonfinite ? JITR_B200_STATUS_NONFINITE : (singular ? JITR_B200_STATUS_SINGULAR : JITR_B200_STATUS_OK);
             }
-            nl = l + 1;
-            if (l >= 1 && A.tol > 0.0) {
-                // |1 - S| < tol for both j  (xs/elastic.py:178-181), compared in squares
-                const double ep = 1.0 - Sj[0].x, em = 1.0 - Sj[1].x, tol2 = A.tol * A.tol;
-                const bool small = fma(ep, ep, Sj[0].y * Sj[0].y) < tol2 && fma(em, em, Sj[1].y * Sj[1].y) < tol2;
-                // (a vote makes the exit provably warp-uniform for the compiler: the warp-collective
-                // instructions of the solve are then emitted without divergence guards)
-                if (__all_sync(0xffffffffu, small)) break;
-            }
-        }
-        for (int l = nl + lane; l <= A.lmax; l += 32) {
-            Sp_out[l] = zero2;
-            Sm_out[l] = zero2;
-        }
-        if (lane == 0) {
-            A.nl_out[pair] = nl;
-            A.status[pair] = nonfinite ? JITR_B200_STATUS_NONFINITE : (singular ? JITR_B200_STATUS_SINGULAR : JITR_B200_STATUS_OK);
+            pair += stride;
+            active = pair < A.n_pairs;
+            fresh = true;
         }
     }
 }

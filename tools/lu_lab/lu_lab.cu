@@ -136,6 +136,9 @@ __global__ void __launch_bounds__(384, 1) lab_fast_kernel(const LabArgs A) {
             const int i = 32 * s + lane;
             d[s] = i < N ? dg[i] : make_double2(1.0, 0.0);
         }
+#ifdef LAB_ALIGN
+        __syncthreads();  // keep the warps of the CTA in the same code region (instruction-cache experiment)
+#endif
         const double2 corner = fast_schur<PT>(W, dvec, origv, Tp, bsh, d, lane, singular);
         __syncwarp();
         if (lane == 0) A.out[sys] = corner;
