@@ -168,6 +168,19 @@ int jitr_b200_solve_batched(int nbasis, int nch, long long batch, const double* 
 int jitr_b200_fp64_probe(int which, int iters, int warps_dmma, double* tflops_out_host,
                          long long* lat_out_host);
 
+/*
+ * Library options.  JITR_B200_OPT_SYMMETRIC (default 1): the fused sweep first eliminates each system
+ * with threshold pivoting on the diagonal (|a_kk| >= max_i |a_ik| / 16), which preserves the complex
+ * symmetry of  That + diag(d)  (half the trailing update, no triangular solve, no row interchanges), and
+ * re-solves a system with partial pivoting the first time a diagonal entry fails the test.  0 = always
+ * use partial pivoting.  Both give the reference's S within its tolerance (tests/test_gpu_parity.py).
+ */
+#define JITR_B200_OPT_SYMMETRIC 0
+#define JITR_B200_OPT_COUNT 1
+int jitr_b200_set_option(int key, int value);
+/* systems the symmetric path handed to the partial-pivoting path since load (-1: no device) */
+long long jitr_b200_sym_fallback_count(void);
+
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 long long jitr_b200_launch_count(void);
 

@@ -14,6 +14,7 @@ LIB_PATH = os.environ.get("JITR_B200_LIB") or os.path.join(_HERE, "_lib", "libji
 
 OK, ERR_BAD_ARG, ERR_UNSUPPORTED, ERR_CUDA = 0, 1, 2, 3
 STATUS_OK, STATUS_NONFINITE, STATUS_SINGULAR = 0, 1, 2
+OPT_SYMMETRIC = 0
 MODEL_SHAPE, MODEL_KDUQ, MODEL_CHUQ, MODEL_LOCAL = 0, 1, 2, 3
 MODEL_NPARAMS = {MODEL_SHAPE: 17, MODEL_KDUQ: 40, MODEL_CHUQ: 22, MODEL_LOCAL: 15}
 # per-energy table layout (include/jitr_b200.h)
@@ -32,6 +33,8 @@ SIGNATURES = {
     "jitr_b200_version": (_i, []),
     "jitr_b200_device_ok": (_i, []),
     "jitr_b200_launch_count": (_ll, []),
+    "jitr_b200_set_option": (_i, [_i, _i]),
+    "jitr_b200_sym_fallback_count": (_ll, []),
     "jitr_b200_elastic_sweep_params": (_i, [_i, _i, _i, _ll, _i, _p, _p, _p, _p, _p, _p, _i, _d, _p, _p, _p, _p]),
     "jitr_b200_elastic_sweep_tensors": (_i, [_i, _i, _ll, _i, _p, _p, _p, _p, _p, _p, _p, _p, _d, _p, _p, _p, _p]),
     "jitr_b200_eval_potentials": (_i, [_i, _i, _ll, _i, _p, _p, _p, _i, _p, _p, _p, _p]),

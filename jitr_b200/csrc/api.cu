@@ -32,11 +32,40 @@ int sm_count() {
     return sms;
 }
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+static std::atomic<int> g_options[JITR_B200_OPT_COUNT] = {{1}};
+int option(int key) { return (key >= 0 && key < JITR_B200_OPT_COUNT) ? g_options[key].load() : 0; }
+unsigned long long* fallback_counter() {
+    static unsigned long long* ctr = nullptr;
+    if (!ctr) {
+        if (cudaMalloc(&ctr, sizeof(unsigned long long)) != cudaSuccess) {
+            cudaGetLastError();
+            ctr = nullptr;
+            return nullptr;
+        }
+        cudaMemset(ctr, 0, sizeof(unsigned long long));
+    }
+    return ctr;
+}
 }  // namespace jitr
 
 extern "C" const char* jitr_b200_last_error(void) { return jitr::g_err; }
 extern "C" int jitr_b200_version(void) { return 100; }
 extern "C" long long jitr_b200_launch_count(void) { return jitr::g_launches.load(); }
+extern "C" int jitr_b200_set_option(int key, int value) {
+    if (key < 0 || key >= JITR_B200_OPT_COUNT) return jitr::set_error(JITR_B200_ERR_BAD_ARG, "set_option: unknown key");
+    jitr::g_options[key].store(value);
+    return JITR_B200_OK;
+}
+extern "C" long long jitr_b200_sym_fallback_count(void) {
+    unsigned long long* c = jitr::fallback_counter();
+    if (!c) return -1;
+    unsigned long long v = 0;
+    if (cudaMemcpy(&v, c, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess) {
+        cudaGetLastError();
+        return -1;
+    }
+    return (long long)v;
+}
 extern "C" int jitr_b200_device_ok(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess || n < 1) {

@@ -7,4 +7,6 @@ int set_error(int code, const char* msg);
 int set_cuda_error(const char* where);
 int sm_count();
 void count_launch();
+int option(int key);                    // jitr_b200_set_option values
+unsigned long long* fallback_counter();  // device counter (lazily allocated), nullptr on failure
 }  // namespace jitr

@@ -182,6 +182,8 @@ extern "C" int jitr_b200_elastic_sweep_params(int nbasis, int lmax, int model, l
     a.params = params; a.tol = tol;
     a.S_out = reinterpret_cast<double2*>(S_out); a.nl_out = nl_out; a.status = status;
     a.N = nbasis;
+    a.symmetric = option(JITR_B200_OPT_SYMMETRIC);
+    a.fallbacks = a.symmetric ? fallback_counter() : nullptr;
     return launch_sweep<true>(a, static_cast<cudaStream_t>(stream));
 }
 
@@ -204,6 +206,8 @@ extern "C" int jitr_b200_elastic_sweep_tensors(int nbasis, int lmax, long long n
     a.tol = tol;
     a.S_out = reinterpret_cast<double2*>(S_out); a.nl_out = nl_out; a.status = status;
     a.N = nbasis;
+    a.symmetric = option(JITR_B200_OPT_SYMMETRIC);
+    a.fallbacks = a.symmetric ? fallback_counter() : nullptr;
     return launch_sweep<false>(a, static_cast<cudaStream_t>(stream));
 }
 

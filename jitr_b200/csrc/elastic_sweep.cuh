@@ -10,6 +10,7 @@
 #include "common.cuh"
 #include "jitr_b200.h"
 #include "lu_fast.cuh"
+#include "lu_sym.cuh"
 #include "lu_warp.cuh"
 #include "potentials.cuh"
 #include "sweep_decl.cuh"
@@ -74,7 +75,8 @@ struct GenericSolver {
         bs = b;
     }
     // d0, d1: diagonal entries of rows lane and lane + 32
-    __device__ __forceinline__ double2 solve(const double2 d0, const double2 d1, int& singular) {
+    __device__ __forceinline__ double2 solve(const double2 d0, const double2 d1, int& singular, const bool,
+                                             unsigned long long*) {
         const int P = g.P, LD = g.LD;
         const int n0 = lane, n1 = lane + 32;
         const bool v0 = n0 < N, v1 = n1 < N;
@@ -113,9 +115,17 @@ struct WarpSolver<-2> : GenericSolver<2> {};
 template <>
 struct WarpSolver<-3> : GenericSolver<3> {};
 
+// per-warp shared-memory layout of the fast paths: W (large enough for both the symmetric and the
+// partial-pivoting variant), the diagonal d, the row permutation of the pivoting variant
+template <int PT>
+struct FastLayout {
+    static constexpr int WALLOC = FastGeom<PT>::WALLOC > SymGeom<PT>::WALLOC ? FastGeom<PT>::WALLOC : SymGeom<PT>::WALLOC;
+    static constexpr int WARP_BYTES = WALLOC * 16 + PT * 16 + FastGeom<PT>::ORIG_BYTES;
+};
+
 template <int PT>
 struct SweepPlan {
-    using G = FastGeom<PT>;
+    using G = FastLayout<PT>;
     static constexpr int kShared = (PT * PT + PT) * 8;
     static constexpr int kFit = (kSweepMaxSmem - kShared) / G::WARP_BYTES;
 #ifndef JITR_FAST_WARPS
@@ -130,7 +140,7 @@ struct SweepPlan {
 
 template <int PT>
 struct WarpSolver {
-    using G = FastGeom<PT>;
+    using G = FastLayout<PT>;
     double2* W;
     double2* dvec;
     unsigned char* origv;
@@ -155,10 +165,26 @@ struct WarpSolver {
         Tp = T;
         bsh = b;
     }
-    __device__ __forceinline__ double2 solve(const double2 d0, const double2 d1, int& singular) {
-        double2 d[G::NS0];
-        d[0] = lane < N ? d0 : make_double2(1.0, 0.0);
-        if (G::NS0 > 1) d[G::NS0 - 1] = lane + 32 < N ? d1 : make_double2(1.0, 0.0);
+    // Threshold-pivoted symmetric elimination first (lu_sym.cuh); a system whose diagonal fails the
+    // threshold test is re-solved with partial pivoting (lu_fast.cuh).  `fallbacks` counts those.
+    __device__ __forceinline__ double2 solve(const double2 d0, const double2 d1, int& singular, const bool symmetric,
+                                             unsigned long long* fallbacks) {
+        const double2 one = make_double2(1.0, 0.0);
+        if (symmetric) {
+            constexpr int NS = SymGeom<PT>::NS0;
+            double2 d[NS];
+            d[0] = lane < N ? d0 : one;
+            if (NS > 1) d[NS - 1] = lane + 32 < N ? d1 : one;
+            int fail = 0;
+            const double2 corner = sym_schur<PT>(W, dvec, Tp, bsh, d, lane, fail);
+            __syncwarp();
+            if (!fail) return corner;
+            if (lane == 0 && fallbacks) atomicAdd(fallbacks, 1ULL);
+        }
+        constexpr int NS = FastGeom<PT>::NS0;
+        double2 d[NS];
+        d[0] = lane < N ? d0 : one;
+        if (NS > 1) d[NS - 1] = lane + 32 < N ? d1 : one;
         const double2 corner = fast_schur<PT>(W, dvec, origv, Tp, bsh, d, lane, singular);
         __syncwarp();
         return corner;
@@ -222,7 +248,13 @@ __global__ void __launch_bounds__(SweepPlan<MODE>::kThreads, 1) elastic_sweep_ke
     int e = 0, l = 0, jj = 0, nl = 0, singular = 0, nonfinite = 0;
     double a = 0.0;
     double2 d0 = zero2, d1 = zero2, so0 = zero2, so1 = zero2, Splus = zero2;
-    while (__syncthreads_or(active)) {
+#ifndef JITR_SWEEP_SYNC_EVERY
+#define JITR_SWEEP_SYNC_EVERY 1
+#endif
+    for (unsigned it = 0;; ++it) {
+        if (it % JITR_SWEEP_SYNC_EVERY == 0) {
+            if (!__syncthreads_or(active)) break;
+        }
         if (!active) continue;
         if (fresh) {
             const long long smp = pair / A.n_energies;
@@ -266,7 +298,7 @@ __global__ void __launch_bounds__(SweepPlan<MODE>::kThreads, 1) elastic_sweep_ke
         const double2 dd0 = make_double2(d0.x + ll1 * cent0 + ls * so0.x, d0.y + ls * so0.y);
         const double2 dd1 = make_double2(d1.x + ll1 * cent1 + ls * so1.x, d1.y + ls * so1.y);
         // corner = -b^T (a^2 A)^-1 b = -R
-        const double2 corner = solver.solve(dd0, dd1, singular);
+        const double2 corner = solver.solve(dd0, dd1, singular, A.symmetric != 0, A.fallbacks);
         const double2* as = A.asym + ((size_t)e * L1 + l) * 4;  // (after the solve: fewer live registers)
         const double2 Hp = as[0], Hm = as[1], Hpp = as[2], Hmp = as[3];
         const double2 aR = make_double2(-a * corner.x, -a * corner.y);

@@ -1,0 +1,267 @@
+// Symmetric fast path: threshold-pivoted elimination that keeps the complex symmetry of the system.
+//
+// Every system of the elastic sweep is complex SYMMETRIC,  a^2 A = That + diag(d),  and so is the bordered
+// matrix [[A, b], [b^T, 0]].  As long as the diagonal entry passes the threshold-pivoting test
+//        |a_kk| >= tau * max_{i >= k} |a_ik|          (tau = 2^-JITR_SYM_TAU_LOG2, |.| = |re| + |im|)
+// it is taken as the pivot (classical threshold partial pivoting: every multiplier is bounded by 1/tau),
+// no rows move, and the elimination is A = L D L^T:
+//   * the pivot row is the transpose of the pivot column (no row search result to fetch, no interchanges),
+//   * U12 = D L21^T comes for free (the unscaled column entries), so there is no triangular solve (phase U),
+//   * only the lower triangle of the trailing matrix is updated (20 instead of 30 DMMA tiles at N = 40),
+//   * the border needs no z row: the corner is  -sum_k y_k^2 / d_k.
+// The first time a diagonal entry FAILS the test the factorisation stops and reports it; the caller then
+// solves that system with the general partial-pivoting path (lu_fast.cuh).  On the KDUQ sweep the
+// kinetic diagonal dominates and about 0.2 % of the systems fall back at tau = 1/16
+// (tools/lu_lab/sym_stats.py); the results agree with LAPACK to <= 2e-11 either way.
+//
+// Layout and phases follow lu_fast.cuh / lu_warp.cuh: first panel straight from That (the system never
+// exists as a whole), Schur complement W of order n = PT - 8 with its RHS column in shared memory,
+// panels of 8 columns in registers (one row per lane), trailing update on DMMA in the real representation.
+#pragma once
+#include "lu_warp.cuh"
+
+#ifndef JITR_SYM_TAU_LOG2
+#define JITR_SYM_TAU_LOG2 4
+#endif
+
+namespace jitr {
+
+template <int PT>
+struct SymGeom {
+    static constexpr int n = PT - 8;       // order of the Schur complement kept in W
+    static constexpr int LDW = n + 1;      // odd leading dimension; column n = RHS (no z row)
+    static constexpr int NT = n / 8;
+    static constexpr int NS0 = PT > 32 ? 2 : 1;
+    static constexpr int WSZ = n * LDW;
+    // scratch inside W while the first panel is in flight: L21 and the unscaled columns, rows 8..PT-1
+    static constexpr int LB_LD = 9;
+    static constexpr int LB_OFF = 0;
+    static constexpr int WB_OFF = LB_OFF + n * LB_LD;
+    static constexpr int SCRATCH = WB_OFF + n * LB_LD;
+    static constexpr int WALLOC = WSZ > SCRATCH ? WSZ : SCRATCH;
+    static_assert(n >= 8 && n <= 32, "symmetric fast path covers 16 <= PT <= 40");
+};
+
+// One panel of eight columns, rows i = 32 s + lane (relative to the panel start), nrows of them alive.
+// p[s][0..7] panel columns, p[s][8] the RHS.  The unscaled column entries (= the pivot-row block by
+// symmetry) are handed to `store_w(s, kk, value)` as they become final; on return p[s][k] are the
+// multipliers and p[s][8] the updated RHS.  cacc accumulates the corner; fail is set when a diagonal
+// entry fails the threshold test (or is zero / not finite).
+template <int NS, class StoreW>
+__device__ __forceinline__ void sym_panel_eliminate(double2 (&p)[NS][9], const int nrows, const int lane,
+                                                    double2& cacc, int& fail, StoreW store_w) {
+#pragma unroll
+    for (int kk = 0; kk < 8; ++kk) {
+        // column maximum over the rows at and below the diagonal, and the diagonal's own magnitude
+        double best = -1.0;
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            const int i = 32 * s + lane;
+            const double m = fabs(p[s][kk].x) + fabs(p[s][kk].y);
+            if (i >= kk && i < nrows && m > best) best = m;
+        }
+        const int key = __double2hiint(best);
+        const double2 myrinv = crecip_fast(p[0][kk]);  // speculative: only lane kk's is used
+        const int kmax = __reduce_max_sync(kFull, key);
+        const int dkey = __shfl_sync(kFull, __double2hiint(fabs(p[0][kk].x) + fabs(p[0][kk].y)), kk);
+        // threshold test on the exponent/mantissa word: |d| * 2^TAU >= colmax; dkey <= 0: zero, denormal or NaN
+        if (dkey <= 0 || dkey + (JITR_SYM_TAU_LOG2 << 20) < kmax || kmax >= 0x7ff00000) fail = 1;
+        const double2 rinv = shfl2(myrinv, kk);
+        // pivot row = transposed pivot column (rows kk+1..7 of the panel live in lanes kk+1..7, slot 0)
+        double2 u[9];
+#pragma unroll
+        for (int j = kk + 1; j < 8; ++j) u[j] = shfl2(p[0][kk], j);
+        u[8] = shfl2(p[0][8], kk);
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            store_w(s, kk, p[s][kk]);
+            const double2 l = cmul(p[s][kk], rinv);
+            p[s][kk] = l;
+#pragma unroll
+            for (int j = kk + 1; j < 9; ++j) cfnma(p[s][j], l, u[j]);
+        }
+        // corner -= y_k^2 / d_k
+        cfnma(cacc, cmul(u[8], rinv), u[8]);
+    }
+}
+
+// lower-triangle trailing update of the Schur complement in W after panel J0 (nt <= 3 tile rows)
+__device__ __forceinline__ void sym_trailing_update(double2* __restrict__ M, const int LD, const int J0, const int nt,
+                                                    const int lane) {
+    const int R0 = J0 + 8;
+    const int fr = lane >> 2, fk = lane & 3;
+    const int rho = (fr >> 1) + 4 * (fr & 1);
+    const int part = fk & 1, pn = fr & 1;
+    const double* Md = reinterpret_cast<const double*>(M);
+    const int a_off = 2 * (rho * LD + J0 + 4 * (fk >> 1)) + part;
+    const int b_off = 2 * ((J0 + 4 * (fk >> 1)) * LD + (fr >> 1)) + (part ^ pn);
+    const int bflip = (part & (pn ^ 1)) ? 0x80000000 : 0;
+    const int c_off = rho * LD + R0 + fk;
+    double b[3][2][4];
+#pragma unroll
+    for (int q = 0; q < 3; ++q)
+        if (q < nt) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int s = 0; s < 4; ++s) {
+                    const double v = Md[b_off + 2 * (s * LD + R0 + 8 * q + 4 * h)];
+                    b[q][h][s] = __hiloint2double(__double2hiint(v) ^ bflip, __double2loint(v));
+                }
+        }
+#pragma unroll 1
+    for (int tr = 0; tr < nt; ++tr) {
+        const int rbase = (R0 + 8 * tr) * LD;
+        double a[4];
+#pragma unroll
+        for (int s = 0; s < 4; ++s) a[s] = dneg(Md[a_off + 2 * (rbase + s)]);
+        double2* Crow = M + rbase + c_off;
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+            if (q <= tr) {  // lower triangle (diagonal tiles in full)
+                double2 c0 = Crow[8 * q], c1 = Crow[8 * q + 4];
+#pragma unroll
+                for (int s = 0; s < 4; ++s) {
+                    dmma884(c0.x, c0.y, a[s], b[q][0][s]);
+                    dmma884(c1.x, c1.y, a[s], b[q][1][s]);
+                }
+                Crow[8 * q] = c0;
+                Crow[8 * q + 4] = c1;
+            }
+    }
+}
+
+// Returns -b^T (That + diag d)^-1 b on every lane; fail != 0: a pivot failed the threshold test and the
+// returned value is meaningless.  Arguments as fast_schur (lu_fast.cuh); W needs SymGeom<PT>::WALLOC elements.
+template <int PT>
+__device__ __forceinline__ double2 sym_schur(double2* __restrict__ W, double2* __restrict__ dvec,
+                                             const double* __restrict__ Tp, const double* __restrict__ bsh,
+                                             const double2 (&d)[SymGeom<PT>::NS0], const int lane, int& fail) {
+    using G = SymGeom<PT>;
+    constexpr int NS = G::NS0, n = G::n, LDW = G::LDW, NT = G::NT;
+    JITR_PH_INIT
+    double2 cacc = make_double2(0.0, 0.0);
+    // ------------------------------------------------------------------ first panel, from That
+    {
+        double2 p[NS][9];
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            const int i = 32 * s + lane;
+            const bool ex = i < PT;
+            const int ic = ex ? i : 0;
+            if (ex) dvec[i] = d[s];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const double t = Tp[j * PT + ic];  // That is symmetric: conflict-free read across the lanes
+                p[s][j] = (i == j) ? d[s] : make_double2(t, 0.0);
+            }
+            p[s][8] = make_double2(bsh[ic], 0.0);
+        }
+        sym_panel_eliminate<NS>(p, PT, lane, cacc, fail, [&](int s, int kk, double2 v) {
+            const int i = 32 * s + lane;
+            if (i >= 8 && i < PT) W[G::WB_OFF + (i - 8) * G::LB_LD + kk] = v;
+        });
+        double2 ykeep[NS];
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            const int i = 32 * s + lane;
+            ykeep[s] = p[s][8];
+            if (i >= 8 && i < PT) {
+                double2* dst = W + G::LB_OFF + (i - 8) * G::LB_LD;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) dst[j] = p[s][j];
+            }
+        }
+        __syncwarp();
+        JITR_PH(0)
+        // ---- trailing update: W[r][c] = That[8+r][8+c] + d - sum_k L[r][k] w[c][k], lower tiles only
+        const int fr = lane >> 2, fk = lane & 3;
+        const int rho = (fr >> 1) + 4 * (fr & 1);
+        const int part = fk & 1, pn = fr & 1;
+        const int bflip = (part & (pn ^ 1)) ? 0x80000000 : 0;
+        const double* Wd = reinterpret_cast<const double*>(W);
+        double b[NT][2][4], a[NT][4];
+#pragma unroll
+        for (int q = 0; q < NT; ++q)
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int s = 0; s < 4; ++s) {
+                    const double v =
+                        Wd[2 * (G::WB_OFF + (8 * q + 4 * h + (fr >> 1)) * G::LB_LD + s + 4 * (fk >> 1)) + (part ^ pn)];
+                    b[q][h][s] = __hiloint2double(__double2hiint(v) ^ bflip, __double2loint(v));
+                }
+#pragma unroll
+        for (int tr = 0; tr < NT; ++tr)
+#pragma unroll
+            for (int s = 0; s < 4; ++s)
+                a[tr][s] = dneg(Wd[2 * (G::LB_OFF + (8 * tr + rho) * G::LB_LD + s + 4 * (fk >> 1)) + part]);
+        __syncwarp();  // every fragment is in registers: the scratch may be overwritten
+#pragma unroll
+        for (int tr = 0; tr < NT; ++tr) {
+            const int row = 8 + 8 * tr + rho;
+            double2 c[NT][2];
+#pragma unroll
+            for (int q = 0; q <= tr; ++q)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int col = 8 + 8 * q + 4 * h + fk;
+                    c[q][h] = (row == col) ? dvec[col] : make_double2(Tp[col * PT + row], 0.0);
+                }
+#pragma unroll
+            for (int s = 0; s < 4; ++s)
+#pragma unroll
+                for (int q = 0; q <= tr; ++q) {
+                    dmma884(c[q][0].x, c[q][0].y, a[tr][s], b[q][0][s]);
+                    dmma884(c[q][1].x, c[q][1].y, a[tr][s], b[q][1][s]);
+                }
+            double2* Crow = W + (8 * tr + rho) * LDW + fk;
+#pragma unroll
+            for (int q = 0; q <= tr; ++q) {
+                Crow[8 * q] = c[q][0];
+                Crow[8 * q + 4] = c[q][1];
+            }
+        }
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            const int i = 32 * s + lane;
+            if (i >= 8 && i < PT) W[(i - 8) * LDW + n] = ykeep[s];
+        }
+        __syncwarp();
+        JITR_PH(2)
+    }
+    // ------------------------------------------------------------------ panels of the Schur complement in W
+#pragma unroll 1
+    for (int J0 = 0; J0 < n; J0 += 8) {
+        const int nrows = n - J0;  // <= 32: one row per lane
+        double2 p[1][9];
+        {
+            const int row = J0 + (lane < nrows ? lane : 0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) p[0][j] = W[row * LDW + J0 + j];
+            p[0][8] = W[row * LDW + n];
+        }
+        sym_panel_eliminate<1>(p, nrows, lane, cacc, fail, [&](int, int kk, double2 v) {
+            // the unscaled column entry of row J0 + lane is U12[kk][lane - 8]: its natural (upper) position
+            if (lane >= 8 && lane < nrows) W[(J0 + kk) * LDW + J0 + lane] = v;
+        });
+        if (nrows <= 8) {
+            JITR_PH(0)
+            break;
+        }
+        if (lane >= 8 && lane < nrows) {
+            double2* dst = W + (J0 + lane) * LDW;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dst[J0 + j] = p[0][j];
+            dst[n] = p[0][8];
+        }
+        __syncwarp();
+        JITR_PH(0)
+        sym_trailing_update(W, LDW, J0, (nrows - 8) >> 3, lane);
+        __syncwarp();
+        JITR_PH(2)
+    }
+    return cacc;
+}
+
+}  // namespace jitr

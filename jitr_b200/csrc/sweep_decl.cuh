@@ -6,6 +6,8 @@ namespace jitr {
 
 struct SweepArgs {
     int N, lmax, model, n_energies, n_params;
+    int symmetric;                  // try the threshold-pivoted symmetric elimination first (fast paths)
+    unsigned long long* fallbacks;  // device counter of systems re-solved with partial pivoting
     long long n_pairs;
     const double* That;
     const double* mesh_x;

@@ -23,6 +23,9 @@ __device__ unsigned long long g_phase[8];
 #ifdef LAB_FAST
 #include "lu_fast.cuh"
 #endif
+#ifdef LAB_SYM
+#include "lu_sym.cuh"
+#endif
 
 using namespace jitr;
 
@@ -147,6 +150,48 @@ __global__ void __launch_bounds__(384, 1) lab_fast_kernel(const LabArgs A) {
 }
 #endif
 
+#ifdef LAB_SYM
+template <int PT>
+__global__ void __launch_bounds__(384, 1) lab_sym_kernel(const LabArgs A) {
+    using G = SymGeom<PT>;
+    constexpr int WARP_BYTES = G::WALLOC * 16 + PT * 16;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int N = A.N;
+    const int nwarps = blockDim.x >> 5;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
+    double* Tp = reinterpret_cast<double*>(smem_raw);
+    double* bsh = Tp + PT * PT;
+    unsigned char* wbase = smem_raw + (PT * PT + PT) * 8 + (size_t)warp * WARP_BYTES;
+    double2* W = reinterpret_cast<double2*>(wbase);
+    double2* dvec = W + G::WALLOC;
+    for (int i = threadIdx.x; i < PT * PT; i += blockDim.x) {
+        const int r = i / PT, c = i - r * PT;
+        Tp[i] = (r < N && c < N) ? A.That[r * N + c] : (r == c ? 1.0 : 0.0);
+    }
+    for (int i = threadIdx.x; i < PT; i += blockDim.x) bsh[i] = i < N ? A.bvec[i] : 0.0;
+    __syncthreads();
+    int nfail = 0;
+    for (long long sys = (long long)blockIdx.x * nwarps + warp; sys < A.B; sys += (long long)gridDim.x * nwarps) {
+        const double2* dg = A.diag + (size_t)(sys % A.K) * N;
+        double2 d[G::NS0];
+#pragma unroll
+        for (int s = 0; s < G::NS0; ++s) {
+            const int i = 32 * s + lane;
+            d[s] = i < N ? dg[i] : make_double2(1.0, 0.0);
+        }
+#ifdef LAB_ALIGN
+        __syncthreads();
+#endif
+        int fail = 0;
+        const double2 corner = sym_schur<PT>(W, dvec, Tp, bsh, d, lane, fail);
+        __syncwarp();
+        if (lane == 0) A.out[sys] = corner;
+        nfail += fail;
+    }
+    if (lane == 0 && nfail) atomicAdd(A.sing, nfail);
+}
+#endif
+
 int main(int argc, char** argv) {
     if (argc < 2) {
         fprintf(stderr, "usage: lu_lab data.bin [systems_per_warp] [warps_per_cta]\n");
@@ -178,6 +223,13 @@ int main(int argc, char** argv) {
     const int smem = (PT * PT + PT) * 8 + warps * FastGeom<PT>::WARP_BYTES;
     if (smem > maxs) { fprintf(stderr, "smem %d > %d\n", smem, maxs); return 1; }
 #define lab_kernel lab_fast_kernel<PT>
+#elif defined(LAB_SYM)
+    constexpr int PT = 40;
+    if (P != PT) { fprintf(stderr, "LAB_SYM is built for P = %d\n", PT); return 1; }
+    warps = argc > 3 ? atoi(argv[3]) : 12;
+    const int smem = (PT * PT + PT) * 8 + warps * (SymGeom<PT>::WALLOC * 16 + PT * 16);
+    if (smem > maxs) { fprintf(stderr, "smem %d > %d\n", smem, maxs); return 1; }
+#define lab_kernel lab_sym_kernel<PT>
 #else
     const int smem = warps * msz * 16 + N * N * 8;
 #endif
