@@ -251,6 +251,7 @@ def main():
     sync_all()
     clocks = ClockSampler(local) if rank == 0 else None
     launches0 = L.jitr_b200_launch_count()
+    fallbacks0 = L.jitr_b200_sym_fallback_count()
     t_wall0 = time.time()
     t_sweep = t_obs = 0.0
     e_begin, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -265,6 +266,7 @@ def main():
     sync_all()
     t_wall1 = time.time()
     launches = L.jitr_b200_launch_count() - launches0
+    fallbacks = L.jitr_b200_sym_fallback_count() - fallbacks0
     total_ms = e_begin.elapsed_time(e_end)
     for evs in per_step_events:
         t_sweep += evs[0].elapsed_time(evs[1])
@@ -357,6 +359,9 @@ def main():
         "config": workload_config(args.samples, world),
         "samples_per_s": S_total * nE / (ms_per_step * 1e-3),
         "solves_per_pair": all_solves / (S_total * nE),
+        "pivoting": {"scheme": "threshold pivoting on the diagonal (tau = 1/16, symmetric LDL^T), partial-pivoting LU on failure",
+                     "partial_pivoting_fallbacks_per_step_rank0": int(fallbacks // max(args.steps, 1)),
+                     "fallback_fraction": float(fallbacks) / max(args.steps, 1) / max(my_solves, 1)},
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu_baseline,
     }
     print(json.dumps(line))

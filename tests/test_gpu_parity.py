@@ -215,6 +215,71 @@ def test_no_early_break_and_size_independent_properties():
     assert float(S[:, 1, 0].abs().max()) == 0.0
 
 
+def test_partial_pivoting_only_option_matches(golden):
+    """JITR_B200_OPT_SYMMETRIC = 0 forces partial pivoting for every system; both pivoting schemes must
+    give the reference's S (the symmetric threshold-pivoted path is the default)."""
+    g = golden("config1_n208Pb_30MeV")
+    rx, kin, ws = make_ws(g)
+    model = model_for("config1_n208Pb_30MeV", g)
+    params = torch.tensor(g["params"], dtype=torch.float64, device="cuda")
+    L = _cabi.lib()
+    try:
+        assert L.jitr_b200_set_option(_cabi.OPT_SYMMETRIC, 0) == 0
+        S0, nl0, st0 = ws.integral_workspace.smatrix_params(model, params)
+        x0 = ws.xs_params(model, params)
+    finally:
+        assert L.jitr_b200_set_option(_cabi.OPT_SYMMETRIC, 1) == 0
+    S1, nl1, st1 = ws.integral_workspace.smatrix_params(model, params)
+    x1 = ws.xs_params(model, params)
+    assert int(st0.abs().sum()) == 0 and int(st1.abs().sum()) == 0
+    check_xs_against_golden(x0, S0, nl0, g, range(len(g["params"])))
+    check_xs_against_golden(x1, S1, nl1, g, range(len(g["params"])))
+    assert torch.equal(nl0, nl1)
+    assert L.jitr_b200_set_option(99, 0) == _cabi.ERR_BAD_ARG
+
+
+def test_symmetric_path_falls_back_to_partial_pivoting():
+    """A diagonal entry that fails the threshold test (|a_kk| < max_i |a_ik| / 16) must send the system
+    to the partial-pivoting path: a potential tuned so that the FIRST diagonal entry a^2 A[0][0] is tiny
+    against its column at one partial wave (later diagonal entries are Schur complements and cannot be
+    tuned from the potential alone)."""
+    N, lmax = 40, 6
+    rx = ElasticReaction((40, 20), (1, 0), mass_target=37214.69, mass_projectile=939.5654983938299)
+    kin = rx.kinematics(20.0)
+    angles = np.linspace(0.2, 3.0, 31)
+    ws = jitr_b200.DifferentialWorkspace.build_from_system(rx, kin, 10.0, jitr_b200.Solver(N), lmax, angles, smatrix_abs_tol=0.0)
+    iw = ws.integral_workspace
+    q = iw.solver.kernel.quadrature
+    That = q.kinetic_hat()
+    a, Ecm = iw.a, kin.Ecm
+    r = iw.radial_grid()
+    rng = np.random.default_rng(11)
+    B = 24
+    c = np.zeros((B, N), dtype=np.complex128)
+    for bidx in range(B):
+        base = -45.0 / (1.0 + np.exp((r - 4.2) / 0.65)) * (1.0 + 0.2j)
+        k = 0
+        l = int(rng.integers(0, lmax + 1))
+        # a^2 A[k][k] = That_kk + l(l+1)/x_k^2 + a^2 (V_k / Ecm - 1)  ->  small at partial wave l
+        base[k] = Ecm * (1.0 - (That[k, k] + l * (l + 1) / q.abscissa[k] ** 2 - 10.0 ** rng.uniform(-3, 1)) / a**2)
+        c[bidx] = base
+    L = _cabi.lib()
+    f0 = L.jitr_b200_sym_fallback_count()
+    S, nl, status = iw.smatrix_batch(torch.tensor(c, device="cuda"))
+    x = ws.xs_batch(torch.tensor(c, device="cuda"))
+    f1 = L.jitr_b200_sym_fallback_count()
+    assert f1 - f0 >= B, "the tuned systems did not take the partial-pivoting fallback"
+    assert int(status.abs().sum()) == 0
+    ow = orc.ElasticWorkspace(N, lmax, 10.0, tuple(kin), angles, 0, tol=0.0)
+    Sg = S.cpu().numpy()
+    for bidx in range(B):
+        sp, sm = ow.smatrix(c[bidx])
+        assert relerr(Sg[bidx, 0, : len(sp)], sp) < RTOL_S
+        assert relerr(Sg[bidx, 1, 1 : len(sm)], sm[1:]) < RTOL_S
+        dsdo = ow.xs(c[bidx])[0]
+        assert relerr(x.dsdo[bidx].cpu().numpy(), dsdo) < RTOL_XS
+
+
 # ------------------------------------------------------------------ general Solver.solve path
 def test_solver_solve_local_rk_case(golden):
     """restated tests/test_local.py (the RK45 cross-check case) against the reference's own S."""
