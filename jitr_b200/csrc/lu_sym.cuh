@@ -21,7 +21,7 @@
 #include "lu_warp.cuh"
 
 #ifndef JITR_SYM_TAU_LOG2
-#define JITR_SYM_TAU_LOG2 4
+#define JITR_SYM_TAU_LOG2 6
 #endif
 
 namespace jitr {
@@ -36,53 +36,73 @@ struct SymGeom {
     // scratch inside W while the first panel is in flight: L21 and the unscaled columns, rows 8..PT-1
     static constexpr int LB_LD = 9;
     static constexpr int LB_OFF = 0;
-    static constexpr int WB_OFF = LB_OFF + n * LB_LD;
-    static constexpr int SCRATCH = WB_OFF + n * LB_LD;
+    static constexpr int WB_OFF = LB_OFF + n * LB_LD;  // unscaled columns of ALL rows 0..PT-1 (rows < 8: pivot block)
+    static constexpr int SCRATCH = WB_OFF + PT * LB_LD;
     static constexpr int WALLOC = WSZ > SCRATCH ? WSZ : SCRATCH;
     static_assert(n >= 8 && n <= 32, "symmetric fast path covers 16 <= PT <= 40");
 };
 
 // One panel of eight columns, rows i = 32 s + lane (relative to the panel start), nrows of them alive.
 // p[s][0..7] panel columns, p[s][8] the RHS.  The unscaled column entries (= the pivot-row block by
-// symmetry) are handed to `store_w(s, kk, value)` as they become final; on return p[s][k] are the
-// multipliers and p[s][8] the updated RHS.  cacc accumulates the corner; fail is set when a diagonal
-// entry fails the threshold test (or is zero / not finite).
-template <int NS, class StoreW>
+// symmetry) are handed to `store_w(s, kk, value)` as they become final -- for every row below the
+// diagonal -- and the pivot row is read back with `load_u(kk, j)` (entry of row j > kk, a shared-memory
+// broadcast: 2 SM-cycles against the 4 of a 128-bit shuffle; the store is issued anyway).  On return
+// p[s][k] are the multipliers and p[s][8] the updated RHS.  cacc accumulates the corner; fail is set when
+// a diagonal entry fails the threshold test (or is zero / not finite).
+template <int NS, class StoreW, class LoadU>
 __device__ __forceinline__ void sym_panel_eliminate(double2 (&p)[NS][9], const int nrows, const int lane,
-                                                    double2& cacc, int& fail, StoreW store_w) {
+                                                    double2& cacc, int& fail, StoreW store_w, LoadU load_u) {
+    // lane k (k < 8) keeps y_k and 1/d_k of "its" pivot for the corner term, formed once per panel
+    double2 ysave = make_double2(0.0, 0.0), rsave = make_double2(0.0, 0.0);
+    int myfail = 0;
 #pragma unroll
     for (int kk = 0; kk < 8; ++kk) {
-        // column maximum over the rows at and below the diagonal, and the diagonal's own magnitude
-        double best = -1.0;
+        // column maximum over the rows at and below the diagonal, on the high words of max(|re|, |im|)
+        // (integer pipe; within a factor 2 of |re| + |im|, which is all a threshold test needs)
+        int key = -1, key0 = 0;
 #pragma unroll
         for (int s = 0; s < NS; ++s) {
             const int i = 32 * s + lane;
-            const double m = fabs(p[s][kk].x) + fabs(p[s][kk].y);
-            if (i >= kk && i < nrows && m > best) best = m;
+            const int m = max(__double2hiint(p[s][kk].x) & 0x7fffffff, __double2hiint(p[s][kk].y) & 0x7fffffff);
+            if (s == 0) key0 = m;
+            if (i >= kk && i < nrows) key = max(key, m);
         }
-        const int key = __double2hiint(best);
         const double2 myrinv = crecip_fast(p[0][kk]);  // speculative: only lane kk's is used
         const int kmax = __reduce_max_sync(kFull, key);
-        const int dkey = __shfl_sync(kFull, __double2hiint(fabs(p[0][kk].x) + fabs(p[0][kk].y)), kk);
-        // threshold test on the exponent/mantissa word: |d| * 2^TAU >= colmax; dkey <= 0: zero, denormal or NaN
-        if (dkey <= 0 || dkey + (JITR_SYM_TAU_LOG2 << 20) < kmax || kmax >= 0x7ff00000) fail = 1;
-        const double2 rinv = shfl2(myrinv, kk);
-        // pivot row = transposed pivot column (rows kk+1..7 of the panel live in lanes kk+1..7, slot 0)
-        double2 u[9];
+        // threshold test by the diagonal's own lane: |d| * 2^TAU >= colmax; zero, denormal, Inf or NaN fail
+        if (lane == kk) {
+            if (key0 < 0x00100000 || key0 + (JITR_SYM_TAU_LOG2 << 20) < kmax || kmax >= 0x7ff00000) myfail = 1;
+            ysave = p[0][8];
+            rsave = myrinv;
+        }
 #pragma unroll
-        for (int j = kk + 1; j < 8; ++j) u[j] = shfl2(p[0][kk], j);
+        for (int s = 0; s < NS; ++s) store_w(s, kk, p[s][kk]);
+        const double2 rinv = shfl2(myrinv, kk);
+        double2 u[9];
         u[8] = shfl2(p[0][8], kk);
+        __syncwarp();
+        // pivot row = transposed pivot column: the entries the rows kk+1..7 have just stored
+#pragma unroll
+        for (int j = kk + 1; j < 8; ++j) u[j] = load_u(kk, j);
 #pragma unroll
         for (int s = 0; s < NS; ++s) {
-            store_w(s, kk, p[s][kk]);
             const double2 l = cmul(p[s][kk], rinv);
             p[s][kk] = l;
 #pragma unroll
             for (int j = kk + 1; j < 9; ++j) cfnma(p[s][j], l, u[j]);
         }
-        // corner -= y_k^2 / d_k
-        cfnma(cacc, cmul(u[8], rinv), u[8]);
     }
+    // corner -= sum_k y_k^2 / d_k : one term per lane k < 8, summed over the eight lanes
+    double2 term = cmul(cmul(ysave, rsave), ysave);
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+        term.x += __shfl_xor_sync(kFull, term.x, o);
+        term.y += __shfl_xor_sync(kFull, term.y, o);
+    }
+    const double2 tot = shfl2(term, 0);  // lanes >= 8 hold zeros: take the sum from the first group
+    cacc.x -= tot.x;
+    cacc.y -= tot.y;
+    if (__any_sync(kFull, myfail)) fail = 1;
 }
 
 // lower-triangle trailing update of the Schur complement in W after panel J0 (nt <= 3 tile rows)
@@ -157,10 +177,13 @@ __device__ __forceinline__ double2 sym_schur(double2* __restrict__ W, double2* _
             }
             p[s][8] = make_double2(bsh[ic], 0.0);
         }
-        sym_panel_eliminate<NS>(p, PT, lane, cacc, fail, [&](int s, int kk, double2 v) {
-            const int i = 32 * s + lane;
-            if (i >= 8 && i < PT) W[G::WB_OFF + (i - 8) * G::LB_LD + kk] = v;
-        });
+        sym_panel_eliminate<NS>(
+            p, PT, lane, cacc, fail,
+            [&](int s, int kk, double2 v) {
+                const int i = 32 * s + lane;
+                if (i > kk && i < PT) W[G::WB_OFF + i * G::LB_LD + kk] = v;
+            },
+            [&](int kk, int j) { return W[G::WB_OFF + j * G::LB_LD + kk]; });
         double2 ykeep[NS];
 #pragma unroll
         for (int s = 0; s < NS; ++s) {
@@ -188,7 +211,7 @@ __device__ __forceinline__ double2 sym_schur(double2* __restrict__ W, double2* _
 #pragma unroll
                 for (int s = 0; s < 4; ++s) {
                     const double v =
-                        Wd[2 * (G::WB_OFF + (8 * q + 4 * h + (fr >> 1)) * G::LB_LD + s + 4 * (fk >> 1)) + (part ^ pn)];
+                        Wd[2 * (G::WB_OFF + (8 + 8 * q + 4 * h + (fr >> 1)) * G::LB_LD + s + 4 * (fk >> 1)) + (part ^ pn)];
                     b[q][h][s] = __hiloint2double(__double2hiint(v) ^ bflip, __double2loint(v));
                 }
 #pragma unroll
@@ -241,10 +264,13 @@ __device__ __forceinline__ double2 sym_schur(double2* __restrict__ W, double2* _
             for (int j = 0; j < 8; ++j) p[0][j] = W[row * LDW + J0 + j];
             p[0][8] = W[row * LDW + n];
         }
-        sym_panel_eliminate<1>(p, nrows, lane, cacc, fail, [&](int, int kk, double2 v) {
-            // the unscaled column entry of row J0 + lane is U12[kk][lane - 8]: its natural (upper) position
-            if (lane >= 8 && lane < nrows) W[(J0 + kk) * LDW + J0 + lane] = v;
-        });
+        sym_panel_eliminate<1>(
+            p, nrows, lane, cacc, fail,
+            [&](int, int kk, double2 v) {
+                // the unscaled column entry of row J0 + lane is U[kk][lane]: its natural (upper) position
+                if (lane > kk && lane < nrows) W[(J0 + kk) * LDW + J0 + lane] = v;
+            },
+            [&](int kk, int j) { return W[(J0 + kk) * LDW + J0 + j]; });
         if (nrows <= 8) {
             JITR_PH(0)
             break;
