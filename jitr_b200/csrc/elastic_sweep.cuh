@@ -17,7 +17,7 @@
 
 namespace jitr {
 
-constexpr int kSweepMaxSmem = 232448;  // max dynamic shared memory per block on sm_100
+constexpr int kSweepMaxSmem = 232448 - 64;  // max dynamic shared memory per block on sm_100, less the static part
 
 // ---------------------------------------------------------------------------------------------
 // Per-warp solver of one system  a^2 A = That + diag(d):  returns -b^T (a^2 A)^-1 b.
@@ -180,6 +180,10 @@ struct WarpSolver {
             __syncwarp();
             if (!fail) return corner;
             if (lane == 0 && fallbacks) atomicAdd(fallbacks, 1ULL);
+#ifdef JITR_EXPERIMENT_NO_FALLBACK
+            singular = 1;
+            return corner;
+#endif
         }
         constexpr int NS = FastGeom<PT>::NS0;
         double2 d[NS];
@@ -223,9 +227,7 @@ struct LockStep {
     __device__ __forceinline__ void arrive(int b, int lane) const {
         __syncwarp();
         if (lane == 0) {
-            unsigned long long state;
-            asm volatile("mbarrier.arrive.shared::cta.b64 %0, [%1];" : "=l"(state) : "r"(bar[b]) : "memory");
-            (void)state;
+            asm volatile("{ .reg .b64 st; mbarrier.arrive.shared::cta.b64 st, [%0]; }" ::"r"(bar[b]) : "memory");
         }
     }
 };

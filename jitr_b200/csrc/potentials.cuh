@@ -40,23 +40,25 @@ __device__ __forceinline__ void ws_forms(double r, double R, double a, double& f
 }
 
 __device__ __forceinline__ void eval_shape(const Shape& s, double r, double2& vc, double2& vso, double& vcoul) {
-    double f, fp;
-    ws_forms(r, s.Rv, s.av, f, fp);
-    double re = -s.Vv * f;
-    ws_forms(r, s.Rw, s.aw, f, fp);
-    double im = -s.Wv * f;
-    ws_forms(r, s.Rd, s.ad, f, fp);
+    // The built-in models share geometries between terms (KDUQ: volume real/imaginary and both
+    // spin-orbit terms; CHUQ: imaginary volume/surface; Local: both spin-orbit terms): each distinct
+    // (R, a) is evaluated once.  The comparisons are warp-uniform.
+    double fv, fpv, fw, fpw, fd, fpd, fs, fps, fws, fpws;
+    ws_forms(r, s.Rv, s.av, fv, fpv);
+    if (s.Rw == s.Rv && s.aw == s.av) { fw = fv; fpw = fpv; } else ws_forms(r, s.Rw, s.aw, fw, fpw);
+    if (s.Rd == s.Rw && s.ad == s.aw) { fd = fw; fpd = fpw; } else ws_forms(r, s.Rd, s.ad, fd, fpd);
+    ws_forms(r, s.Rso, s.aso, fs, fps);
+    if (s.Rwso == s.Rso && s.awso == s.aso) { fws = fs; fpws = fps; } else ws_forms(r, s.Rwso, s.awso, fws, fpws);
+    (void)fd; (void)fs; (void)fws;
+    double re = -s.Vv * fv;
+    double im = -s.Wv * fw;
     // - (-4 ad) Vd f'  - i (-4 ad) Wd f'   (omp.py:68-73, kduq.py:163-167)
-    re -= (-4.0 * s.ad) * s.Vd * fp;
-    im -= (-4.0 * s.ad) * s.Wd * fp;
+    re -= (-4.0 * s.ad) * s.Vd * fpd;
+    im -= (-4.0 * s.ad) * s.Wd * fpd;
     vc = make_double2(re, im);
     // thomas_safe = (1/r) f'  (potential_forms.py:70-88)
     double y = 1.0 / r;
-    ws_forms(r, s.Rso, s.aso, f, fp);
-    double sre = s.Vso * (y * fp);
-    ws_forms(r, s.Rwso, s.awso, f, fp);
-    double sim = s.Wso * (y * fp);
-    vso = make_double2(sre, sim);
+    vso = make_double2(s.Vso * (y * fps), s.Wso * (y * fpws));
     if (s.Zz == 0.0) {
         vcoul = 0.0;
     } else {
