@@ -58,10 +58,17 @@ struct GenericSolver {
     const double* bs;
     LuGeom g;
     int N, lane;
-    __device__ __forceinline__ void init(unsigned char* smem, const double* That, const double* bvec, int N_, int nwarps,
-                                         int warp, int lane_) {
+    const double* mx;
+    __device__ __forceinline__ void centrifugal(double& c0, double& c1) const {
+        const double x0 = mx[lane < N ? lane : 0], x1 = mx[lane + 32 < N ? lane + 32 : 0];
+        c0 = 1.0 / (x0 * x0);
+        c1 = 1.0 / (x1 * x1);
+    }
+    __device__ __forceinline__ void init(unsigned char* smem, const double* That, const double* bvec,
+                                         const double* mesh_x, int N_, int nwarps, int warp, int lane_) {
         N = N_;
         lane = lane_;
+        mx = mesh_x;
         g.N = N;
         g.P = (N + 7) & ~7;
         g.LD = g.P + 1;
@@ -126,7 +133,7 @@ struct FastLayout {
 template <int PT>
 struct SweepPlan {
     using G = FastLayout<PT>;
-    static constexpr int kShared = (PT * PT + PT) * 8;
+    static constexpr int kShared = (PT * PT + PT + PT) * 8;
     static constexpr int kFit = (kSweepMaxSmem - kShared) / G::WARP_BYTES;
 #ifndef JITR_FAST_WARPS
 #define JITR_FAST_WARPS 16
@@ -141,34 +148,45 @@ struct SweepPlan {
 template <int PT>
 struct WarpSolver {
     using G = FastLayout<PT>;
-    double2* W;
-    double2* dvec;
-    unsigned char* origv;
-    const double* Tp;
-    const double* bsh;
+    // only a byte offset is kept in registers; the pointers are re-derived from the dynamic shared
+    // memory base at every solve (register pressure is what limits this kernel to 168 registers)
+    unsigned wofs;
     int N, lane;
-    __device__ __forceinline__ void init(unsigned char* smem, const double* That, const double* bvec, int N_, int nwarps,
-                                         int warp, int lane_) {
+    static constexpr int kShared = (PT * PT + PT + PT) * 8;  // That (padded), b, 1/x^2
+    __device__ __forceinline__ void init(unsigned char* smem, const double* That, const double* bvec,
+                                         const double* mesh_x, int N_, int nwarps, int warp, int lane_) {
         N = N_;
         lane = lane_;
         double* T = reinterpret_cast<double*>(smem);
         double* b = T + PT * PT;
-        unsigned char* wbase = smem + SweepPlan<PT>::kShared + (size_t)warp * G::WARP_BYTES;
-        W = reinterpret_cast<double2*>(wbase);
-        dvec = W + G::WALLOC;
-        origv = reinterpret_cast<unsigned char*>(dvec + PT);
+        double* c = b + PT;
+        wofs = kShared + warp * G::WARP_BYTES;
         for (int i = threadIdx.x; i < PT * PT; i += blockDim.x) {  // That padded with the identity
-            const int r = i / PT, c = i - r * PT;
-            T[i] = (r < N && c < N) ? That[r * N + c] : (r == c ? 1.0 : 0.0);
+            const int r = i / PT, cc = i - r * PT;
+            T[i] = (r < N && cc < N) ? That[r * N + cc] : (r == cc ? 1.0 : 0.0);
         }
-        for (int i = threadIdx.x; i < PT; i += blockDim.x) b[i] = i < N ? bvec[i] : 0.0;
-        Tp = T;
-        bsh = b;
+        for (int i = threadIdx.x; i < PT; i += blockDim.x) {
+            b[i] = i < N ? bvec[i] : 0.0;
+            c[i] = i < N ? 1.0 / (mesh_x[i] * mesh_x[i]) : 0.0;
+        }
+    }
+    // centrifugal factors 1/x_n^2 of this lane's two mesh points
+    __device__ __forceinline__ void centrifugal(double& c0, double& c1) const {
+        extern __shared__ __align__(16) unsigned char smem_raw[];
+        const double* c = reinterpret_cast<const double*>(smem_raw) + PT * PT + PT;
+        c0 = c[lane];
+        c1 = c[lane + 32 < PT ? lane + 32 : 0];
     }
     // Threshold-pivoted symmetric elimination first (lu_sym.cuh); a system whose diagonal fails the
     // threshold test is re-solved with partial pivoting (lu_fast.cuh).  `fallbacks` counts those.
     __device__ __forceinline__ double2 solve(const double2 d0, const double2 d1, int& singular, const bool symmetric,
                                              unsigned long long* fallbacks) {
+        extern __shared__ __align__(16) unsigned char smem_raw[];
+        const double* Tp = reinterpret_cast<const double*>(smem_raw);
+        const double* bsh = Tp + PT * PT;
+        double2* W = reinterpret_cast<double2*>(smem_raw + wofs);
+        double2* dvec = W + G::WALLOC;
+        unsigned char* origv = reinterpret_cast<unsigned char*>(dvec + PT);
         const double2 one = make_double2(1.0, 0.0);
         if (symmetric) {
             constexpr int NS = SymGeom<PT>::NS0;
@@ -180,10 +198,6 @@ struct WarpSolver {
             __syncwarp();
             if (!fail) return corner;
             if (lane == 0 && fallbacks) atomicAdd(fallbacks, 1ULL);
-#ifdef JITR_EXPERIMENT_NO_FALLBACK
-            singular = 1;
-            return corner;
-#endif
         }
         constexpr int NS = FastGeom<PT>::NS0;
         double2 d[NS];
@@ -264,16 +278,13 @@ __global__ void __launch_bounds__(SweepPlan<MODE>::kThreads, 1) elastic_sweep_ke
     // broadcast from lane 0: tells the compiler the warp index (hence the whole work loop) is warp-uniform
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
     WarpSolver<MODE> solver;
-    solver.init(smem_raw, A.That, A.bvec, N, nwarps, warp, lane);
+    solver.init(smem_raw, A.That, A.bvec, A.mesh_x, N, nwarps, warp, lane);
     __syncthreads();
 
     // mesh points owned by this lane (two slots, N <= 64)
     const int n0 = lane, n1 = lane + 32;
     const bool v1 = n1 < N;
     const bool v0 = n0 < N;
-    const double x0 = A.mesh_x[v0 ? n0 : 0], x1 = A.mesh_x[v1 ? n1 : 0];
-    const double t0 = A.That[(v0 ? n0 : 0) * (N + 1)], t1 = A.That[(v1 ? n1 : 0) * (N + 1)];
-    const double cent0 = 1.0 / (x0 * x0), cent1 = 1.0 / (x1 * x1);
     const int L1 = A.lmax + 1;
     const double2 zero2 = make_double2(0.0, 0.0);
 
@@ -286,8 +297,8 @@ __global__ void __launch_bounds__(SweepPlan<MODE>::kThreads, 1) elastic_sweep_ke
     bool active = pair < A.n_pairs;  // warp-uniform
     bool fresh = true;               // the pair's potentials have not been evaluated yet
     int e = 0, l = 0, jj = 0, nl = 0, singular = 0, nonfinite = 0;
-    double a = 0.0;
-    double2 d0 = zero2, d1 = zero2, so0 = zero2, so1 = zero2, Splus = zero2;
+    bool plus_small = false;  // |1 - S+| < tol at the current l
+    double2 d0 = zero2, d1 = zero2, so0 = zero2, so1 = zero2;
     __shared__ unsigned long long lock_bars[2];
     __shared__ int warps_active;
     LockStep lock;
@@ -308,9 +319,10 @@ __global__ void __launch_bounds__(SweepPlan<MODE>::kThreads, 1) elastic_sweep_ke
             const long long smp = pair / A.n_energies;
             e = (int)(pair - smp * A.n_energies);
             const double* et = A.etab + (size_t)e * JITR_B200_ET_STRIDE;
-            a = et[JITR_B200_ET_A];
-            const double E0 = et[JITR_B200_ET_ECM], radius = et[JITR_B200_ET_RCH];
+            const double a = et[JITR_B200_ET_A], E0 = et[JITR_B200_ET_ECM], radius = et[JITR_B200_ET_RCH];
             const double a2 = a * a;
+            const double x0 = A.mesh_x[v0 ? n0 : 0], x1 = A.mesh_x[v1 ? n1 : 0];
+            const double t0 = A.That[(v0 ? n0 : 0) * (N + 1)], t1 = A.That[(v1 ? n1 : 0) * (N + 1)];
             // ---- potentials on this lane's mesh points, in the a^2-scaled form of the diagonal
             double2 vc0, vs0, vc1, vs1;
             if (PARAMS) {
@@ -343,12 +355,15 @@ __global__ void __launch_bounds__(SweepPlan<MODE>::kThreads, 1) elastic_sweep_ke
         // ---- one system: partial wave l, j = l + 1/2 (jj = 0) or l - 1/2 (jj = 1)
         const double ll1 = (double)l * (double)(l + 1);
         const double ls = (jj == 0) ? (double)l : -(double)(l + 1);
+        double cent0, cent1;
+        solver.centrifugal(cent0, cent1);
         const double2 dd0 = make_double2(d0.x + ll1 * cent0 + ls * so0.x, d0.y + ls * so0.y);
         const double2 dd1 = make_double2(d1.x + ll1 * cent1 + ls * so1.x, d1.y + ls * so1.y);
         // corner = -b^T (a^2 A)^-1 b = -R
         const double2 corner = solver.solve(dd0, dd1, singular, A.symmetric != 0, A.fallbacks);
         const double2* as = A.asym + ((size_t)e * L1 + l) * 4;  // (after the solve: fewer live registers)
         const double2 Hp = as[0], Hm = as[1], Hpp = as[2], Hmp = as[3];
+        const double a = A.etab[(size_t)e * JITR_B200_ET_STRIDE + JITR_B200_ET_A];
         const double2 aR = make_double2(-a * corner.x, -a * corner.y);
         // S = (H- - a R H-') / (H+ - a R H+')   (rmatrix/core.py:51-56 with nch = 1)
         const double2 t_m = cmul(aR, Hmp), t_p = cmul(aR, Hpp);
@@ -358,9 +373,12 @@ __global__ void __launch_bounds__(SweepPlan<MODE>::kThreads, 1) elastic_sweep_ke
         if (!(isfinite(S.x) && isfinite(S.y))) nonfinite = 1;
         double2* Sp_out = A.S_out + (size_t)pair * 2 * L1;
         double2* Sm_out = Sp_out + L1;
+        // |1 - S| < tol  (xs/elastic.py:178-181), compared in squares
+        const double e1 = 1.0 - S.x;
+        const bool small = fma(e1, e1, S.y * S.y) < A.tol * A.tol;
         bool pair_done = false;
         if (jj == 0) {
-            Splus = S;
+            plus_small = small;
             if (lane == 0) Sp_out[l] = S;
             if (l == 0) {  // l = 0 has the single j = 1/2 system; S- [0] = 0 (xs/elastic.py:112,152)
                 if (lane == 0) Sm_out[0] = zero2;
@@ -375,11 +393,8 @@ __global__ void __launch_bounds__(SweepPlan<MODE>::kThreads, 1) elastic_sweep_ke
             nl = l + 1;
             pair_done = l == A.lmax;
             if (A.tol > 0.0) {
-                // |1 - S| < tol for both j  (xs/elastic.py:178-181), compared in squares
-                const double ep = 1.0 - Splus.x, em = 1.0 - S.x, tol2 = A.tol * A.tol;
-                const bool small = fma(ep, ep, Splus.y * Splus.y) < tol2 && fma(em, em, S.y * S.y) < tol2;
                 // (the vote keeps every branch of this loop provably warp-uniform for the compiler)
-                if (__all_sync(0xffffffffu, small)) pair_done = true;
+                if (__all_sync(0xffffffffu, small && plus_small)) pair_done = true;
             }
             l += 1;
             jj = 0;

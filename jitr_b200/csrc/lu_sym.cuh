@@ -33,12 +33,16 @@ struct SymGeom {
     static constexpr int NT = n / 8;
     static constexpr int NS0 = PT > 32 ? 2 : 1;
     static constexpr int WSZ = n * LDW;
-    // scratch inside W while the first panel is in flight: L21 and the unscaled columns, rows 8..PT-1
+    // scratch inside W while the first panel is in flight:
+    //   WB  the unscaled columns of ALL rows 0..PT-1 (rows < 8: the pivot block), at the start of W
+    //   LB  the multipliers L21 of rows 8..PT-1, at the END of W: tile row tr of the Schur complement,
+    //       stored to W rows 8 tr .. 8 tr + 7, then only overwrites LB rows of tile rows <= tr, so the
+    //       A fragments can be fetched one tile row at a time instead of being held in registers
     static constexpr int LB_LD = 9;
-    static constexpr int LB_OFF = 0;
-    static constexpr int WB_OFF = LB_OFF + n * LB_LD;  // unscaled columns of ALL rows 0..PT-1 (rows < 8: pivot block)
-    static constexpr int SCRATCH = WB_OFF + PT * LB_LD;
-    static constexpr int WALLOC = WSZ > SCRATCH ? WSZ : SCRATCH;
+    static constexpr int WB_OFF = 0;
+    static constexpr int LB_MIN = n * (n - 8);  // = WSZ - n * LB_LD
+    static constexpr int LB_OFF = LB_MIN > PT * LB_LD ? LB_MIN : PT * LB_LD;
+    static constexpr int WALLOC = LB_OFF + n * LB_LD;  // >= WSZ
     static_assert(n >= 8 && n <= 32, "symmetric fast path covers 16 <= PT <= 40");
 };
 
@@ -203,7 +207,7 @@ __device__ __forceinline__ double2 sym_schur(double2* __restrict__ W, double2* _
         const int part = fk & 1, pn = fr & 1;
         const int bflip = (part & (pn ^ 1)) ? 0x80000000 : 0;
         const double* Wd = reinterpret_cast<const double*>(W);
-        double b[NT][2][4], a[NT][4];
+        double b[NT][2][4];
 #pragma unroll
         for (int q = 0; q < NT; ++q)
 #pragma unroll
@@ -214,14 +218,14 @@ __device__ __forceinline__ double2 sym_schur(double2* __restrict__ W, double2* _
                         Wd[2 * (G::WB_OFF + (8 + 8 * q + 4 * h + (fr >> 1)) * G::LB_LD + s + 4 * (fk >> 1)) + (part ^ pn)];
                     b[q][h][s] = __hiloint2double(__double2hiint(v) ^ bflip, __double2loint(v));
                 }
-#pragma unroll
-        for (int tr = 0; tr < NT; ++tr)
-#pragma unroll
-            for (int s = 0; s < 4; ++s)
-                a[tr][s] = dneg(Wd[2 * (G::LB_OFF + (8 * tr + rho) * G::LB_LD + s + 4 * (fk >> 1)) + part]);
-        __syncwarp();  // every fragment is in registers: the scratch may be overwritten
+        __syncwarp();  // the B fragments are in registers: WB (the start of W) may be overwritten
 #pragma unroll
         for (int tr = 0; tr < NT; ++tr) {
+            double a[4];
+#pragma unroll
+            for (int s = 0; s < 4; ++s)
+                a[s] = dneg(Wd[2 * (G::LB_OFF + (8 * tr + rho) * G::LB_LD + s + 4 * (fk >> 1)) + part]);
+            __syncwarp();  // (the last tile row overwrites its own LB rows)
             const int row = 8 + 8 * tr + rho;
             double2 c[NT][2];
 #pragma unroll
@@ -235,8 +239,8 @@ __device__ __forceinline__ double2 sym_schur(double2* __restrict__ W, double2* _
             for (int s = 0; s < 4; ++s)
 #pragma unroll
                 for (int q = 0; q <= tr; ++q) {
-                    dmma884(c[q][0].x, c[q][0].y, a[tr][s], b[q][0][s]);
-                    dmma884(c[q][1].x, c[q][1].y, a[tr][s], b[q][1][s]);
+                    dmma884(c[q][0].x, c[q][0].y, a[s], b[q][0][s]);
+                    dmma884(c[q][1].x, c[q][1].y, a[s], b[q][1][s]);
                 }
             double2* Crow = W + (8 * tr + rho) * LDW + fk;
 #pragma unroll
