@@ -211,20 +211,23 @@ struct WarpSolver {
 
 // ---------------------------------------------------------------------------------------------
 // Loose lock step of the warps of a CTA: warp w may start iteration it only after EVERY warp has
-// finished iteration it - 2 (two mbarriers, used on alternate iterations, one arrival per warp).
+// finished iteration it - K (K mbarriers used round robin, one arrival per warp and iteration).
 // The warps stay within one solve of each other -- close enough to share the instruction cache --
 // but a warp that needs longer for one iteration (potential evaluation at the start of a pair,
 // the partial-pivoting fallback) does not stall the other eleven the way a full barrier did
 // (ncu before: 15 % of all warp cycles in the barrier).
 // ---------------------------------------------------------------------------------------------
+#ifndef JITR_LOCKSTEP_SLACK
+#define JITR_LOCKSTEP_SLACK 2
+#endif
 struct LockStep {
-    unsigned bar[2];  // shared-memory addresses of the two mbarriers
+    static constexpr int K = JITR_LOCKSTEP_SLACK;  // iterations a warp may run ahead of the slowest one
+    unsigned bar0;  // shared-memory address of the first of the K mbarriers
     __device__ __forceinline__ void init(unsigned long long* smem_bars, int nwarps) {
-        bar[0] = (unsigned)__cvta_generic_to_shared(smem_bars);
-        bar[1] = bar[0] + 8;
+        bar0 = (unsigned)__cvta_generic_to_shared(smem_bars);
         if (threadIdx.x == 0) {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar[0]), "r"(nwarps));
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar[1]), "r"(nwarps));
+            for (int k = 0; k < K; ++k)
+                asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar0 + 8 * k), "r"(nwarps));
         }
     }
     // block until the phase `parity` of barrier b has completed
@@ -234,14 +237,14 @@ struct LockStep {
             asm volatile(
                 "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
                 : "=r"(done)
-                : "r"(bar[b]), "r"(parity)
+                : "r"(bar0 + 8 * b), "r"(parity)
                 : "memory");
         } while (!done);
     }
     __device__ __forceinline__ void arrive(int b, int lane) const {
         __syncwarp();
         if (lane == 0) {
-            asm volatile("{ .reg .b64 st; mbarrier.arrive.shared::cta.b64 st, [%0]; }" ::"r"(bar[b]) : "memory");
+            asm volatile("{ .reg .b64 st; mbarrier.arrive.shared::cta.b64 st, [%0]; }" ::"r"(bar0 + 8 * b) : "memory");
         }
     }
 };
@@ -299,7 +302,7 @@ __global__ void __launch_bounds__(SweepPlan<MODE>::kThreads, 1) elastic_sweep_ke
     int e = 0, l = 0, jj = 0, nl = 0, singular = 0, nonfinite = 0;
     bool plus_small = false;  // |1 - S+| < tol at the current l
     double2 d0 = zero2, d1 = zero2, so0 = zero2, so1 = zero2;
-    __shared__ unsigned long long lock_bars[2];
+    __shared__ unsigned long long lock_bars[LockStep::K];
     __shared__ int warps_active;
     LockStep lock;
     lock.init(lock_bars, nwarps);
@@ -307,8 +310,8 @@ __global__ void __launch_bounds__(SweepPlan<MODE>::kThreads, 1) elastic_sweep_ke
     __syncthreads();
     if (!active && lane == 0) atomicSub(&warps_active, 1);
     for (unsigned it = 0;; ++it) {
-        const int b = it & 1;
-        if (it >= 2) lock.wait(b, ((it >> 1) - 1) & 1);  // every warp has finished iteration it - 2
+        const int b = it % LockStep::K;
+        if (it >= LockStep::K) lock.wait(b, (it / LockStep::K - 1) & 1);  // every warp has finished iteration it - K
         // warps_active only decreases and reaches 0 after every warp's last arrival: a common exit point
         if (__all_sync(0xffffffffu, *(volatile int*)&warps_active == 0)) break;
         if (!active) {
