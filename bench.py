@@ -359,7 +359,7 @@ def main():
         "config": workload_config(args.samples, world),
         "samples_per_s": S_total * nE / (ms_per_step * 1e-3),
         "solves_per_pair": all_solves / (S_total * nE),
-        "pivoting": {"scheme": "threshold pivoting on the diagonal (tau = 1/16, symmetric LDL^T), partial-pivoting LU on failure",
+        "pivoting": {"scheme": "threshold pivoting on the diagonal (|a_kk| >= max_i |a_ik| / 64, symmetric LDL^T); a system that fails the test is re-solved by partial-pivoting LU",
                      "partial_pivoting_fallbacks_per_step_rank0": int(fallbacks // max(args.steps, 1)),
                      "fallback_fraction": float(fallbacks) / max(args.steps, 1) / max(my_solves, 1)},
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu_baseline,

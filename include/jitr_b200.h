@@ -170,7 +170,7 @@ int jitr_b200_fp64_probe(int which, int iters, int warps_dmma, double* tflops_ou
 
 /*
  * Library options.  JITR_B200_OPT_SYMMETRIC (default 1): the fused sweep first eliminates each system
- * with threshold pivoting on the diagonal (|a_kk| >= max_i |a_ik| / 16), which preserves the complex
+ * with threshold pivoting on the diagonal (|a_kk| >= max_i |a_ik| / 64), which preserves the complex
  * symmetry of  That + diag(d)  (half the trailing update, no triangular solve, no row interchanges), and
  * re-solves a system with partial pivoting the first time a diagonal entry fails the test.  0 = always
  * use partial pivoting.  Both give the reference's S within its tolerance (tests/test_gpu_parity.py).

@@ -2,7 +2,7 @@
 //
 // Every system of the elastic sweep is complex SYMMETRIC,  a^2 A = That + diag(d),  and so is the bordered
 // matrix [[A, b], [b^T, 0]].  As long as the diagonal entry passes the threshold-pivoting test
-//        |a_kk| >= tau * max_{i >= k} |a_ik|          (tau = 2^-JITR_SYM_TAU_LOG2, |.| = |re| + |im|)
+//        |a_kk| >= tau * max_{i >= k} |a_ik|          (tau = 2^-JITR_SYM_TAU_LOG2, |.| = max(|re|, |im|))
 // it is taken as the pivot (classical threshold partial pivoting: every multiplier is bounded by 1/tau),
 // no rows move, and the elimination is A = L D L^T:
 //   * the pivot row is the transpose of the pivot column (no row search result to fetch, no interchanges),
@@ -11,8 +11,9 @@
 //   * the border needs no z row: the corner is  -sum_k y_k^2 / d_k.
 // The first time a diagonal entry FAILS the test the factorisation stops and reports it; the caller then
 // solves that system with the general partial-pivoting path (lu_fast.cuh).  On the KDUQ sweep the
-// kinetic diagonal dominates and about 0.2 % of the systems fall back at tau = 1/16
-// (tools/lu_lab/sym_stats.py); the results agree with LAPACK to <= 2e-11 either way.
+// kinetic diagonal dominates: 0.013 % of the systems fall back at tau = 1/64 (0.2 % at 1/16), element
+// growth of the unpivoted elimination is 1.0 and the corner agrees with LAPACK to <= 2e-11 either way
+// (profiles/r01_pivoting_stats.md).
 //
 // Layout and phases follow lu_fast.cuh / lu_warp.cuh: first panel straight from That (the system never
 // exists as a whole), Schur complement W of order n = PT - 8 with its RHS column in shared memory,
