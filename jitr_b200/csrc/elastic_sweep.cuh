@@ -145,6 +145,29 @@ struct SweepPlan {
     static int smem(int, int w) { return kShared + w * G::WARP_BYTES; }
 };
 
+// The partial-pivoting re-solve of a system that failed the threshold test: rare (1e-4 of the systems),
+// deliberately out of line so that its code stays out of the hot loop's instruction footprint and out of
+// the compiler's convergence analysis of the main kernel (with it inlined the analysis gave up and wrapped
+// every warp-collective instruction of the hot path in divergence guards: 15.5k instead of 7k instructions).
+template <int PT>
+static __device__ __noinline__ double2 pivoting_fallback(unsigned wofs, double2 d0, double2 d1, int lane, int* singular) {
+    using G = FastLayout<PT>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const double* Tp = reinterpret_cast<const double*>(smem_raw);
+    const double* bsh = Tp + PT * PT;
+    double2* W = reinterpret_cast<double2*>(smem_raw + wofs);
+    double2* dvec = W + G::WALLOC;
+    unsigned char* origv = reinterpret_cast<unsigned char*>(dvec + PT);
+    constexpr int NS = FastGeom<PT>::NS0;
+    double2 d[NS];
+    d[0] = d0;
+    if (NS > 1) d[NS - 1] = d1;
+    int sing = 0;
+    const double2 corner = fast_schur<PT>(W, dvec, origv, Tp, bsh, d, lane, sing);
+    if (sing) *singular = 1;
+    return corner;
+}
+
 template <int PT>
 struct WarpSolver {
     using G = FastLayout<PT>;
@@ -181,30 +204,28 @@ struct WarpSolver {
     // threshold test is re-solved with partial pivoting (lu_fast.cuh).  `fallbacks` counts those.
     __device__ __forceinline__ double2 solve(const double2 d0, const double2 d1, int& singular, const bool symmetric,
                                              unsigned long long* fallbacks) {
-        extern __shared__ __align__(16) unsigned char smem_raw[];
-        const double* Tp = reinterpret_cast<const double*>(smem_raw);
-        const double* bsh = Tp + PT * PT;
-        double2* W = reinterpret_cast<double2*>(smem_raw + wofs);
-        double2* dvec = W + G::WALLOC;
-        unsigned char* origv = reinterpret_cast<unsigned char*>(dvec + PT);
         const double2 one = make_double2(1.0, 0.0);
+        const double2 da = lane < N ? d0 : one, db = lane + 32 < N ? d1 : one;
         if (symmetric) {
+            extern __shared__ __align__(16) unsigned char smem_raw[];
+            const double* Tp = reinterpret_cast<const double*>(smem_raw);
+            const double* bsh = Tp + PT * PT;
+            double2* W = reinterpret_cast<double2*>(smem_raw + wofs);
+            double2* dvec = W + G::WALLOC;
             constexpr int NS = SymGeom<PT>::NS0;
             double2 d[NS];
-            d[0] = lane < N ? d0 : one;
-            if (NS > 1) d[NS - 1] = lane + 32 < N ? d1 : one;
+            d[0] = da;
+            if (NS > 1) d[NS - 1] = db;
             int fail = 0;
             const double2 corner = sym_schur<PT>(W, dvec, Tp, bsh, d, lane, fail);
             __syncwarp();
             if (!fail) return corner;
             if (lane == 0 && fallbacks) atomicAdd(fallbacks, 1ULL);
         }
-        constexpr int NS = FastGeom<PT>::NS0;
-        double2 d[NS];
-        d[0] = lane < N ? d0 : one;
-        if (NS > 1) d[NS - 1] = lane + 32 < N ? d1 : one;
-        const double2 corner = fast_schur<PT>(W, dvec, origv, Tp, bsh, d, lane, singular);
+        int sing = 0;
+        const double2 corner = pivoting_fallback<PT>(wofs, da, db, lane, &sing);
         __syncwarp();
+        if (__any_sync(0xffffffffu, sing)) singular = 1;
         return corner;
     }
 };
