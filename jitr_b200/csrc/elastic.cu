@@ -33,88 +33,99 @@ struct ObsArgs {
     double* tot_rxn;
 };
 
-__global__ void __launch_bounds__(256) elastic_observables_kernel(const ObsArgs A) {
+constexpr int kObsWarps = 8;
+constexpr int kObsAnglesPerLane = 8;  // angles a lane sums at once (register blocking over the l loop)
+
+// One WARP per (sample, energy) pair, no CTA barrier in the sample loop: lanes l form the 2 L coefficient
+// pairs of the sample (staged in the warp's slice of shared memory), then every lane sums up to eight
+// angles at once over l, so a coefficient is fetched once per eight angles.
+__global__ void __launch_bounds__(kObsWarps * 32) elastic_observables_kernel(const ObsArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int L1 = A.lmax + 1, NA = A.n_angles;
     double* Ps = reinterpret_cast<double*>(smem_raw);  // [L1][NA]
     double* P1s = Ps + (size_t)L1 * NA;                 // [L1][NA]
-    double2* ca = reinterpret_cast<double2*>(P1s + (size_t)L1 * NA);  // [L1] coefficient of P_l
-    double2* cb = ca + L1;                                            // [L1] coefficient of P^1_l
-    double* red = reinterpret_cast<double*>(cb + L1);                 // [2]
+    double2* coef = reinterpret_cast<double2*>(P1s + (size_t)L1 * NA);  // [warps][2][L1]
     const int e = blockIdx.y;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
     const double* Pg = A.P + (size_t)e * L1 * NA;
     const double* P1g = A.P1 + (size_t)e * L1 * NA;
     for (int i = threadIdx.x; i < L1 * NA; i += blockDim.x) {
         Ps[i] = Pg[i];
         P1s[i] = P1g[i];
     }
+    __syncthreads();
+    double2* ca = coef + (size_t)warp * 2 * L1;  // coefficient of P_l
+    double2* cb = ca + L1;                        // coefficient of P^1_l
     const double k = A.kvec[e];
     const long long s_begin = (long long)blockIdx.x * A.chunk;
     long long s_end = s_begin + A.chunk;
     if (s_end > A.n_samples) s_end = A.n_samples;
-    for (long long s = s_begin; s < s_end; ++s) {
+    for (long long s = s_begin + warp; s < s_end; s += kObsWarps) {
         const long long pair = s * A.n_energies + e;
         const int nl = A.nl[pair];
         const double2* Sp = A.S + (size_t)pair * 2 * L1;
         const double2* Sm = Sp + L1;
-        __syncthreads();  // tables loaded / previous sample's coefficients consumed
-        if (threadIdx.x < ((L1 + 31) & ~31)) {  // whole warps, so the shuffles below are well defined
-            const int l = threadIdx.x;
-            double2 a_l = make_double2(0.0, 0.0), b_l = make_double2(0.0, 0.0);
-            double rx = 0.0, tt = 0.0;
-            if (l < nl) {
-                const double2 sp = Sp[l], sm = Sm[l], ph = A.phase[(size_t)e * L1 + l];
-                // (l+1)(S+ - 1) + l (S- - 1) ;  S+ - S-     (xs/elastic.py:357-362)
-                const double2 wa = make_double2((l + 1) * (sp.x - 1.0) + l * (sm.x - 1.0), (l + 1) * sp.y + l * sm.y);
-                const double2 wb = make_double2(sp.x - sm.x, sp.y - sm.y);
-                a_l = cmul(ph, wa);
-                b_l = cmul(ph, wb);
-                rx = (l + 1) * (1.0 - (sp.x * sp.x + sp.y * sp.y)) + l * (1.0 - (sm.x * sm.x + sm.y * sm.y));
-                tt = (l + 1) * (1.0 - sp.x) + l * (1.0 - sm.x);
-            }
-            if (l < L1) {
-                ca[l] = a_l;
-                cb[l] = b_l;
-            }
-            for (int o = 16; o > 0; o >>= 1) {
-                rx += __shfl_down_sync(0xffffffffu, rx, o);
-                tt += __shfl_down_sync(0xffffffffu, tt, o);
-            }
-            if ((threadIdx.x & 31) == 0) {
-                red[2 * (threadIdx.x >> 5)] = tt;
-                red[2 * (threadIdx.x >> 5) + 1] = rx;
-            }
+        double rx = 0.0, tt = 0.0;
+        for (int l = lane; l < nl; l += 32) {
+            const double2 sp = Sp[l], sm = Sm[l], ph = A.phase[(size_t)e * L1 + l];
+            // (l+1)(S+ - 1) + l (S- - 1) ;  S+ - S-     (xs/elastic.py:357-362)
+            const double2 wa = make_double2((l + 1) * (sp.x - 1.0) + l * (sm.x - 1.0), (l + 1) * sp.y + l * sm.y);
+            const double2 wb = make_double2(sp.x - sm.x, sp.y - sm.y);
+            ca[l] = cmul(ph, wa);
+            cb[l] = cmul(ph, wb);
+            rx += (l + 1) * (1.0 - (sp.x * sp.x + sp.y * sp.y)) + l * (1.0 - (sm.x * sm.x + sm.y * sm.y));
+            tt += (l + 1) * (1.0 - sp.x) + l * (1.0 - sm.x);
         }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            double tt = 0.0, rx = 0.0;
-            for (int w = 0; w < (L1 + 31) / 32; ++w) {
-                tt += red[2 * w];
-                rx += red[2 * w + 1];
-            }
+        for (int o = 16; o > 0; o >>= 1) {
+            rx += __shfl_down_sync(0xffffffffu, rx, o);
+            tt += __shfl_down_sync(0xffffffffu, tt, o);
+        }
+        if (lane == 0) {
             A.tot_rxn[2 * pair] = tt * (10.0 * 2.0 * M_PI / (k * k));
             A.tot_rxn[2 * pair + 1] = rx * (10.0 * M_PI / (k * k));
         }
-        for (int t = threadIdx.x; t < NA; t += blockDim.x) {
-            double2 fa = A.f_c[(size_t)e * NA + t];
-            double2 fb = make_double2(0.0, 0.0);
-            for (int l = 0; l < nl; ++l) {
-                const double pl = Ps[l * NA + t], p1 = P1s[l * NA + t];
-                const double2 al = ca[l], bl = cb[l];
-                fa.x = fma(pl, al.x, fa.x);
-                fa.y = fma(pl, al.y, fa.y);
-                fb.x = fma(p1, bl.x, fb.x);
-                fb.y = fma(p1, bl.y, fb.y);
+        __syncwarp();
+        for (int t0 = 0; t0 < NA; t0 += 32 * kObsAnglesPerLane) {
+            double2 fa[kObsAnglesPerLane], fb[kObsAnglesPerLane];
+            int tj[kObsAnglesPerLane];
+#pragma unroll
+            for (int j = 0; j < kObsAnglesPerLane; ++j) {
+                const int t = t0 + 32 * j + lane;
+                tj[j] = t < NA ? t : NA - 1;
+                fa[j] = A.f_c[(size_t)e * NA + tj[j]];
+                fb[j] = make_double2(0.0, 0.0);
             }
-            const double d0 = fa.x * fa.x + fa.y * fa.y + fb.x * fb.x + fb.y * fb.y;
-            const double den = fmax(d0, 1e-30);
-            // conj(a) b = (a.x - i a.y)(b.x + i b.y)
-            const double re = fa.x * fb.x + fa.y * fb.y, im = fa.x * fb.y - fa.y * fb.x;
-            const size_t o = (size_t)pair * NA + t;
-            A.dsdo[o] = d0 * 10.0;
-            if (A.Ay) A.Ay[o] = 2.0 * im / den;
-            if (A.Q) A.Q[o] = 2.0 * re / den;
+            for (int l = 0; l < nl; ++l) {
+                const double2 al = ca[l], bl = cb[l];
+                const double* Pl = Ps + l * NA;
+                const double* P1l = P1s + l * NA;
+#pragma unroll
+                for (int j = 0; j < kObsAnglesPerLane; ++j) {
+                    if (t0 + 32 * j < NA) {  // warp-uniform
+                        const double pl = Pl[tj[j]], p1 = P1l[tj[j]];
+                        fa[j].x = fma(pl, al.x, fa[j].x);
+                        fa[j].y = fma(pl, al.y, fa[j].y);
+                        fb[j].x = fma(p1, bl.x, fb[j].x);
+                        fb[j].y = fma(p1, bl.y, fb[j].y);
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < kObsAnglesPerLane; ++j) {
+                const int t = t0 + 32 * j + lane;
+                if (t < NA) {
+                    const double d0 = fa[j].x * fa[j].x + fa[j].y * fa[j].y + fb[j].x * fb[j].x + fb[j].y * fb[j].y;
+                    const double den = fmax(d0, 1e-30);
+                    // conj(a) b = (a.x - i a.y)(b.x + i b.y)
+                    const double re = fa[j].x * fb[j].x + fa[j].y * fb[j].y, im = fa[j].x * fb[j].y - fa[j].y * fb[j].x;
+                    const size_t o = (size_t)pair * NA + t;
+                    A.dsdo[o] = d0 * 10.0;
+                    if (A.Ay) A.Ay[o] = 2.0 * im / den;
+                    if (A.Q) A.Q[o] = 2.0 * re / den;
+                }
+            }
         }
+        __syncwarp();  // the coefficients of this sample are consumed before the next one overwrites them
     }
 }
 
@@ -226,7 +237,7 @@ extern "C" int jitr_b200_elastic_observables(int lmax, int n_angles, long long n
     a.f_c = reinterpret_cast<const double2*>(f_c);
     a.kvec = kvec; a.dsdo = dsdo; a.Ay = Ay; a.Q = Q; a.tot_rxn = tot_rxn;
     const int L1 = lmax + 1;
-    const size_t smem = (size_t)2 * L1 * n_angles * 8 + (size_t)2 * L1 * 16 + 2 * 8 * 8;
+    const size_t smem = (size_t)2 * L1 * n_angles * 8 + (size_t)kObsWarps * 2 * L1 * 16;
     if (smem > 232448) return set_error(JITR_B200_ERR_UNSUPPORTED, "elastic_observables: (lmax+1)*n_angles tables exceed shared memory");
     static size_t configured = 0;
     if (smem > configured) {
@@ -242,7 +253,7 @@ extern "C" int jitr_b200_elastic_observables(int lmax, int n_angles, long long n
     if (chunk < 1) chunk = 1;
     a.chunk = (int)(chunk > (1 << 30) ? (1 << 30) : chunk);
     dim3 grid((unsigned)((n_samples + a.chunk - 1) / a.chunk), (unsigned)n_energies);
-    elastic_observables_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(a);
+    elastic_observables_kernel<<<grid, kObsWarps * 32, smem, static_cast<cudaStream_t>(stream)>>>(a);
     count_launch();
     if (cudaGetLastError() != cudaSuccess) return set_cuda_error("elastic_observables launch");
     return JITR_B200_OK;
