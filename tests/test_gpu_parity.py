@@ -193,6 +193,43 @@ def test_fused_sweep_vs_oracle_random_shapes():
             assert abs(float(x.rxn[s, ie]) - rxn) / rxn < RTOL_XS
 
 
+@pytest.mark.parametrize("N", [6, 12, 20, 27, 35, 40, 48, 56, 64])
+def test_sweep_every_nbasis_path_vs_oracle(N):
+    """Every solver mode of the fused sweep: generic (N <= 8 and 40 < N <= 64, two or three row slots per
+    lane) and the assembly-free fast paths P = 16, 24, 32, 40 (N not a multiple of 8 exercises the identity
+    padding), both pivoting schemes, against the oracle on the same potentials."""
+    lmax = 5
+    rx = ElasticReaction((48, 20), (1, 1), mass_target=44657.272049078, mass_projectile=938.271653086152)
+    kin = rx.kinematics(18.0)
+    iw = jitr_b200.IntegralWorkspace(rx, kin, 9.5, jitr_b200.Solver(N), lmax, smatrix_abs_tol=0.0)
+    r = iw.radial_grid()
+    rng = np.random.default_rng(100 + N)
+    B = 6
+    c = np.zeros((B, N), dtype=np.complex128)
+    so = np.zeros((B, N), dtype=np.complex128)
+    co = np.zeros((B, N), dtype=np.complex128)
+    for b in range(B):
+        V, W, R0, a0 = rng.uniform(40, 55), rng.uniform(2, 9), rng.uniform(4.2, 4.9), rng.uniform(0.55, 0.75)
+        c[b] = -(V + 1j * W) * orc.woods_saxon_safe(r, R0, a0) + 4 * a0 * 1j * rng.uniform(3, 8) * orc.woods_saxon_prime_safe(r, R0 + 0.3, a0)
+        so[b] = rng.uniform(5, 9) * orc.thomas_safe(r, R0 - 0.4, 0.6)
+        co[b] = orc.coulomb_charged_sphere(r, 20, 1.25 * 48 ** (1 / 3))
+    ow = orc.ElasticWorkspace(N, lmax, 9.5, tuple(kin), np.linspace(0.3, 3.0, 7), 20, tol=0.0)
+    L = _cabi.lib()
+    for sym in (1, 0):
+        try:
+            assert L.jitr_b200_set_option(_cabi.OPT_SYMMETRIC, sym) == 0
+            S, nl, status = iw.smatrix_batch(torch.tensor(c, device="cuda"), torch.tensor(so, device="cuda"), torch.tensor(co, device="cuda"))
+        finally:
+            L.jitr_b200_set_option(_cabi.OPT_SYMMETRIC, 1)
+        assert int(status.abs().sum()) == 0
+        Sg = S.cpu().numpy()
+        for b in range(B):
+            sp, sm = ow.smatrix(c[b], so[b], co[b])
+            # N as small as 6 is far from converged: the systems are what they are, parity is what is tested
+            assert relerr(Sg[b, 0, : len(sp)], sp) < RTOL_S
+            assert relerr(Sg[b, 1, 1 : len(sm)], sm[1:]) < RTOL_S
+
+
 def test_no_early_break_and_size_independent_properties():
     """tol <= 0 issues every (l, j); for a REAL potential |S| = 1 (unitarity) for every partial wave
     and sigma_rxn = 0 -- a size-independent property checked on a larger batch."""
