@@ -327,7 +327,7 @@ def main():
     achieved = my_solves * FLOPS_PER_SOLVE / (sweep_ms * 1e-3) / 1e12
     roofline = {
         "bound": "fp64", "kernel": "elastic_sweep_kernel<PARAMS=true, MODE=40> (fused potentials + assembly-free LU + R->S)", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-        "frac": achieved / peak, "traffic": None,
+        "frac": achieved / peak, "traffic": traffic_bytes(B * nE),
         "peak_source": "measured live: FP64 pipe micro-benchmark in this library (max of DFMA and DMMA m8n8k4 issue-bound loops); "
                        "MEASURED_PEAKS.json has no FP64 entry; nominal 37.2",
         "peak_dfma_measured": peak_dfma, "peak_dmma_measured": peak_dmma, "frac_of_nominal_37.2": achieved / 37.2,
@@ -371,6 +371,16 @@ def main():
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def traffic_bytes(pairs):
+    """DRAM bytes of one sweep launch, scaled per (sample, energy) pair from the committed ncu capture."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        return {"bytes": t["sweep_dram_bytes_per_pair"] * pairs, "per_pair": t["sweep_dram_bytes_per_pair"],
+                "algorithmic_bytes_per_pair": 2 * (LMAX + 1) * 16 + 8 + 40 * 8 / 64.0, "source": t["source"]}
+    except Exception:
+        return None
 
 
 def peaks():
