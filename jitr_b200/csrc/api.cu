@@ -46,6 +46,20 @@ unsigned long long* fallback_counter() {
     }
     return ctr;
 }
+unsigned long long* next_work_counter(cudaStream_t st) {
+    constexpr int kRing = 256;
+    static unsigned long long* ring = nullptr;
+    static std::atomic<unsigned> seq{0};
+    if (!ring) {
+        if (cudaMalloc(&ring, kRing * sizeof(unsigned long long)) != cudaSuccess) {
+            ring = nullptr;
+            return nullptr;
+        }
+    }
+    unsigned long long* c = ring + (seq.fetch_add(1) % kRing);
+    if (cudaMemsetAsync(c, 0, sizeof(unsigned long long), st) != cudaSuccess) return nullptr;
+    return c;
+}
 }  // namespace jitr
 
 extern "C" const char* jitr_b200_last_error(void) { return jitr::g_err; }

@@ -316,8 +316,15 @@ __global__ void __launch_bounds__(SweepPlan<MODE>::kThreads, 1) elastic_sweep_ke
     // the same ~45 KB of unrolled code; left alone, the early break lets the 12 warps drift to unrelated
     // code regions and the SM's instruction cache thrashes (ncu: 2.5 no-instruction stall cycles per
     // issued instruction, icc hit rate 63 %); aligned, one warp's fetch serves the other eleven.
-    const long long stride = (long long)gridDim.x * nwarps;
-    long long pair = (long long)blockIdx.x * nwarps + warp;
+    // Pairs are handed out dynamically (one atomic per pair): the number of partial waves per pair varies
+    // threefold with the energy, and a static round-robin (stride = #warps, a multiple of 16) gave every
+    // warp a fixed subset of 4 of the 64 energies -- up to 21 % of a warp's time was an idle tail.
+    auto next_pair = [&]() -> long long {
+        unsigned long long v = 0;
+        if (lane == 0) v = atomicAdd(A.work_counter, 1ULL);
+        return (long long)__shfl_sync(0xffffffffu, v, 0);
+    };
+    long long pair = next_pair();
     bool active = pair < A.n_pairs;  // warp-uniform
     bool fresh = true;               // the pair's potentials have not been evaluated yet
     int e = 0, l = 0, jj = 0, nl = 0, singular = 0, nonfinite = 0;
@@ -433,7 +440,7 @@ __global__ void __launch_bounds__(SweepPlan<MODE>::kThreads, 1) elastic_sweep_ke
                 A.status[pair] =
                     nonfinite ? JITR_B200_STATUS_NONFINITE : (singular ? JITR_B200_STATUS_SINGULAR : JITR_B200_STATUS_OK);
             }
-            pair += stride;
+            pair = next_pair();
             active = pair < A.n_pairs;
             fresh = true;
             if (!active && lane == 0) atomicSub(&warps_active, 1);
@@ -459,7 +466,10 @@ int launch_sweep_mode(const SweepArgs& a, cudaStream_t st) {
     long long blocks = (a.n_pairs + warps - 1) / warps;
     if (blocks > sms) blocks = sms;
     if (blocks < 1) return JITR_B200_OK;
-    kern<<<(unsigned)blocks, warps * 32, smem, st>>>(a);
+    SweepArgs args = a;
+    args.work_counter = next_work_counter(st);
+    if (!args.work_counter) return set_cuda_error("elastic_sweep work counter");
+    kern<<<(unsigned)blocks, warps * 32, smem, st>>>(args);
     count_launch();
     if (cudaGetLastError() != cudaSuccess) return set_cuda_error("elastic_sweep launch");
     return JITR_B200_OK;
