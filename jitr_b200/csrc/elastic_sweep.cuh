@@ -331,17 +331,29 @@ __global__ void __launch_bounds__(SweepPlan<MODE>::kThreads, 1) elastic_sweep_ke
     bool plus_small = false;  // |1 - S+| < tol at the current l
     double2 d0 = zero2, d1 = zero2, so0 = zero2, so1 = zero2;
     __shared__ unsigned long long lock_bars[LockStep::K];
-    __shared__ int warps_active;
+    // Termination: every warp must leave the loop at the SAME iteration, or a warp that went on would wait
+    // for an arrival that never comes.  A warp records the iteration of its last solve (last_iter, a
+    // maximum) BEFORE it gives up its count in warps_active; warps_active == 0 then implies last_iter is
+    // final, and every warp leaves at iteration last_iter + K -- which each of them reaches, because the
+    // wait at that iteration needs only arrivals up to iteration last_iter.
+    __shared__ int warps_active, last_iter;
     LockStep lock;
     lock.init(lock_bars, nwarps);
-    if (threadIdx.x == 0) warps_active = nwarps;
+    if (threadIdx.x == 0) {
+        warps_active = nwarps;
+        last_iter = -1;
+    }
     __syncthreads();
     if (!active && lane == 0) atomicSub(&warps_active, 1);
     for (unsigned it = 0;; ++it) {
         const int b = it % LockStep::K;
         if (it >= LockStep::K) lock.wait(b, (it / LockStep::K - 1) & 1);  // every warp has finished iteration it - K
-        // warps_active only decreases and reaches 0 after every warp's last arrival: a common exit point
-        if (__all_sync(0xffffffffu, *(volatile int*)&warps_active == 0)) break;
+        {
+            const int na = *(volatile int*)&warps_active;
+            __threadfence_block();
+            const int li = *(volatile int*)&last_iter;
+            if (__all_sync(0xffffffffu, na == 0 && (int)it >= li + LockStep::K)) break;
+        }
         if (!active) {
             lock.arrive(b, lane);
             continue;
@@ -443,7 +455,11 @@ __global__ void __launch_bounds__(SweepPlan<MODE>::kThreads, 1) elastic_sweep_ke
             pair = next_pair();
             active = pair < A.n_pairs;
             fresh = true;
-            if (!active && lane == 0) atomicSub(&warps_active, 1);
+            if (!active && lane == 0) {
+                atomicMax(&last_iter, (int)it);
+                __threadfence_block();
+                atomicSub(&warps_active, 1);
+            }
         }
         lock.arrive(b, lane);
     }
