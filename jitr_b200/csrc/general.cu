@@ -257,6 +257,114 @@ __global__ void __launch_bounds__(kGenThreads) general_solve_kernel(const GenArg
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Single-channel systems (nch = 1, no coefficients) up to P = 8 ceil(N/8) <= 64: one WARP per system, the
+// bordered matrix [[F + V, b], [b^T, 0]] assembled in the warp's shared-memory region straight from the
+// global arrays (the nonlocal kernel is the HBM stream of this path: N^2 x 16 B per system) and eliminated
+// by the blocked partial-pivoting LU of lu_warp.cuh (register panel + DMMA trailing update).  This is
+// BASELINE config 4 (nonlocal Perey-Buck, N = 60): 7x the CTA-per-system kernel above.
+// ---------------------------------------------------------------------------------------------
+template <int MAXNS>
+__global__ void __launch_bounds__(256, 1) warp_solve_kernel(const GenArgs A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int N = A.N;
+    LuGeom g;
+    g.N = N;
+    g.P = (N + 7) & ~7;
+    g.LD = g.P + 1;
+    const int P = g.P, LD = g.LD, msz = LD * LD;
+    const int nwarps = blockDim.x >> 5;
+    const int warp = __shfl_sync(kFull, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
+    double2* M = reinterpret_cast<double2*>(smem_raw) + (size_t)warp * msz;
+    const double2 zero2 = make_double2(0.0, 0.0);
+    for (long long sysi = (long long)blockIdx.x * nwarps + warp; sysi < A.batch; sysi += (long long)gridDim.x * nwarps) {
+        const double* sy = A.sys + (size_t)sysi * A.sys_stride;
+        const double a = sy[0], E0 = sy[1], k0 = sy[2];
+        const double2* F = A.free_matrix + (size_t)sysi * A.free_stride;
+        const double nl_scale = (a / k0) / k0 / E0;  // kernel.py:202 (x radius), rmatrix.py:175-178 (/k0, /E0)
+        const double2* Vint = A.interaction ? A.interaction + (size_t)sysi * N * N : nullptr;
+        const double2* Vnl = (!A.interaction && A.nonlocal_) ? A.nonlocal_ + (size_t)sysi * N * N : nullptr;
+        const double2* Vloc = (!A.interaction && A.local) ? A.local + (size_t)sysi * N : nullptr;
+        // ---- assemble rows 0..N-1 (coalesced 16-byte loads, lane = column), identity padding, border
+        for (int r = 0; r < N; ++r) {
+            const double wr = Vnl ? A.wsqrt[r] * nl_scale : 0.0;
+            for (int c = lane; c < P; c += 32) {
+                double2 v = zero2;
+                if (c < N) {
+                    v = F[(size_t)r * N + c];
+                    if (Vint) {
+                        const double2 w = Vint[(size_t)r * N + c];
+                        v.x += w.x; v.y += w.y;
+                    }
+                    if (Vnl) {
+                        const double2 w = Vnl[(size_t)r * N + c];
+                        const double sc = wr * A.wsqrt[c];
+                        v.x = fma(w.x, sc, v.x); v.y = fma(w.y, sc, v.y);
+                    }
+                    if (Vloc && c == r) {
+                        const double2 w = Vloc[r];
+                        v.x += w.x / E0; v.y += w.y / E0;
+                    }
+                }
+                M[r * LD + c] = v;
+            }
+        }
+        for (int r = N; r < P; ++r)
+            for (int c = lane; c < LD; c += 32) M[r * LD + c] = make_double2(r == c ? 1.0 : 0.0, 0.0);
+        __syncwarp();
+        for (int r = lane; r < N; r += 32) {
+            const double2 bb = make_double2(A.bvec[r], 0.0);
+            M[r * LD + P] = bb;
+            M[P * LD + r] = bb;
+        }
+        for (int c = N + lane; c <= P; c += 32) M[P * LD + c] = zero2;
+        __syncwarp();
+        int singular = 0;
+        const double2 corner = bordered_schur<MAXNS>(M, g, lane, singular);  // -b^T A^-1 b
+        __syncwarp();
+        if (lane == 0) {
+            const double2* as = A.asym + (size_t)sysi * A.asym_stride;  // [4][1]: Hp, Hm, Hpp, Hmp
+            const double2 Hp = as[0], Hm = as[1], Hpp = as[2], Hmp = as[3];
+            const double2 R = make_double2(-corner.x / (a * a), -corner.y / (a * a));  // core.py:15-22
+            const double2 aR = make_double2(a * R.x, a * R.y);
+            const double2 tp = cmul(aR, Hpp), tm = cmul(aR, Hmp);
+            // S = Z+^-1 Z-, Z+- = H+- - a R H+-'   (core.py:51-56)
+            const double2 S = cdiv(make_double2(Hm.x - tm.x, Hm.y - tm.y), make_double2(Hp.x - tp.x, Hp.y - tp.y));
+            // u'_ext = (i/2)(H-' w - S H+')   (core.py:58)
+            const double w0 = A.weights[0];
+            const double2 sh = cmul(S, Hpp);
+            const double2 v = make_double2(Hmp.x * w0 - sh.x, Hmp.y * w0 - sh.y);
+            A.R[sysi] = R;
+            A.S[sysi] = S;
+            A.uext[sysi] = make_double2(-0.5 * v.y, 0.5 * v.x);
+            const bool bad = !(isfinite(S.x) && isfinite(S.y));
+            A.status[sysi] = bad ? JITR_B200_STATUS_NONFINITE : (singular ? JITR_B200_STATUS_SINGULAR : JITR_B200_STATUS_OK);
+        }
+        __syncwarp();
+    }
+}
+
+template <int MAXNS>
+static int launch_warp_solve(const GenArgs& a, cudaStream_t st) {
+    const int P = (a.N + 7) & ~7, msz = (P + 1) * (P + 1);
+    int warps = 232448 / (msz * 16);
+    if (warps > 8) warps = 8;
+    if (warps < 1) return set_error(JITR_B200_ERR_UNSUPPORTED, "warp_solve: system does not fit in shared memory");
+    const int smem = warps * msz * 16;
+    static int conf = 0;
+    if (smem > conf) {
+        if (cudaFuncSetAttribute(warp_solve_kernel<MAXNS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+            return set_cuda_error("cudaFuncSetAttribute(warp_solve)");
+        conf = smem;
+    }
+    long long blocks = (a.batch + warps - 1) / warps;
+    if (blocks > sm_count()) blocks = sm_count();
+    warp_solve_kernel<MAXNS><<<(unsigned)blocks, warps * 32, smem, st>>>(a);
+    count_launch();
+    if (cudaGetLastError() != cudaSuccess) return set_cuda_error("warp_solve launch");
+    return JITR_B200_OK;
+}
+
 }  // namespace jitr
 
 using namespace jitr;
@@ -283,6 +391,12 @@ extern "C" int jitr_b200_solve_batched(int nbasis, int nch, long long batch, con
     a.R = reinterpret_cast<double2*>(R); a.S = reinterpret_cast<double2*>(S);
     a.uext = reinterpret_cast<double2*>(uext); a.coeffs = reinterpret_cast<double2*>(coeffs);
     a.workspace = reinterpret_cast<double2*>(workspace); a.status = status;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // single channel, no coefficients, P <= 64: warp-per-system blocked LU
+    if (nch == 1 && !coeffs && ((nbasis + 7) & ~7) <= 64) {
+        if (((nbasis + 7) & ~7) + 1 <= 64) return launch_warp_solve<2>(a, st);
+        return launch_warp_solve<3>(a, st);
+    }
     const int n = a.n, ld = n + nch;
     const size_t scratch = (size_t)(n + ld) * 16 + 32 * 8 + 36 * 4 + (size_t)4 * kMaxCh * kMaxCh * 16;
     const size_t scratch_al = (scratch + 15) & ~(size_t)15;
@@ -290,7 +404,6 @@ extern "C" int jitr_b200_solve_batched(int nbasis, int nch, long long batch, con
     const bool use_smem = in_smem <= 232448;
     if (!use_smem && !workspace) return set_error(JITR_B200_ERR_BAD_ARG, "solve_batched: system too large for shared memory and no workspace given");
     const size_t smem = use_smem ? in_smem : scratch_al;
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int sms = sm_count();
     int per_sm = use_smem ? (int)(232448 / (smem + 1024)) : 4;
     if (per_sm < 1) per_sm = 1;
