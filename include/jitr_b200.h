@@ -38,6 +38,7 @@ extern "C" {
 #define JITR_B200_MODEL_KDUQ 1   /* 40 global Koning-Delaroche numbers (neutron rows padded with 0) */
 #define JITR_B200_MODEL_CHUQ 2   /* 22 global Chapel-Hill numbers */
 #define JITR_B200_MODEL_LOCAL 3  /* 15 LocalOpticalPotential numbers */
+#define JITR_B200_MODEL_WLH 4    /* 46 global Whitehead-Lim-Holt numbers (optical_potentials/wlh.py) */
 
 /* layout of one row of the per-energy table (doubles) */
 #define JITR_B200_ET_A 0        /* dimensionless channel radius a = k * R_ch */
@@ -74,7 +75,7 @@ int jitr_b200_device_ok(void);
  *   rmatrix/rmatrix.py:126-246 Solver.interaction_matrix/.solve
  *   rmatrix/core.py:7-60    rmatrix_with_inverse, solve_smatrix_with_inverse
  *   optical_potentials/potential_forms.py:40-153, kduq.py:100-197,370-559, chuq.py:92-227,
- *   omp.py:54-149           evaluation of (central, spin_orbit, coulomb) on the mesh
+ *   wlh.py:61-111,251-383, omp.py:54-149   evaluation of (central, spin_orbit, coulomb) on the mesh
  *
  *   nbasis      N, number of Lagrange-Legendre functions, 1..64 (N <= 40 takes the assembly-free fast path)
  *   That        [N][N] real: a-independent kinetic+Bloch matrix (quadrature.py:197-218 with a=1,l=0)

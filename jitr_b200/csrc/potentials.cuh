@@ -1,6 +1,7 @@
 // Built-in optical-potential forms and global-parameter maps, evaluated on the mesh inside the
 // fused solve kernel.  Reference: optical_potentials/potential_forms.py:11,40-88,134-153 (forms),
-// kduq.py:100-131,370-528 (KDUQ map), chuq.py:140-227 (CHUQ map), omp.py:54-149 (Local).
+// kduq.py:100-131,370-528 (KDUQ map), chuq.py:140-227 (CHUQ map), wlh.py:251-383 (WLH map),
+// omp.py:54-149 (Local).
 #pragma once
 #include <cuda_runtime.h>
 #include "jitr_b200.h"
@@ -170,11 +171,45 @@ __device__ __forceinline__ Shape shape_from_local(const double* __restrict__ p, 
     return s;
 }
 
+// wlh.calculate_params, wlh.py:251-383 ; 46 entries (get_param_names order)
+__device__ __forceinline__ Shape shape_from_wlh(const double* __restrict__ p, const double* __restrict__ et) {
+    const double A = et[JITR_B200_ET_AT], Z = et[JITR_B200_ET_ZT], Zp = et[JITR_B200_ET_ZP];
+    const double E = et[JITR_B200_ET_ELAB];
+    const double A13 = et[ET_A13], Am13 = et[ET_AM13];
+    const double asym = (A - 2.0 * Z) / A;
+    const double factor = (Zp == 1.0) ? 1.0 : -1.0;  // (-1)**(Zp+1)
+    const double E2 = E * E, E3 = E * E * E;
+    const double uv = p[0] - p[1] * E + p[2] * E2 + p[3] * E3 + factor * (p[4] - p[5] * E + p[6] * E2) * asym;
+    const double rv = p[7] - p[8] * Am13 - p[9] * E + p[10] * E2;
+    const double av = p[11] - factor * p[12] * E - p[13] * E2 - (p[14] - p[15] * asym) * asym;
+    const double uw = p[16] + p[17] * E - p[18] * E2 + (factor * p[19] - p[20] * E) * asym;
+    const double rw = p[21] + (p[22] + p[23] * A) / (p[24] + A + p[25] * E) + p[26] * E2;
+    const double aw = p[27] - (p[28] * E) / (-p[29] - E) + (p[30] - p[31] * E) * asym;
+    double ud = 0.0;
+    if ((Zp == 0.0 && E < 40.0) || (Zp == 1.0 && E < 20.0 && A > 100.0))
+        ud = -(p[32] - p[33] * E - (p[34] - p[35] * E) * asym);
+    const double rd = p[36] - p[38] * E - p[37] * Am13;
+    const double ad = p[39];
+    const double uso = p[40] - p[41] * A;
+    const double rso = p[42] - p[43] * Am13;
+    const double aso = p[44] - p[45] * A;
+    Shape s;
+    s.Vv = uv; s.Rv = rv * A13; s.av = av;
+    s.Wv = uw; s.Rw = rw * A13; s.aw = aw;
+    s.Vd = 0.0; s.Wd = ud; s.Rd = rd * A13; s.ad = ad;
+    s.Vso = uso / kKappa2; s.Rso = rso * A13; s.aso = aso;
+    s.Wso = 0.0; s.Rwso = rso * A13; s.awso = aso;
+    s.RC = rv * A13;
+    s.Zz = Z * Zp;
+    return s;
+}
+
 __device__ __forceinline__ Shape shape_from_model(int model, const double* __restrict__ p, const double* __restrict__ et) {
     switch (model) {
         case JITR_B200_MODEL_KDUQ: return shape_from_kduq(p, et);
         case JITR_B200_MODEL_CHUQ: return shape_from_chuq(p, et);
         case JITR_B200_MODEL_LOCAL: return shape_from_local(p, et);
+        case JITR_B200_MODEL_WLH: return shape_from_wlh(p, et);
         default: return shape_from_canonical(p, et);
     }
 }

@@ -377,6 +377,46 @@ def chuq_potentials(r, projectile, target, Elab, p):
     return central.astype(np.complex128), so.astype(np.complex128), coulomb_charged_sphere(r, zz, RC)
 
 
+def wlh_shape_params(projectile, target, Elab, p):
+    """WLH global parameters (46) -> shape parameters.  wlh.py:251-383."""
+    (uv0, uv1, uv2, uv3, uv4, uv5, uv6, rv0, rv1, rv2, rv3, av0, av1, av2, av3, av4, uw0, uw1, uw2, uw3, uw4,
+     rw0, rw1, rw2, rw3, rw4, rw5, aw0, aw1, aw2, aw3, aw4, ud0, ud1, ud3, ud4, rd0, rd1, rd2, ad0,
+     uso0, uso1, rso0, rso1, aso0, aso1) = p
+    A, Z = target
+    Ap, Zp = projectile
+    asym_factor = (A - 2 * Z) / A
+    factor = (-1) ** (Zp + 1)
+    uv = uv0 - uv1 * Elab + uv2 * Elab**2 + uv3 * Elab**3 + factor * (uv4 - uv5 * Elab + uv6 * Elab**2) * asym_factor
+    rv = rv0 - rv1 * A ** (-1.0 / 3) - rv2 * Elab + rv3 * Elab**2
+    av = av0 - factor * av1 * Elab - av2 * Elab**2 - (av3 - av4 * asym_factor) * asym_factor
+    uw = uw0 + uw1 * Elab - uw2 * Elab**2 + (factor * uw3 - uw4 * Elab) * asym_factor
+    rw = rw0 + (rw1 + rw2 * A) / (rw3 + A + rw4 * Elab) + rw5 * Elab**2
+    aw = aw0 - (aw1 * Elab) / (-aw2 - Elab) + (aw3 - aw4 * Elab) * asym_factor
+    if (tuple(projectile) == (1, 0) and Elab < 40) or (tuple(projectile) == (1, 1) and Elab < 20 and A > 100):
+        ud = -(ud0 - ud1 * Elab - (ud3 - ud4 * Elab) * asym_factor)
+    else:
+        ud = 0
+    rd = rd0 - rd2 * Elab - rd1 * A ** (-1.0 / 3)
+    ad = ad0
+    uso = uso0 - uso1 * A
+    rso = rso0 - rso1 * A ** (-1.0 / 3.0)
+    aso = aso0 - aso1 * A
+    A13 = A ** (1.0 / 3.0)
+    return (uv, rv * A13, av, uw, rw * A13, aw, ud, rd * A13, ad), (uso, rso * A13, aso), (Z * Zp, rv * A13)
+
+
+def wlh_potentials(r, projectile, target, Elab, p):
+    """(central, spin_orbit, coulomb) on grid r.  wlh.py:61-111, :396-421."""
+    (uv, Rv, av, uw, Rw, aw, ud, Rd, ad), (uso, Rso, aso), (zz, RC) = wlh_shape_params(projectile, target, Elab, p)
+    central = (
+        -uv * woods_saxon_safe(r, Rv, av)
+        - 1j * uw * woods_saxon_safe(r, Rw, aw)
+        - 1j * (-4 * ad) * ud * woods_saxon_prime_safe(r, Rd, ad)
+    )
+    so = (uso / WAVENUMBER_PION**2) * thomas_safe(r, Rso, aso)
+    return central.astype(np.complex128), so.astype(np.complex128), coulomb_charged_sphere(r, zz, RC)
+
+
 def local_omp_potentials(r, A_target, zz, p, A_proj=None):
     """LocalOpticalPotential.  omp.py:54-149 (15 parameters)."""
     Vv, rv, av, Wv, rw, aw, Wd, Vd, rd, ad, Vso, Wso, rso, aso, rC = p

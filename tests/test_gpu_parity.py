@@ -12,7 +12,7 @@ pytestmark = pytest.mark.gpu
 
 import jitr_b200  # noqa: E402
 from jitr_b200 import _cabi  # noqa: E402
-from jitr_b200.optical_potentials import LocalOpticalPotential, ShapeModel, chuq, kduq  # noqa: E402
+from jitr_b200.optical_potentials import LocalOpticalPotential, ShapeModel, chuq, kduq, wlh  # noqa: E402
 from jitr_b200.reactions import ElasticReaction, ProjectileTargetSystem  # noqa: E402
 from oracle import jitr_oracle as orc  # noqa: E402
 
@@ -47,6 +47,8 @@ def model_for(name, g):
         return chuq.CHUQ()
     if name.startswith("localomp"):
         return LocalOpticalPotential()
+    if name.startswith("wlh"):
+        return wlh.WLH(tuple(int(v) for v in g["projectile"]))
     return kduq.KDUQ(tuple(int(v) for v in g["projectile"]))
 
 
@@ -71,7 +73,7 @@ ELASTIC = [
     "config1_n208Pb_30MeV", "config3_p48Ca_30MeV",
     "config2_n40Ca_E00", "config2_n40Ca_E06", "config2_n40Ca_E15", "config2_n40Ca_E31",
     "config2_n208Pb_E00", "config2_n208Pb_E06", "config2_n208Pb_E15", "config2_n208Pb_E31",
-    "chuq_p90Zr_25MeV", "chuq_n90Zr_12MeV", "localomp_p54Fe_35MeV",
+    "chuq_p90Zr_25MeV", "chuq_n90Zr_12MeV", "localomp_p54Fe_35MeV", "wlh_n208Pb_14MeV", "wlh_p48Ca_45MeV",
 ]
 
 
@@ -131,7 +133,8 @@ def test_optional_spin_orbit_equals_zeros(golden):
 
 def test_device_potential_forms_vs_reference(golden):
     """SingleChannelOpticalModel.evaluate: device forms vs the reference's numpy forms (golden) to ~1 ulp."""
-    for name in ("config1_n208Pb_30MeV", "config3_p48Ca_30MeV", "chuq_p90Zr_25MeV", "chuq_n90Zr_12MeV", "localomp_p54Fe_35MeV"):
+    for name in ("config1_n208Pb_30MeV", "config3_p48Ca_30MeV", "chuq_p90Zr_25MeV", "chuq_n90Zr_12MeV", "localomp_p54Fe_35MeV",
+                 "wlh_n208Pb_14MeV", "wlh_p48Ca_45MeV"):
         g = golden(name)
         rx, kin, ws = make_ws(g)
         model = model_for(name, g)

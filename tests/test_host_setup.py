@@ -99,8 +99,16 @@ def test_param_vectors(golden):
     c = golden("chuq_params")
     np.testing.assert_array_equal(chuq.get_ch89(), c["ch89"])
     assert chuq.get_param_names() == list(c["names"])
+    w = golden("wlh_params")
+    from jitr_b200.optical_potentials import wlh
+
+    np.testing.assert_array_equal(wlh.get_wlh_mean((1, 0)), w["mean_n"])
+    np.testing.assert_array_equal(wlh.get_wlh_mean((1, 1)), w["mean_p"])
+    assert wlh.get_param_names((1, 0)) == list(w["names_n"]) and wlh.get_param_names((1, 1)) == list(w["names_p"])
     with pytest.raises(RuntimeError):
         kduq.KDUQ((4, 2))
+    with pytest.raises(RuntimeError):
+        wlh.WLH((2, 1))
 
 
 def test_neutral_asymptotics_closed_form_matches_mpmath():

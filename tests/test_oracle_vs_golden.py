@@ -27,6 +27,7 @@ ELASTIC = [
     ("config2_n40Ca_E00", "kduq"), ("config2_n40Ca_E31", "kduq"),
     ("config2_n208Pb_E06", "kduq"), ("config2_n208Pb_E15", "kduq"),
     ("chuq_p90Zr_25MeV", "chuq"), ("chuq_n90Zr_12MeV", "chuq"), ("localomp_p54Fe_35MeV", "local"),
+    ("wlh_n208Pb_14MeV", "wlh"), ("wlh_p48Ca_45MeV", "wlh"),
 ]
 
 
@@ -39,6 +40,8 @@ def _potentials(g, model, p):
         return orc.kduq_potentials(r, prj, tgt, Elab, p)
     if model == "chuq":
         return orc.chuq_potentials(r, prj, tgt, Elab, p)
+    if model == "wlh":
+        return orc.wlh_potentials(r, prj, tgt, Elab, p)
     return orc.local_omp_potentials(r, tgt[0], tgt[1] * prj[1], p)
 
 
@@ -90,6 +93,21 @@ def test_kduq_shape_params(golden):
             with np.errstate(over="ignore"):
                 c, s, co = orc.kduq_shape_params(prj, (int(A), int(Z)), float(E), samples[i])
             np.testing.assert_allclose(list(c) + list(s) + list(co), g[key][i], rtol=1e-14)
+
+
+def test_wlh_shape_params(golden):
+    """wlh.calculate_params restated (both branches of the surface term, neutrons and protons)."""
+    g = golden("wlh_shape_params")
+    pr = golden("wlh_params")
+    k = 0
+    for prj_a, prj_z, A, Z, E in g["cases"]:
+        prj, tgt = (int(prj_a), int(prj_z)), (int(A), int(Z))
+        plist = [pr["mean_n"]] + list(pr["samples_n"][:3]) if prj == (1, 0) else [pr["mean_p"]] + list(pr["samples_p"][:3])
+        for p in plist:
+            c, s_, co = orc.wlh_shape_params(prj, tgt, float(E), p)
+            np.testing.assert_allclose(np.array(list(c) + list(s_) + list(co), dtype=np.float64), g["shapes"][k], rtol=1e-14, atol=0)
+            k += 1
+    assert k == len(g["shapes"])
 
 
 def test_local_rk_case(golden):
