@@ -284,7 +284,7 @@ static __device__ __noinline__ PairPotentials eval_pair_potentials(int model, co
     double co;
     const double rr[2] = {r0, r1};
     double2 vc[2], vs[2];
-#pragma unroll 1
+#pragma unroll  // both mesh points in one instruction stream: the chains (exp, divisions) are latency bound
     for (int s = 0; s < 2; ++s) {
         eval_shape(sh, rr[s], vc[s], vs[s], co);
         vc[s].x += co;
