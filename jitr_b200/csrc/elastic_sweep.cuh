@@ -81,14 +81,12 @@ struct GenericSolver {
         Ts = T;
         bs = b;
     }
-    // d0, d1: diagonal entries of rows lane and lane + 32
-    __device__ __forceinline__ double2 solve(const double2 d0, const double2 d1, int& singular, const bool,
-                                             unsigned long long*) {
+    // [[That + diag, 0, b], [0, I, 0], [b^T, 0, 0]] in the warp's region
+    __device__ __forceinline__ void assemble(const double2 d0, const double2 d1) {
         const int P = g.P, LD = g.LD;
         const int n0 = lane, n1 = lane + 32;
         const bool v0 = n0 < N, v1 = n1 < N;
         const double2 zero2 = make_double2(0.0, 0.0);
-        // ---- assemble the bordered matrix  [[That + diag, 0, b], [0, I, 0], [b^T, 0, 0]]
         for (int i = 0; i < N; ++i) {
             const double* Trow = Ts + i * N;
             double2* Mrow = M + i * LD;
@@ -112,6 +110,20 @@ struct GenericSolver {
         }
         for (int j = N + lane; j <= P; j += 32) M[P * LD + j] = zero2;  // z row: padding + corner
         __syncwarp();
+    }
+    // d0, d1: diagonal entries of rows lane and lane + 32.  P <= 64: threshold-pivoted symmetric elimination
+    // first (lu_sym.cuh), partial pivoting (lu_warp.cuh) when a diagonal entry fails the test or P > 64.
+    __device__ __forceinline__ double2 solve(const double2 d0, const double2 d1, int& singular, const bool symmetric,
+                                             unsigned long long* fallbacks) {
+        assemble(d0, d1);
+        if (symmetric && g.P <= 64) {
+            int fail = 0;
+            const double2 corner = sym_schur_inplace(M, g.P, g.LD, lane, fail);
+            __syncwarp();
+            if (!fail) return corner;
+            if (lane == 0 && fallbacks) atomicAdd(fallbacks, 1ULL);
+            assemble(d0, d1);
+        }
         const double2 corner = bordered_schur<MAXNS>(M, g, lane, singular);
         __syncwarp();
         return corner;

@@ -156,6 +156,113 @@ __device__ __forceinline__ void sym_trailing_update(double2* __restrict__ M, con
     }
 }
 
+// lower-triangle trailing update after panel J0 of an n x n matrix of any order (tile columns in blocks of 3)
+__device__ __forceinline__ void sym_trailing_update_blocks(double2* __restrict__ M, const int LD, const int J0,
+                                                           const int nt, const int lane) {
+    const int R0 = J0 + 8;
+    const int fr = lane >> 2, fk = lane & 3;
+    const int rho = (fr >> 1) + 4 * (fr & 1);
+    const int part = fk & 1, pn = fr & 1;
+    const double* Md = reinterpret_cast<const double*>(M);
+    const int a_off = 2 * (rho * LD + J0 + 4 * (fk >> 1)) + part;
+    const int b_off = 2 * ((J0 + 4 * (fk >> 1)) * LD + (fr >> 1)) + (part ^ pn);
+    const int bflip = (part & (pn ^ 1)) ? 0x80000000 : 0;
+    const int c_off = rho * LD + R0 + fk;
+#pragma unroll 1
+    for (int q0 = 0; q0 < nt; q0 += 3) {
+        double b[3][2][4];
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+            if (q0 + q < nt) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+#pragma unroll
+                    for (int s = 0; s < 4; ++s) {
+                        const double v = Md[b_off + 2 * (s * LD + R0 + 8 * (q0 + q) + 4 * h)];
+                        b[q][h][s] = __hiloint2double(__double2hiint(v) ^ bflip, __double2loint(v));
+                    }
+            }
+#pragma unroll 1
+        for (int tr = q0; tr < nt; ++tr) {
+            const int rbase = (R0 + 8 * tr) * LD;
+            double a[4];
+#pragma unroll
+            for (int s = 0; s < 4; ++s) a[s] = dneg(Md[a_off + 2 * (rbase + s)]);
+            double2* Crow = M + rbase + c_off + 8 * q0;
+#pragma unroll
+            for (int q = 0; q < 3; ++q)
+                if (q0 + q <= tr) {  // lower triangle (diagonal tiles in full)
+                    double2 c0 = Crow[8 * q], c1 = Crow[8 * q + 4];
+#pragma unroll
+                    for (int s = 0; s < 4; ++s) {
+                        dmma884(c0.x, c0.y, a[s], b[q][0][s]);
+                        dmma884(c1.x, c1.y, a[s], b[q][1][s]);
+                    }
+                    Crow[8 * q] = c0;
+                    Crow[8 * q + 4] = c1;
+                }
+        }
+    }
+}
+
+// One panel (columns J0..J0+7) of the threshold-pivoted symmetric elimination of a matrix ASSEMBLED in shared
+// memory: rows/columns 0..P-1, RHS in column P, leading dimension LD (the layout of lu_warp.cuh without its z
+// row).  NS row slots per lane.  Returns true after the last panel.
+template <int NS>
+__device__ __forceinline__ bool sym_panel_inplace(double2* __restrict__ M, const int P, const int LD, const int J0,
+                                                  const int lane, double2& cacc, int& fail) {
+    const int nrows = P - J0;
+    double2 p[NS][9];
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+        const int i = 32 * s + lane;
+        const int row = J0 + (i < nrows ? i : 0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) p[s][j] = M[row * LD + J0 + j];
+        p[s][8] = M[row * LD + P];
+    }
+    sym_panel_eliminate<NS>(
+        p, nrows, lane, cacc, fail,
+        [&](int s, int kk, double2 v) {
+            const int i = 32 * s + lane;  // the unscaled column entry of row J0 + i is U[kk][i]: its (upper) position
+            if (i > kk && i < nrows) M[(J0 + kk) * LD + J0 + i] = v;
+        },
+        [&](int kk, int j) { return M[(J0 + kk) * LD + J0 + j]; });
+    if (nrows <= 8) return true;
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+        const int i = 32 * s + lane;
+        if (i >= 8 && i < nrows) {
+            double2* dst = M + (J0 + i) * LD;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dst[J0 + j] = p[s][j];
+            dst[P] = p[s][8];
+        }
+    }
+    return false;
+}
+
+// Threshold-pivoted symmetric elimination of an assembled bordered system (generic solver modes, P <= 64).
+// Returns -b^T A^-1 b; fail != 0: a diagonal entry failed the test (the caller re-assembles and uses
+// partial pivoting).
+__device__ __forceinline__ double2 sym_schur_inplace(double2* __restrict__ M, const int P, const int LD, const int lane,
+                                                     int& fail) {
+    double2 cacc = make_double2(0.0, 0.0);
+    JITR_PH_INIT
+#pragma unroll 1
+    for (int J0 = 0; J0 < P; J0 += 8) {
+        const bool last = (P - J0 > 32) ? sym_panel_inplace<2>(M, P, LD, J0, lane, cacc, fail)
+                                        : sym_panel_inplace<1>(M, P, LD, J0, lane, cacc, fail);
+        JITR_PH(0)
+        if (last) break;
+        __syncwarp();
+        sym_trailing_update_blocks(M, LD, J0, (P - J0 - 8) >> 3, lane);
+        __syncwarp();
+        JITR_PH(2)
+    }
+    return cacc;
+}
+
 // Returns -b^T (That + diag d)^-1 b on every lane; fail != 0: a pivot failed the threshold test and the
 // returned value is meaningless.  Arguments as fast_schur (lu_fast.cuh); W needs SymGeom<PT>::WALLOC elements.
 template <int PT>
