@@ -233,6 +233,27 @@ def test_sweep_every_nbasis_path_vs_oracle(N):
             assert relerr(Sg[b, 1, 1 : len(sm)], sm[1:]) < RTOL_S
 
 
+def test_sweep_is_deterministic_under_dynamic_work_distribution(golden):
+    """Pairs are handed to the warps dynamically and the warps run in loose lock step: results must be bit
+    identical whatever the batch size (awkward pair counts around the warps-per-CTA and grid multiples also
+    exercise the termination of the lock step)."""
+    g = golden("kduq_params")
+    rows = np.zeros((1800, 40))
+    rows[:, :37] = np.tile(g["federal_n"], (5, 1))[:1800]
+    rx = ElasticReaction((208, 82), (1, 0), mass_target=193687.12278341982, mass_projectile=939.5654983938299)
+    solver = jitr_b200.Solver(40)
+    ang = np.linspace(0.1, np.pi, 11)
+    wss = [jitr_b200.DifferentialWorkspace.build_from_system(rx, rx.kinematics(E), 12.0, solver, 30, ang) for E in (7.0, 61.0)]
+    sweep = jitr_b200.ElasticSweep(wss)
+    model = kduq.KDUQ((1, 0))
+    full = torch.tensor(rows, device="cuda")
+    Sref, nlref, stref = sweep.smatrix_params(model, full)
+    assert int(stref.abs().sum()) == 0
+    for B in (1, 5, 6, 7, 73, 74, 75, 887, 888, 889, 1799):
+        S, nl, st = sweep.smatrix_params(model, full[:B])
+        assert torch.equal(nl, nlref[:B]) and torch.equal(S, Sref[:B])
+
+
 def test_no_early_break_and_size_independent_properties():
     """tol <= 0 issues every (l, j); for a REAL potential |S| = 1 (unitarity) for every partial wave
     and sigma_rxn = 0 -- a size-independent property checked on a larger batch."""
