@@ -288,6 +288,7 @@ class ElasticSweep:
             if iw.solver.kernel.quadrature.nbasis != self.N or iw.lmax != self.lmax or iw.smatrix_abs_tol != self.tol:
                 raise ValueError("all workspaces of a sweep must share nbasis, lmax and smatrix_abs_tol")
         self.tabs = self.solver.device_tables(self.device)
+        self._free_cache = {}
         etab = np.stack([energy_table_row(iw.reaction, iw.kinematics, iw.a) for iw in self.integral])
         asym = np.stack([iw._asym_table for iw in self.integral])  # (E, L1, 4)
         t = lambda v, dt: torch.tensor(np.ascontiguousarray(v), dtype=dt, device=self.device)
@@ -314,6 +315,72 @@ class ElasticSweep:
         rf = [model.radius_factor(iw.reaction) for iw in self.integral]
         self.etab[:, _cabi.ET_RSCALE] = torch.tensor(rf, dtype=torch.float64, device=self.device)
 
+    # ------------------------------------------------------------------ nbasis > 64
+    MAX_FUSED_NBASIS = 64
+
+    def _eval_potentials(self, model, params):
+        """Built-in forms on the mesh of every energy: (B, E, N) central, spin_orbit (complex) and coulomb (real)
+        CUDA tensors (jitr_b200_eval_potentials: the same device code the fused sweep inlines)."""
+        import torch
+
+        B = params.shape[0]
+        c = torch.empty((B, self.nE, self.N), dtype=torch.complex128, device=self.device)
+        so = torch.empty_like(c)
+        co = torch.empty((B, self.nE, self.N), dtype=torch.float64, device=self.device)
+        rc = _cabi.lib().jitr_b200_eval_potentials(
+            self.N, model.model_id, B, self.nE, _cabi.ptr(self.tabs["x"]), _cabi.ptr(self.etab), _cabi.ptr(params),
+            params.shape[1], _cabi.ptr(c), _cabi.ptr(so), _cabi.ptr(co), _cabi.stream_ptr(),
+        )
+        _cabi.check(rc, "jitr_b200_eval_potentials")
+        return c, so, co.to(torch.complex128)
+
+    def _smatrix_large(self, central, spin_orbit, coulomb, out=None):
+        """nbasis beyond the fused kernel (N > 64, e.g. the reference's Frescox regression cases with N = 100):
+        per (energy, l) the systems  A = F_l + diag((V_c + V_C + (l.s) V_so) / E0)  of all samples and both j go
+        through the general batched solve (jitr_b200_solve_batched); the early break of
+        xs/elastic.py:178-181 is applied afterwards (and the l loop stops once every sample has met it)."""
+        import torch
+
+        B, L1 = central.shape[0], self.lmax + 1
+        S, nl, status = self._alloc_S(B) if out is None else out
+        S.zero_()
+        status.zero_()
+        vc = central if coulomb is None else central + coulomb
+        q = self.solver.kernel.quadrature
+        eye = np.eye(self.N)
+        for e, iw in enumerate(self.integral):
+            kin = iw.kinematics
+            done = torch.zeros(B, dtype=torch.bool, device=self.device)
+            nle = torch.full((B,), L1, dtype=torch.int32, device=self.device)
+            for l in range(L1):
+                key = (e, l)
+                if key not in self._free_cache:
+                    self._free_cache[key] = torch.tensor(q.kinetic_matrix(iw.a, l) - eye, dtype=torch.complex128, device=self.device)
+                asym_l = self.asym[e, l].reshape(4, 1)
+                if l == 0 or spin_orbit is None:
+                    loc = vc[:, e]
+                    r = self.solver.solve_batch(iw.a, kin.Ecm, kin.k, 1, self._free_cache[key], asym_l, local_potential=loc)
+                    sp = r["S"][:, 0, 0]
+                    sm = sp if l > 0 else torch.zeros_like(sp)
+                    st = r["status"]
+                else:
+                    loc = torch.cat([vc[:, e] + l * spin_orbit[:, e], vc[:, e] - (l + 1) * spin_orbit[:, e]], dim=0)
+                    r = self.solver.solve_batch(iw.a, kin.Ecm, kin.k, 1, self._free_cache[key], asym_l, local_potential=loc)
+                    sp, sm = r["S"][:B, 0, 0], r["S"][B:, 0, 0]
+                    st = torch.maximum(r["status"][:B], r["status"][B:])
+                live = ~done
+                S[:, e, 0, l] = torch.where(live, sp, torch.zeros_like(sp))
+                S[:, e, 1, l] = torch.where(live, sm, torch.zeros_like(sm))
+                status[:, e] = torch.maximum(status[:, e], torch.where(live, st, torch.zeros_like(st)))
+                if l >= 1 and self.tol > 0:
+                    hit = live & ((1 - sp).abs() < self.tol) & ((1 - sm).abs() < self.tol)
+                    nle = torch.where(hit, torch.full_like(nle, l + 1), nle)
+                    done = done | hit
+                    if bool(done.all()):
+                        break
+            nl[:, e] = nle
+        return S, nl, status
+
     # ------------------------------------------------------------------ S-matrix
     def _alloc_S(self, B):
         import torch
@@ -333,6 +400,9 @@ class ElasticSweep:
             self.set_radius_factor(model)
             self._rf_model = model
         B = params.shape[0]
+        if self.N > self.MAX_FUSED_NBASIS:
+            c, so, co = self._eval_potentials(model, params)
+            return self._smatrix_large(c, so, co, out=out)
         S, nl, status = self._alloc_S(B) if out is None else out
         rc = _cabi.lib().jitr_b200_elastic_sweep_params(
             self.N, self.lmax, model.model_id, B, self.nE, _cabi.ptr(self.tabs["That"]), _cabi.ptr(self.tabs["x"]),
@@ -358,6 +428,8 @@ class ElasticSweep:
         spin_orbit = prep(spin_orbit, "spin_orbit_potential")
         coulomb = prep(coulomb, "coulomb_potential")
         B = central.shape[0]
+        if self.N > self.MAX_FUSED_NBASIS:
+            return self._smatrix_large(central, spin_orbit, coulomb, out=out)
         S, nl, status = self._alloc_S(B) if out is None else out
         rc = _cabi.lib().jitr_b200_elastic_sweep_tensors(
             self.N, self.lmax, B, self.nE, _cabi.ptr(self.tabs["That"]), _cabi.ptr(self.tabs["x"]), _cabi.ptr(self.tabs["b"]),

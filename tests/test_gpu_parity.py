@@ -254,6 +254,37 @@ def test_sweep_is_deterministic_under_dynamic_work_distribution(golden):
         assert torch.equal(nl, nlref[:B]) and torch.equal(S, Sref[:B])
 
 
+def test_workspace_beyond_fused_nbasis_vs_oracle():
+    """N = 80 > 64 (the reference's Frescox regression cases use N up to 100): the workspace API routes the
+    partial waves through the general batched solve; same S, same early break, same cross sections."""
+    N, lmax = 80, 14
+    rx = ElasticReaction((78, 28), (1, 1), mass_target=72601.0, mass_projectile=938.271653086152)
+    kin = rx.kinematics(20.0)
+    ang = np.linspace(0.2, 3.0, 23)
+    ws = jitr_b200.DifferentialWorkspace.build_from_system(rx, kin, 16.0, jitr_b200.Solver(N), lmax, ang)
+    r = ws.radial_grid()
+    model = LocalOpticalPotential()
+    p = np.array([[52.0, 1.17, 0.75, 2.5, 1.26, 0.58, 7.5, 0.0, 1.26, 0.58, 6.2, -0.1, 1.01, 0.75, 1.25],
+                  [48.0, 1.20, 0.70, 1.5, 1.30, 0.60, 8.5, 0.5, 1.22, 0.55, 5.0, 0.0, 1.05, 0.70, 1.30]])
+    x, status = ws._as_sweep().xs_params(model, torch.tensor(p, device="cuda"), return_status=True)
+    S, nl, _ = ws.integral_workspace.smatrix_params(model, torch.tensor(p, device="cuda"))
+    assert int(status.abs().sum()) == 0
+    ow = orc.ElasticWorkspace(N, lmax, 16.0, tuple(kin), ang, 28)
+    for b in range(2):
+        c, so, co = orc.local_omp_potentials(r, 78, 28, p[b])
+        sp, sm = ow.smatrix(c, so, co)
+        assert int(nl[b]) == len(sp)
+        assert relerr(S[b, 0, : len(sp)].cpu().numpy(), sp) < RTOL_S
+        assert relerr(S[b, 1, 1 : len(sm)].cpu().numpy(), sm[1:]) < RTOL_S
+        dsdo, Ay, Q, tot, rxn = ow.xs(c, so, co)
+        assert relerr(x.dsdo[b, 0].cpu().numpy(), dsdo) < RTOL_XS
+        assert abs(float(x.rxn[b, 0]) - rxn) / rxn < RTOL_XS
+    # single-sample reference API on the same workspace
+    c, so, co = orc.local_omp_potentials(r, 78, 28, p[0])
+    one = ws.xs(c, so, co)
+    assert relerr(one.dsdo, ow.xs(c, so, co)[0]) < RTOL_XS
+
+
 def test_no_early_break_and_size_independent_properties():
     """tol <= 0 issues every (l, j); for a REAL potential |S| = 1 (unitarity) for every partial wave
     and sigma_rxn = 0 -- a size-independent property checked on a larger batch."""
