@@ -150,7 +150,8 @@ int jitr_b200_elastic_observables(int lmax, int n_angles, long long n_samples, i
  *   weights     [nch] incoming-channel weights (rmatrix.py:203-205)
  *   R, S        [batch][nch][nch] complex;  uext [batch][nch] complex
  *   coeffs      [batch][nch][N] complex or NULL              (core.py:63-82)
- *   workspace   [batch][n][n+nch] complex scratch in device memory (only read/written here)
+ *   workspace   device scratch of jitr_b200_solve_workspace_bytes(nbasis, nch, batch, coeffs != NULL) bytes
+ *               (NULL when that is 0); only read and written inside the call
  */
 int jitr_b200_solve_batched(int nbasis, int nch, long long batch, const double* free_matrix,
                             long long free_stride, const double* local, const double* nonlocal_,
@@ -158,6 +159,9 @@ int jitr_b200_solve_batched(int nbasis, int nch, long long batch, const double* 
                             int sys_stride, const double* bvec, const double* asym, long long asym_stride,
                             const double* weights, double* R, double* S, double* uext, double* coeffs,
                             double* workspace, int* status, void* stream);
+
+/* bytes of device scratch jitr_b200_solve_batched needs for this problem (0: none; -1: bad arguments) */
+long long jitr_b200_solve_workspace_bytes(int nbasis, int nch, long long batch, int coeffs);
 
 /*
  * FP64 pipe probes (roofline denominators; MEASURED_PEAKS.json has no FP64 entry).

@@ -39,6 +39,76 @@ struct GenArgs {
 constexpr int kGenThreads = 256;
 constexpr int kMaxCh = 16;
 
+// R (in small[0 .. nch^2)) -> Z+-, S = Z+^-1 Z-, u'_ext; writes R, S, uext, status of system sysi.  Called by the
+// whole CTA after a barrier that made R visible; ends with a barrier (ue = small + 3 kMaxCh^2 is then readable).
+__device__ __forceinline__ void finish_system(const GenArgs& A, const long long sysi, const double a, const int bad_flags,
+                                              double2* small, const int tid, const int nt) {
+    const int nch = A.nch;
+    double2* Rm = small;                          // [nch][nch]
+    double2* Zp = small + kMaxCh * kMaxCh;        // [nch][nch]
+    double2* Zm = small + 2 * kMaxCh * kMaxCh;    // [nch][nch] -> S
+    double2* ue = small + 3 * kMaxCh * kMaxCh;    // [nch]
+    const double2* as = A.asym + (size_t)sysi * A.asym_stride;  // [4][nch]: Hp, Hm, Hpp, Hmp
+    for (int ij = tid; ij < nch * nch; ij += nt) {
+        const int i = ij / nch, j = ij - i * nch;
+        // Z+- = diag(H+-) - a R diag(H+-')   (core.py:51-53)
+        const double2 r = Rm[ij];
+        const double2 tp = cmul(r, as[2 * nch + j]), tm = cmul(r, as[3 * nch + j]);
+        double2 zp = make_double2(-a * tp.x, -a * tp.y), zm = make_double2(-a * tm.x, -a * tm.y);
+        if (i == j) {
+            zp.x += as[j].x; zp.y += as[j].y;
+            zm.x += as[nch + j].x; zm.y += as[nch + j].y;
+        }
+        Zp[ij] = zp;
+        Zm[ij] = zm;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        // S = Z+^-1 Z-  by Gaussian elimination with partial pivoting (nch <= kMaxCh)
+        for (int k = 0; k < nch; ++k) {
+            int p = k;
+            double best = -1.0;
+            for (int i = k; i < nch; ++i) {
+                const double2 v = Zp[i * nch + k];
+                const double m = v.x * v.x + v.y * v.y;
+                if (m > best) { best = m; p = i; }
+            }
+            if (p != k)
+                for (int c = 0; c < nch; ++c) {
+                    double2 t = Zp[k * nch + c]; Zp[k * nch + c] = Zp[p * nch + c]; Zp[p * nch + c] = t;
+                    t = Zm[k * nch + c]; Zm[k * nch + c] = Zm[p * nch + c]; Zm[p * nch + c] = t;
+                }
+            const double2 rinv = crecip(Zp[k * nch + k]);
+            for (int i = k + 1; i < nch; ++i) {
+                const double2 l = cmul(Zp[i * nch + k], rinv);
+                for (int c = k + 1; c < nch; ++c) cfnma(Zp[i * nch + c], l, Zp[k * nch + c]);
+                for (int c = 0; c < nch; ++c) cfnma(Zm[i * nch + c], l, Zm[k * nch + c]);
+            }
+        }
+        for (int c = 0; c < nch; ++c)
+            for (int i = nch - 1; i >= 0; --i) {
+                double2 v = Zm[i * nch + c];
+                for (int m = i + 1; m < nch; ++m) cfnma(v, Zp[i * nch + m], Zm[m * nch + c]);
+                Zm[i * nch + c] = cmul(v, crecip(Zp[i * nch + i]));
+            }
+        // u'_ext = (i/2)(H-' w - S H+')   (core.py:58)
+        int bad = bad_flags;
+        for (int i = 0; i < nch; ++i) {
+            double2 v = make_double2(as[3 * nch + i].x * A.weights[i], as[3 * nch + i].y * A.weights[i]);
+            for (int j = 0; j < nch; ++j) cfnma(v, Zm[i * nch + j], as[2 * nch + j]);
+            ue[i] = make_double2(-0.5 * v.y, 0.5 * v.x);
+            if (!(isfinite(v.x) && isfinite(v.y))) bad |= 1;
+        }
+        A.status[sysi] = (bad & 1) ? JITR_B200_STATUS_NONFINITE : ((bad & 2) ? JITR_B200_STATUS_SINGULAR : JITR_B200_STATUS_OK);
+    }
+    __syncthreads();
+    for (int ij = tid; ij < nch * nch; ij += nt) {
+        A.R[(size_t)sysi * nch * nch + ij] = Rm[ij];
+        A.S[(size_t)sysi * nch * nch + ij] = Zm[ij];
+    }
+    for (int i = tid; i < nch; i += nt) A.uext[(size_t)sysi * nch + i] = ue[i];
+}
+
 template <bool IN_SMEM>
 __global__ void __launch_bounds__(kGenThreads) general_solve_kernel(const GenArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -169,9 +239,6 @@ __global__ void __launch_bounds__(kGenThreads) general_solve_kernel(const GenArg
         __syncthreads();
         // ---------------- R_ij = b^T X_(i-block, j) / a^2     (core.py:15-22)
         double2* Rm = small;                          // [nch][nch]
-        double2* Zp = small + kMaxCh * kMaxCh;        // [nch][nch]
-        double2* Zm = small + 2 * kMaxCh * kMaxCh;    // [nch][nch] -> S
-        double2* ue = small + 3 * kMaxCh * kMaxCh;    // [nch]
         for (int ij = tid; ij < nch * nch; ij += nt) {
             const int i = ij / nch, j = ij - i * nch;
             double2 acc = make_double2(0.0, 0.0);
@@ -183,65 +250,8 @@ __global__ void __launch_bounds__(kGenThreads) general_solve_kernel(const GenArg
             Rm[ij] = make_double2(acc.x / (a * a), acc.y / (a * a));
         }
         __syncthreads();
-        const double2* as = A.asym + (size_t)sysi * A.asym_stride;  // [4][nch]: Hp, Hm, Hpp, Hmp
-        for (int ij = tid; ij < nch * nch; ij += nt) {
-            const int i = ij / nch, j = ij - i * nch;
-            // Z+- = diag(H+-) - a R diag(H+-')   (core.py:51-53)
-            const double2 r = Rm[ij];
-            const double2 tp = cmul(r, as[2 * nch + j]), tm = cmul(r, as[3 * nch + j]);
-            double2 zp = make_double2(-a * tp.x, -a * tp.y), zm = make_double2(-a * tm.x, -a * tm.y);
-            if (i == j) {
-                zp.x += as[j].x; zp.y += as[j].y;
-                zm.x += as[nch + j].x; zm.y += as[nch + j].y;
-            }
-            Zp[ij] = zp;
-            Zm[ij] = zm;
-        }
-        __syncthreads();
-        if (tid == 0) {
-            // S = Z+^-1 Z-  by Gaussian elimination with partial pivoting (nch <= kMaxCh)
-            for (int k = 0; k < nch; ++k) {
-                int p = k;
-                double best = -1.0;
-                for (int i = k; i < nch; ++i) {
-                    const double2 v = Zp[i * nch + k];
-                    const double m = v.x * v.x + v.y * v.y;
-                    if (m > best) { best = m; p = i; }
-                }
-                if (p != k)
-                    for (int c = 0; c < nch; ++c) {
-                        double2 t = Zp[k * nch + c]; Zp[k * nch + c] = Zp[p * nch + c]; Zp[p * nch + c] = t;
-                        t = Zm[k * nch + c]; Zm[k * nch + c] = Zm[p * nch + c]; Zm[p * nch + c] = t;
-                    }
-                const double2 rinv = crecip(Zp[k * nch + k]);
-                for (int i = k + 1; i < nch; ++i) {
-                    const double2 l = cmul(Zp[i * nch + k], rinv);
-                    for (int c = k + 1; c < nch; ++c) cfnma(Zp[i * nch + c], l, Zp[k * nch + c]);
-                    for (int c = 0; c < nch; ++c) cfnma(Zm[i * nch + c], l, Zm[k * nch + c]);
-                }
-            }
-            for (int c = 0; c < nch; ++c)
-                for (int i = nch - 1; i >= 0; --i) {
-                    double2 v = Zm[i * nch + c];
-                    for (int m = i + 1; m < nch; ++m) cfnma(v, Zp[i * nch + m], Zm[m * nch + c]);
-                    Zm[i * nch + c] = cmul(v, crecip(Zp[i * nch + i]));
-                }
-            // u'_ext = (i/2)(H-' w - S H+')   (core.py:58)
-            int bad = redi[33];
-            for (int i = 0; i < nch; ++i) {
-                double2 v = make_double2(as[3 * nch + i].x * A.weights[i], as[3 * nch + i].y * A.weights[i]);
-                for (int j = 0; j < nch; ++j) cfnma(v, Zm[i * nch + j], as[2 * nch + j]);
-                ue[i] = make_double2(-0.5 * v.y, 0.5 * v.x);
-                if (!(isfinite(v.x) && isfinite(v.y))) bad |= 1;
-            }
-            A.status[sysi] = (bad & 1) ? JITR_B200_STATUS_NONFINITE : ((bad & 2) ? JITR_B200_STATUS_SINGULAR : JITR_B200_STATUS_OK);
-        }
-        __syncthreads();
-        for (int ij = tid; ij < nch * nch; ij += nt) {
-            A.R[(size_t)sysi * nch * nch + ij] = Rm[ij];
-            A.S[(size_t)sysi * nch * nch + ij] = Zm[ij];
-        }
-        for (int i = tid; i < nch; i += nt) A.uext[(size_t)sysi * nch + i] = ue[i];
+        finish_system(A, sysi, a, redi[33], small, tid, nt);
+        const double2* ue = small + 3 * kMaxCh * kMaxCh;
         if (A.coeffs) {
             // x = A^-1 vec_i(b u'_ext,i) = sum_i u'_ext,i X[:, i]    (core.py:81-82)
             for (int r = tid; r < n; r += nt) {
@@ -344,6 +354,339 @@ __global__ void __launch_bounds__(256, 1) warp_solve_kernel(const GenArgs A) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Coupled-channel / large systems (BASELINE config 5: 3 channels x N = 50, n = 150): one CTA per system,
+// right-looking blocked LU with partial pivoting of the BORDERED matrix
+//        [ A    0   B ]    rows 0..n-1    (identity padding up to P = 8 ceil(n/8))
+//        [ 0    I   0 ]
+//        [ B^T  0   0 ]    rows P..P+nch-1: one "z" row per channel (never a pivot candidate)
+// whose corner block is left as -B^T A^-1 B = -a^2 R (rmatrix/core.py:15-22 without the inverse).  The matrix
+// (PR x PC complex128, 410 KB for config 5 -- more than one SM's shared memory) lives in a per-CTA slab of
+// the device workspace, i.e. in L2 (148 x 2 slabs = 121 MB of the 126 MB); what is reused stays on chip:
+//   P  the 8-column panel in REGISTERS, one matrix row per thread; pivot search REDUX per warp + one
+//      shared-memory exchange per column (two CTA barriers per column); rows are not moved, each thread
+//      tracks the position of its row;
+//   U  thread c owns trailing column c: gathers the eight pivot rows from their OLD positions, moves the
+//      (at most eight) displaced rows to the positions the pivots left, forward-substitutes with L11 from
+//      shared memory, leaves U12 in shared memory (and in the slab when coefficients are wanted);
+//   T  A22 -= L21 U12 on DMMA m8n8k4 in the real representation of the complex product (fragment mapping of
+//      lu_warp.cuh), L21 and U12 from shared memory, the C tiles streamed slab -> accumulators -> slab.
+// Wavefunction coefficients (core.py:63-82) add a blocked back substitution on the stored U.
+// ---------------------------------------------------------------------------------------------
+constexpr int kBlkThreads = 256;
+constexpr int kBlkLpLd = 9;
+
+struct BlkGeom {
+    int P, PR, PC;       // padded order, rows (P + z rows), columns (P + RHS columns); PR == PC
+    int ub_ld;           // odd leading dimension of the U12 buffer
+    int off_l11, off_ub, off_prow, off_small, off_xs, off_int;  // shared-memory offsets in double2 units
+};
+
+__host__ __device__ inline BlkGeom blk_geom(int n, int nch) {
+    BlkGeom g;
+    g.P = (n + 7) & ~7;
+    const int zb = (nch + 7) & ~7;
+    g.PR = g.P + zb;
+    g.PC = g.P + zb;
+    g.ub_ld = (g.PC - 8) | 1;
+    int o = (g.PR - 8) * kBlkLpLd;  // Lp
+    g.off_l11 = o; o += 64;
+    g.off_ub = o; o += 8 * g.ub_ld;
+    g.off_prow = o; o += 10;
+    g.off_small = o; o += 4 * kMaxCh * kMaxCh;
+    g.off_xs = o; o += 8 * kMaxCh;
+    g.off_int = o; o += 8;  // 32 ints
+    return g;
+}
+static inline size_t blk_smem_bytes(const BlkGeom& g) { return (size_t)(g.off_int + 8 + 8) * 16; }
+
+template <int NQ>
+__device__ __forceinline__ void blk_trailing_item(double2* __restrict__ M, const int ld, const int R0, const int tr,
+                                                  const int tc0, const double* __restrict__ Lpd,
+                                                  const double* __restrict__ Ubd, const int ub_ld, const int lane) {
+    const int fr = lane >> 2, fk = lane & 3;
+    const int rho = (fr >> 1) + 4 * (fr & 1);
+    const int part = fk & 1, pn = fr & 1;
+    const int bflip = (part & (pn ^ 1)) ? 0x80000000 : 0;
+    double2* Crow = M + (size_t)(R0 + 8 * tr + rho) * ld + R0 + 8 * tc0 + fk;
+    double2 c[NQ][2];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+        c[q][0] = Crow[8 * q];
+        c[q][1] = Crow[8 * q + 4];
+    }
+    double a[4];
+#pragma unroll
+    for (int s = 0; s < 4; ++s) a[s] = dneg(Lpd[2 * ((8 * tr + rho) * kBlkLpLd + s + 4 * (fk >> 1)) + part]);
+#pragma unroll
+    for (int s = 0; s < 4; ++s)
+#pragma unroll
+        for (int q = 0; q < NQ; ++q)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const double v = Ubd[2 * ((s + 4 * (fk >> 1)) * ub_ld + 8 * (tc0 + q) + 4 * h + (fr >> 1)) + (part ^ pn)];
+                const double b = __hiloint2double(__double2hiint(v) ^ bflip, __double2loint(v));
+                dmma884(c[q][h].x, c[q][h].y, a[s], b);
+            }
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+        Crow[8 * q] = c[q][0];
+        Crow[8 * q + 4] = c[q][1];
+    }
+}
+
+__global__ void __launch_bounds__(kBlkThreads, 2) block_solve_kernel(const GenArgs A, const BlkGeom G) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int n = A.n, N = A.N, nch = A.nch;
+    const int P = G.P, PR = G.PR, PC = G.PC, ld = G.PC;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(kFull, tid >> 5, 0);
+    constexpr int NW = kBlkThreads / 32;
+    double2* sm = reinterpret_cast<double2*>(smem_raw);
+    double2* Lp = sm;                    // [(PR - 8)][9]  multipliers of the rows below the panel, by position
+    double2* L11 = sm + G.off_l11;       // [8][8]         multipliers inside the pivot rows
+    double2* Ub = sm + G.off_ub;         // [8][ub_ld]     U12 (trailing columns incl. RHS)
+    double2* prow = sm + G.off_prow;     // pivot row (columns j+1..7), [8] = 1/pivot
+    double2* small = sm + G.off_small;
+    double2* xs = sm + G.off_xs;         // [8][kMaxCh] back-substitution block
+    int* si = reinterpret_cast<int*>(sm + G.off_int);
+    int* wkey = si;                      // [8]
+    int* wtid = si + 8;                  // [8]
+    int* src = si + 16;                  // [8] old position of pivot row j
+    int* dfrom = si + 24;                // [8]
+    int* dto = si + 32;                  // [8]
+    int* misc = si + 40;                 // [0] pivot's old position, [1] displaced count, [2] flags
+    double2* M = A.workspace + (size_t)blockIdx.x * PR * ld;
+    const double2 zero2 = make_double2(0.0, 0.0);
+
+    for (long long sysi = blockIdx.x; sysi < A.batch; sysi += gridDim.x) {
+        const double* sy = A.sys + (size_t)sysi * A.sys_stride;
+        const double a = sy[0], E0 = sy[1], k0s = sy[2];
+        const double2* F = A.free_matrix + (size_t)sysi * A.free_stride;
+        const double nl_scale = (a / k0s) / k0s / E0;  // kernel.py:202 (x radius), rmatrix.py:175-178 (/k0, /E0)
+        // ---------------- assemble the bordered matrix into the slab
+        for (int r = warp; r < PR; r += NW) {
+            const int ci = r / N, nn = r - ci * N;
+            for (int c = lane; c < PC; c += 32) {
+                double2 v = zero2;
+                if (r < n) {
+                    if (c < n) {
+                        v = F[(size_t)r * n + c];
+                        const int cj = c / N, mm = c - cj * N;
+                        if (A.interaction) {
+                            const double2 w = A.interaction[(size_t)sysi * n * n + (size_t)r * n + c];
+                            v.x += w.x; v.y += w.y;
+                        } else {
+                            if (A.local && nn == mm) {
+                                const double2 w = A.local[(((size_t)sysi * nch + ci) * nch + cj) * N + nn];
+                                v.x += w.x / E0; v.y += w.y / E0;
+                            }
+                            if (A.nonlocal_) {
+                                const double2 w = A.nonlocal_[((((size_t)sysi * nch + ci) * nch + cj) * N + nn) * N + mm];
+                                const double s = A.wsqrt[nn] * A.wsqrt[mm] * nl_scale;
+                                v.x += w.x * s; v.y += w.y * s;
+                            }
+                        }
+                    } else if (c >= P && c - P == ci) {
+                        v.x = A.bvec[nn];
+                    }
+                } else if (r < P) {
+                    if (c == r) v.x = 1.0;
+                } else if (c < n) {
+                    const int cj = c / N;
+                    if (cj == r - P) v.x = A.bvec[c - cj * N];
+                }
+                M[(size_t)r * ld + c] = v;
+            }
+        }
+        if (tid == 0) misc[2] = 0;
+        __syncthreads();
+        // ---------------- blocked elimination
+#pragma unroll 1
+        for (int k0 = 0; k0 < P; k0 += 8) {
+            const int m = PR - k0;
+            const bool have = tid < m;
+            const int start = k0 + tid;
+            int pos = start;
+            const bool cand = have && start < P;
+            bool done = false;
+            double2 p[8];
+            {
+                const double2* rowp = M + (size_t)(have ? start : k0) * ld + k0;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) p[c] = rowp[c];
+            }
+            if (tid == 0) misc[1] = 0;
+            const int nw = (m + 31) >> 5;  // warps that hold rows
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (warp < nw) {
+                    const int key = (cand && !done) ? __double2hiint(fabs(p[j].x) + fabs(p[j].y)) : -1;
+                    const int wmax = __reduce_max_sync(kFull, key);
+                    const unsigned bal = __ballot_sync(kFull, key == wmax);
+                    if (lane == 0) {
+                        wkey[warp] = wmax;
+                        wtid[warp] = (warp << 5) + __ffs(bal) - 1;
+                    }
+                }
+                __syncthreads();
+                int bk = -2, bt = 0;
+                for (int w = 0; w < nw; ++w) {
+                    const int kk = wkey[w];
+                    if (kk > bk) { bk = kk; bt = wtid[w]; }
+                }
+                if (tid == bt) {
+                    if (bk < 0x00100000) atomicOr(&misc[2], 2);  // zero (or subnormal) pivot
+                    prow[8] = crecip_fast(p[j]);
+#pragma unroll
+                    for (int c = j + 1; c < 8; ++c) prow[c] = p[c];
+                    misc[0] = pos;
+                }
+                __syncthreads();
+                if (tid == bt) {
+                    pos = k0 + j;
+                    done = true;
+                } else if (have && !done) {
+                    if (pos == k0 + j) pos = misc[0];
+                    const double2 l = cmul(p[j], prow[8]);
+                    p[j] = l;
+#pragma unroll
+                    for (int c = j + 1; c < 8; ++c) cfnma(p[c], l, prow[c]);
+                }
+            }
+            if (have) {
+                if (done) {
+                    const int r = pos - k0;
+                    src[r] = start;
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) L11[r * 8 + c] = p[c];
+                    if (A.coeffs) {
+                        double2* rowp = M + (size_t)pos * ld + k0;
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) rowp[c] = p[c];  // U11 on and right of the diagonal
+                    }
+                } else {
+                    double2* lp = Lp + (pos - k0 - 8) * kBlkLpLd;
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) lp[c] = p[c];
+                    if (start < k0 + 8) {
+                        const int i = atomicAdd(&misc[1], 1);
+                        dfrom[i] = start;
+                        dto[i] = pos;
+                    }
+                }
+            }
+            __syncthreads();
+            // ------------ phase U (+ the row moves of the trailing columns)
+            const int wtr = PC - k0 - 8;
+            if (tid < wtr) {
+                const int col = k0 + 8 + tid;
+                double2 av[8], dv[8];
+                const int nd = misc[1];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) av[j] = M[(size_t)src[j] * ld + col];
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    if (i < nd) dv[i] = M[(size_t)dfrom[i] * ld + col];
+#pragma unroll
+                for (int kk = 1; kk < 8; ++kk)
+#pragma unroll
+                    for (int k2 = 0; k2 < kk; ++k2) cfnma(av[kk], L11[kk * 8 + k2], av[k2]);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) Ub[j * G.ub_ld + tid] = av[j];
+                if (A.coeffs) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) M[(size_t)(k0 + j) * ld + col] = av[j];
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    if (i < nd) M[(size_t)dto[i] * ld + col] = dv[i];
+            }
+            __syncthreads();
+            // ------------ phase T
+            {
+                const int ntr = (PR - k0 - 8) >> 3, ntc = wtr >> 3;
+                const int ncb = (ntc + 2) / 3;
+                const double* Lpd = reinterpret_cast<const double*>(Lp);
+                const double* Ubd = reinterpret_cast<const double*>(Ub);
+                for (int it = warp; it < ncb * ntr; it += NW) {
+                    const int cb = it / ntr, tr = it - cb * ntr;
+                    const int rem = ntc - 3 * cb;  // warp-uniform
+                    if (rem >= 3) blk_trailing_item<3>(M, ld, k0 + 8, tr, 3 * cb, Lpd, Ubd, G.ub_ld, lane);
+                    else if (rem == 2) blk_trailing_item<2>(M, ld, k0 + 8, tr, 3 * cb, Lpd, Ubd, G.ub_ld, lane);
+                    else blk_trailing_item<1>(M, ld, k0 + 8, tr, 3 * cb, Lpd, Ubd, G.ub_ld, lane);
+                }
+            }
+            __syncthreads();
+        }
+        // ---------------- R = -corner / a^2
+        for (int ij = tid; ij < nch * nch; ij += kBlkThreads) {
+            const int i = ij / nch, j = ij - i * nch;
+            const double2 cv = M[(size_t)(P + i) * ld + P + j];
+            small[ij] = make_double2(-cv.x / (a * a), -cv.y / (a * a));
+        }
+        __syncthreads();
+        finish_system(A, sysi, a, misc[2], small, tid, kBlkThreads);
+        if (A.coeffs) {
+            // X = U^-1 Y for the nch right-hand sides (columns P..P+nch-1), eight rows at a time from the bottom
+            const double2* ue = small + 3 * kMaxCh * kMaxCh;
+#pragma unroll 1
+            for (int kb = P - 8; kb >= 0; kb -= 8) {
+                if (tid < nch) {
+                    double2 x[8];
+#pragma unroll
+                    for (int r = 7; r >= 0; --r) {
+                        double2 v = M[(size_t)(kb + r) * ld + P + tid];
+#pragma unroll
+                        for (int c = r + 1; c < 8; ++c) cfnma(v, M[(size_t)(kb + r) * ld + kb + c], x[c]);
+                        x[r] = cmul(v, crecip(M[(size_t)(kb + r) * ld + kb + r]));
+                        xs[r * kMaxCh + tid] = x[r];
+                        M[(size_t)(kb + r) * ld + P + tid] = x[r];
+                    }
+                }
+                __syncthreads();
+                for (int t = tid; t < kb * nch; t += kBlkThreads) {
+                    const int r = t / nch, j = t - r * nch;
+                    double2 v = M[(size_t)r * ld + P + j];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) cfnma(v, M[(size_t)r * ld + kb + c], xs[c * kMaxCh + j]);
+                    M[(size_t)r * ld + P + j] = v;
+                }
+                __syncthreads();
+            }
+            // x = A^-1 vec_i(b u'_ext,i) = sum_i u'_ext,i X[:, i]    (core.py:81-82)
+            for (int r = tid; r < n; r += kBlkThreads) {
+                double2 acc = zero2;
+                for (int i = 0; i < nch; ++i) {
+                    const double2 t = cmul(ue[i], M[(size_t)r * ld + P + i]);
+                    acc.x += t.x; acc.y += t.y;
+                }
+                A.coeffs[(size_t)sysi * n + r] = acc;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+static int blk_ctas_per_sm() { return 2; }
+
+static int launch_block_solve(const GenArgs& a, cudaStream_t st) {
+    const BlkGeom g = blk_geom(a.n, a.nch);
+    const size_t smem = blk_smem_bytes(g);
+    static size_t conf = 0;
+    if (smem > conf) {
+        if (cudaFuncSetAttribute(block_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return set_cuda_error("cudaFuncSetAttribute(block_solve)");
+        conf = smem;
+    }
+    long long blocks = (long long)sm_count() * blk_ctas_per_sm();
+    if (blocks > a.batch) blocks = a.batch;
+    block_solve_kernel<<<(unsigned)blocks, kBlkThreads, smem, st>>>(a, g);
+    count_launch();
+    if (cudaGetLastError() != cudaSuccess) return set_cuda_error("block_solve launch");
+    return JITR_B200_OK;
+}
+
 template <int MAXNS>
 static int launch_warp_solve(const GenArgs& a, cudaStream_t st) {
     const int P = (a.N + 7) & ~7, msz = (P + 1) * (P + 1);
@@ -368,6 +711,22 @@ static int launch_warp_solve(const GenArgs& a, cudaStream_t st) {
 }  // namespace jitr
 
 using namespace jitr;
+
+extern "C" long long jitr_b200_solve_workspace_bytes(int nbasis, int nch, long long batch, int coeffs) {
+    if (nbasis < 1 || nch < 1 || nch > kMaxCh || batch < 0) return -1;
+    if (nch == 1 && !coeffs && ((nbasis + 7) & ~7) <= 64) return 0;  // warp-per-system: shared memory only
+    const long long n = (long long)nbasis * nch;
+    const BlkGeom g = blk_geom((int)n, nch);
+    if (g.PR <= kBlkThreads) {  // one slab per resident CTA
+        int sms = sm_count();
+        if (sms <= 0) sms = 148;
+        long long ctas = (long long)sms * blk_ctas_per_sm();
+        if (ctas > batch) ctas = batch;
+        return ctas * g.PR * g.PC * 16;
+    }
+    const long long in_smem = (n * (n + nch) + 2 * n + nch) * 16 + 20000;
+    return in_smem > 232448 ? batch * n * (n + nch) * 16 : 0;
+}
 
 extern "C" int jitr_b200_solve_batched(int nbasis, int nch, long long batch, const double* free_matrix,
                                        long long free_stride, const double* local, const double* nonlocal_,
@@ -396,6 +755,10 @@ extern "C" int jitr_b200_solve_batched(int nbasis, int nch, long long batch, con
     if (nch == 1 && !coeffs && ((nbasis + 7) & ~7) <= 64) {
         if (((nbasis + 7) & ~7) + 1 <= 64) return launch_warp_solve<2>(a, st);
         return launch_warp_solve<3>(a, st);
+    }
+    if (blk_geom(a.n, nch).PR <= kBlkThreads) {
+        if (!workspace) return set_error(JITR_B200_ERR_BAD_ARG, "solve_batched: workspace of jitr_b200_solve_workspace_bytes() bytes required");
+        return launch_block_solve(a, st);
     }
     const int n = a.n, ld = n + nch;
     const size_t scratch = (size_t)(n + ld) * 16 + 32 * 8 + 36 * 4 + (size_t)4 * kMaxCh * kMaxCh * 16;

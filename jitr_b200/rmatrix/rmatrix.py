@@ -287,9 +287,11 @@ class Solver:
         uext = torch.empty((B, nch), dtype=torch.complex128, device=dev)
         coeffs = torch.empty((B, nch, nb), dtype=torch.complex128, device=dev) if wavefunction else None
         status = torch.empty((B,), dtype=torch.int32, device=dev)
-        # scratch only when the augmented system exceeds one SM's shared memory
-        need_ws = (n * (n + nch) + 2 * n + nch) * 16 + 20000 > 232448
-        ws = torch.empty((B, n, n + nch), dtype=torch.complex128, device=dev) if need_ws else None
+        # device scratch of the CTA-per-system kernels (one slab per resident CTA; none for the warp kernel)
+        ws_bytes = L.jitr_b200_solve_workspace_bytes(nb, nch, B, int(bool(wavefunction)))
+        if ws_bytes < 0:
+            raise ValueError("jitr_b200_solve_workspace_bytes: bad arguments")
+        ws = torch.empty((ws_bytes // 16,), dtype=torch.complex128, device=dev) if ws_bytes else None
         rc = L.jitr_b200_solve_batched(
             nb, nch, B, _cabi.ptr(free_matrix), free_stride, _cabi.ptr(loc), _cabi.ptr(nl), _cabi.ptr(interaction_matrix),
             _cabi.ptr(tabs["wsqrt"]), _cabi.ptr(sys_t), sys_stride, _cabi.ptr(bvec), _cabi.ptr(asym), asym_stride,
