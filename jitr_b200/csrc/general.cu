@@ -373,13 +373,36 @@ __global__ void __launch_bounds__(256, 1) warp_solve_kernel(const GenArgs A) {
 //      lu_warp.cuh), L21 and U12 from shared memory, the C tiles streamed slab -> accumulators -> slab.
 // Wavefunction coefficients (core.py:63-82) add a blocked back substitution on the stored U.
 // ---------------------------------------------------------------------------------------------
-constexpr int kBlkThreads = 256;
+#ifndef JITR_BLK_THREADS
+#define JITR_BLK_THREADS 256
+#endif
+#ifndef JITR_BLK_CTAS
+#define JITR_BLK_CTAS 2
+#endif
+
+constexpr int kBlkThreads = JITR_BLK_THREADS;
+constexpr int kBlkMaxRows = 256;  // one matrix row per thread of the first eight warps
 constexpr int kBlkLpLd = 9;
+
+// -DJITR_BLK_PROFILE: per-phase clock accumulators (thread 0 of every CTA), read by jitr_b200_debug_block_phases
+#ifdef JITR_BLK_PROFILE
+__device__ unsigned long long g_blk_phase[16];
+#define BLK_PH_INIT long long ph_t = clock64();
+#define BLK_PH(k)                                                                  \
+    if (threadIdx.x == 0) {                                                        \
+        const long long now = clock64();                                           \
+        atomicAdd(&g_blk_phase[k], (unsigned long long)(now - ph_t));              \
+        ph_t = now;                                                                \
+    }
+#else
+#define BLK_PH_INIT
+#define BLK_PH(k)
+#endif
 
 struct BlkGeom {
     int P, PR, PC;       // padded order, rows (P + z rows), columns (P + RHS columns); PR == PC
     int ub_ld;           // odd leading dimension of the U12 buffer
-    int off_l11, off_ub, off_prow, off_small, off_xs, off_int;  // shared-memory offsets in double2 units
+    int off_l11, off_ub, off_pn, off_prow, off_small, off_xs, off_int;  // shared-memory offsets in double2 units
 };
 
 __host__ __device__ inline BlkGeom blk_geom(int n, int nch) {
@@ -392,13 +415,14 @@ __host__ __device__ inline BlkGeom blk_geom(int n, int nch) {
     int o = (g.PR - 8) * kBlkLpLd;  // Lp
     g.off_l11 = o; o += 64;
     g.off_ub = o; o += 8 * g.ub_ld;
-    g.off_prow = o; o += 10;
+    g.off_pn = o; o += g.PR * kBlkLpLd;  // the next panel: rows by position, 8 columns
+    g.off_prow = o; o += 2 * 8 * 8;  // [parity][warp][8]: 1/pivot, columns j+1..7 of the warp's candidate row
     g.off_small = o; o += 4 * kMaxCh * kMaxCh;
     g.off_xs = o; o += 8 * kMaxCh;
-    g.off_int = o; o += 8;  // 32 ints
+    g.off_int = o; o += 24;  // 96 ints
     return g;
 }
-static inline size_t blk_smem_bytes(const BlkGeom& g) { return (size_t)(g.off_int + 8 + 8) * 16; }
+static inline size_t blk_smem_bytes(const BlkGeom& g) { return (size_t)(g.off_int + 24) * 16; }
 
 template <int NQ>
 __device__ __forceinline__ void blk_trailing_item(double2* __restrict__ M, const int ld, const int R0, const int tr,
@@ -435,7 +459,112 @@ __device__ __forceinline__ void blk_trailing_item(double2* __restrict__ M, const
     }
 }
 
-__global__ void __launch_bounds__(kBlkThreads, 2) block_solve_kernel(const GenArgs A, const BlkGeom G) {
+// A22 -= L21 U12: items (kBlkNQ tile columns, one tile row) strided over the warps
+#ifndef JITR_BLK_NQ
+#define JITR_BLK_NQ 3
+#endif
+constexpr int kBlkNQ = JITR_BLK_NQ;
+__device__ __forceinline__ void blk_trailing_simple(double2* __restrict__ M, const int ld, const int R0, const int ntr,
+                                                    const int ntc_all, const int tc_begin, const double* __restrict__ Lpd,
+                                                    const double* __restrict__ Ubd, const int ub_ld, const int warp,
+                                                    const int lane, const int nwarps) {
+    const int ntc = ntc_all - tc_begin;
+    const int ncb = (ntc + kBlkNQ - 1) / kBlkNQ;
+    for (int it = warp; it < ncb * ntr; it += nwarps) {
+        const int cb = it / ntr, tr = it - cb * ntr;
+        const int rem = ntc - kBlkNQ * cb;  // warp-uniform
+        const int tc0 = tc_begin + kBlkNQ * cb;
+        if (rem >= kBlkNQ) blk_trailing_item<kBlkNQ>(M, ld, R0, tr, tc0, Lpd, Ubd, ub_ld, lane);
+        else if (kBlkNQ > 3 && rem == 3) blk_trailing_item<3>(M, ld, R0, tr, tc0, Lpd, Ubd, ub_ld, lane);
+        else if (kBlkNQ > 2 && rem == 2) blk_trailing_item<2>(M, ld, R0, tr, tc0, Lpd, Ubd, ub_ld, lane);
+        else blk_trailing_item<1>(M, ld, R0, tr, tc0, Lpd, Ubd, ub_ld, lane);
+    }
+}
+
+// Wavefunction coefficients (core.py:63-82): X = U^-1 Y for the nch right-hand sides (columns P..P+nch-1 of the
+// slab, which holds U and Y = L^-1 P B after the elimination), eight rows at a time from the bottom; then
+// x = sum_i u'_ext,i X[:, i].  Out of line: keeps its registers out of the elimination loop.
+__device__ __noinline__ void blk_coefficients(const GenArgs& A, const long long sysi, double2* __restrict__ M, const int ld,
+                                              const int P, double2* __restrict__ xs, const double2* __restrict__ ue) {
+    const int n = A.n, nch = A.nch, tid = threadIdx.x;
+    const double2 zero2 = make_double2(0.0, 0.0);
+#pragma unroll 1
+    for (int kb = P - 8; kb >= 0; kb -= 8) {
+        if (tid < nch) {
+            double2 x[8];
+#pragma unroll
+            for (int r = 7; r >= 0; --r) {
+                double2 v = M[(size_t)(kb + r) * ld + P + tid];
+#pragma unroll
+                for (int c = r + 1; c < 8; ++c) cfnma(v, M[(size_t)(kb + r) * ld + kb + c], x[c]);
+                x[r] = cmul(v, crecip(M[(size_t)(kb + r) * ld + kb + r]));
+                xs[r * kMaxCh + tid] = x[r];
+                M[(size_t)(kb + r) * ld + P + tid] = x[r];
+            }
+        }
+        __syncthreads();
+        for (int t = tid; t < kb * nch; t += kBlkThreads) {
+            const int r = t / nch, j = t - r * nch;
+            double2 v = M[(size_t)r * ld + P + j];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) cfnma(v, M[(size_t)r * ld + kb + c], xs[c * kMaxCh + j]);
+            M[(size_t)r * ld + P + j] = v;
+        }
+        __syncthreads();
+    }
+    // x = A^-1 vec_i(b u'_ext,i) = sum_i u'_ext,i X[:, i]    (core.py:81-82)
+    for (int r = tid; r < n; r += kBlkThreads) {
+        double2 acc = zero2;
+        for (int i = 0; i < nch; ++i) {
+            const double2 t = cmul(ue[i], M[(size_t)r * ld + P + i]);
+            acc.x += t.x; acc.y += t.y;
+        }
+        A.coeffs[(size_t)sysi * n + r] = acc;
+    }
+}
+
+// Tile column 0 of the trailing update = the columns of the NEXT panel: computed first, by all warps, and left
+// in shared memory (Pn, rows by position) so that the panel warps can start on it while the other warps
+// finish the rest of the trailing update (look-ahead).
+__device__ __forceinline__ void blk_trailing_col0(const double2* __restrict__ M, const int ld, const int R0,
+                                                  const int ntr, const double* __restrict__ Lpd,
+                                                  const double* __restrict__ Ubd, const int ub_ld,
+                                                  double2* __restrict__ Pn, const int warp, const int lane,
+                                                  const int nwarps) {
+    const int fr = lane >> 2, fk = lane & 3;
+    const int rho = (fr >> 1) + 4 * (fr & 1);
+    const int part = fk & 1, pn = fr & 1;
+    const int bflip = (part & (pn ^ 1)) ? 0x80000000 : 0;
+    const int a_off = 2 * (rho * kBlkLpLd + 4 * (fk >> 1)) + part;
+    const int b_off = 2 * ((4 * (fk >> 1)) * ub_ld + (fr >> 1)) + (part ^ pn);
+    if (warp >= ntr) return;
+    double b[2][4];
+#pragma unroll
+    for (int s = 0; s < 4; ++s)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const double v = Ubd[b_off + 2 * (s * ub_ld + 4 * h)];
+            b[h][s] = __hiloint2double(__double2hiint(v) ^ bflip, __double2loint(v));
+        }
+#pragma unroll 1
+    for (int tr = warp; tr < ntr; tr += nwarps) {
+        const double2* Crow = M + (size_t)(R0 + 8 * tr + rho) * ld + R0 + fk;
+        double2 c0 = Crow[0], c1 = Crow[4];
+        double a[4];
+#pragma unroll
+        for (int s = 0; s < 4; ++s) a[s] = dneg(Lpd[a_off + 2 * (8 * tr * kBlkLpLd + s)]);
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            dmma884(c0.x, c0.y, a[s], b[0][s]);
+            dmma884(c1.x, c1.y, a[s], b[1][s]);
+        }
+        double2* dst = Pn + (8 * tr + rho) * kBlkLpLd + fk;
+        dst[0] = c0;
+        dst[4] = c1;
+    }
+}
+
+__global__ void __launch_bounds__(kBlkThreads, JITR_BLK_CTAS) block_solve_kernel(const GenArgs A, const BlkGeom G) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n = A.n, N = A.N, nch = A.nch;
     const int P = G.P, PR = G.PR, PC = G.PC, ld = G.PC;
@@ -446,19 +575,21 @@ __global__ void __launch_bounds__(kBlkThreads, 2) block_solve_kernel(const GenAr
     double2* Lp = sm;                    // [(PR - 8)][9]  multipliers of the rows below the panel, by position
     double2* L11 = sm + G.off_l11;       // [8][8]         multipliers inside the pivot rows
     double2* Ub = sm + G.off_ub;         // [8][ub_ld]     U12 (trailing columns incl. RHS)
-    double2* prow = sm + G.off_prow;     // pivot row (columns j+1..7), [8] = 1/pivot
+    double2* Pn = sm + G.off_pn;         // [PR][9]        columns of the next panel, rows by position
+    double2* slot = sm + G.off_prow;     // [2][NW][8] candidate rows: [0] = 1/pivot, [c] = column c (c > j)
     double2* small = sm + G.off_small;
     double2* xs = sm + G.off_xs;         // [8][kMaxCh] back-substitution block
     int* si = reinterpret_cast<int*>(sm + G.off_int);
-    int* wkey = si;                      // [8]
-    int* wtid = si + 8;                  // [8]
-    int* src = si + 16;                  // [8] old position of pivot row j
-    int* dfrom = si + 24;                // [8]
-    int* dto = si + 32;                  // [8]
-    int* misc = si + 40;                 // [0] pivot's old position, [1] displaced count, [2] flags
+    int* skey = si;                      // [2][8] pivot key of each warp's candidate (-2: warp holds no rows)
+    int* spos = si + 32;                 // [2][8] its current position
+    int* src = si + 48;                  // [8] old position of pivot row j
+    int* dfrom = si + 56;                // [8]
+    int* dto = si + 64;                  // [8]
+    int* misc = si + 72;                 // [1] displaced count, [2] flags
     double2* M = A.workspace + (size_t)blockIdx.x * PR * ld;
     const double2 zero2 = make_double2(0.0, 0.0);
 
+    BLK_PH_INIT
     for (long long sysi = blockIdx.x; sysi < A.batch; sysi += gridDim.x) {
         const double* sy = A.sys + (size_t)sysi * A.sys_stride;
         const double a = sy[0], E0 = sy[1], k0s = sy[2];
@@ -467,41 +598,61 @@ __global__ void __launch_bounds__(kBlkThreads, 2) block_solve_kernel(const GenAr
         // ---------------- assemble the bordered matrix into the slab
         for (int r = warp; r < PR; r += NW) {
             const int ci = r / N, nn = r - ci * N;
-            for (int c = lane; c < PC; c += 32) {
-                double2 v = zero2;
-                if (r < n) {
-                    if (c < n) {
-                        v = F[(size_t)r * n + c];
+            double2* __restrict__ Mr = M + (size_t)r * ld;
+            if (r < n) {
+                const double2* __restrict__ Fr = F + (size_t)r * n;
+                const double2* __restrict__ Ir = A.interaction ? A.interaction + ((size_t)sysi * n + r) * n : nullptr;
+                for (int c = lane; c < n; c += 32) {
+                    double2 v = Fr[c];
+                    if (Ir) {
+                        const double2 w = Ir[c];
+                        v.x += w.x; v.y += w.y;
+                    } else if (A.nonlocal_) {
                         const int cj = c / N, mm = c - cj * N;
-                        if (A.interaction) {
-                            const double2 w = A.interaction[(size_t)sysi * n * n + (size_t)r * n + c];
-                            v.x += w.x; v.y += w.y;
-                        } else {
-                            if (A.local && nn == mm) {
-                                const double2 w = A.local[(((size_t)sysi * nch + ci) * nch + cj) * N + nn];
-                                v.x += w.x / E0; v.y += w.y / E0;
-                            }
-                            if (A.nonlocal_) {
-                                const double2 w = A.nonlocal_[((((size_t)sysi * nch + ci) * nch + cj) * N + nn) * N + mm];
-                                const double s = A.wsqrt[nn] * A.wsqrt[mm] * nl_scale;
-                                v.x += w.x * s; v.y += w.y * s;
-                            }
-                        }
-                    } else if (c >= P && c - P == ci) {
-                        v.x = A.bvec[nn];
+                        const double2 w = A.nonlocal_[((((size_t)sysi * nch + ci) * nch + cj) * N + nn) * N + mm];
+                        const double sc = A.wsqrt[nn] * A.wsqrt[mm] * nl_scale;
+                        v.x += w.x * sc; v.y += w.y * sc;
                     }
-                } else if (r < P) {
-                    if (c == r) v.x = 1.0;
-                } else if (c < n) {
-                    const int cj = c / N;
-                    if (cj == r - P) v.x = A.bvec[c - cj * N];
+                    Mr[c] = v;
+                    if (c < 8) Pn[r * kBlkLpLd + c] = v;
                 }
-                M[(size_t)r * ld + c] = v;
+                for (int c = n + lane; c < PC; c += 32) {
+                    const double2 v = make_double2((c >= P && c - P == ci) ? A.bvec[nn] : 0.0, 0.0);
+                    Mr[c] = v;
+                    if (c < 8) Pn[r * kBlkLpLd + c] = v;  // only when n < 8
+                }
+            } else if (r < P) {
+                for (int c = lane; c < PC; c += 32) Mr[c] = make_double2(c == r ? 1.0 : 0.0, 0.0);
+                if (lane < 8) Pn[r * kBlkLpLd + lane] = make_double2(lane == r ? 1.0 : 0.0, 0.0);
+            } else {
+                const int zi = r - P;  // z row of channel zi: b in the columns of that channel
+                for (int c = lane; c < PC; c += 32) {
+                    const int c0 = c - zi * N;
+                    const double2 v = make_double2((zi < nch && c0 >= 0 && c0 < N) ? A.bvec[c0] : 0.0, 0.0);
+                    Mr[c] = v;
+                    if (c < 8) Pn[r * kBlkLpLd + c] = v;
+                }
             }
         }
         if (tid == 0) misc[2] = 0;
+        if (!A.interaction && A.local) {
+            // local (coupling) potentials sit on the diagonals of the channel blocks
+            __syncthreads();
+            for (int t = tid; t < nch * nch * N; t += kBlkThreads) {
+                const int cij = t / N, nn = t - cij * N;
+                const int ci = cij / nch, cj = cij - ci * nch;
+                const double2 w = A.local[((size_t)sysi * nch * nch + cij) * N + nn];
+                double2* e = M + (size_t)(ci * N + nn) * ld + cj * N + nn;
+                double2 v = *e;
+                v.x += w.x / E0; v.y += w.y / E0;
+                *e = v;
+                if (cj * N + nn < 8) Pn[(ci * N + nn) * kBlkLpLd + cj * N + nn] = v;
+            }
+        }
         __syncthreads();
-        // ---------------- blocked elimination
+        BLK_PH(0)
+        // ---------------- blocked elimination with look-ahead: while the warps that hold the rows of panel k0
+        // factorise it, the other warps finish the trailing update of panel k0 - 8
 #pragma unroll 1
         for (int k0 = 0; k0 < P; k0 += 8) {
             const int m = PR - k0;
@@ -511,83 +662,110 @@ __global__ void __launch_bounds__(kBlkThreads, 2) block_solve_kernel(const GenAr
             const bool cand = have && start < P;
             bool done = false;
             double2 p[8];
-            {
-                const double2* rowp = M + (size_t)(have ? start : k0) * ld + k0;
+            const int nw = (m + 31) >> 5;  // warps that hold rows (<= 8)
+            if (warp < nw) {
+                {
+                    const double2* rowp = Pn + (have ? tid : 0) * kBlkLpLd;
 #pragma unroll
-                for (int c = 0; c < 8; ++c) p[c] = rowp[c];
-            }
-            if (tid == 0) misc[1] = 0;
-            const int nw = (m + 31) >> 5;  // warps that hold rows
+                    for (int c = 0; c < 8; ++c) p[c] = rowp[c];
+                }
+                if (tid == 0) misc[1] = 0;
+                if (warp == 0 && lane >= nw && lane < 8) skey[lane] = skey[8 + lane] = -2;
+                // pivot key (high word of |re| + |im|, LAPACK izamax) and speculative reciprocal of column 0
+                int key = cand ? __double2hiint(fabs(p[0].x) + fabs(p[0].y)) : -1;
+                double2 rinv = crecip_fast(p[0]);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                if (warp < nw) {
-                    const int key = (cand && !done) ? __double2hiint(fabs(p[j].x) + fabs(p[j].y)) : -1;
+                for (int j = 0; j < 8; ++j) {
+                    const int buf = (j & 1) * 8;
+                    BLK_PH(8)
+                    // every warp publishes its best candidate row; one barrier (of the panel warps) per column
                     const int wmax = __reduce_max_sync(kFull, key);
                     const unsigned bal = __ballot_sync(kFull, key == wmax);
-                    if (lane == 0) {
-                        wkey[warp] = wmax;
-                        wtid[warp] = (warp << 5) + __ffs(bal) - 1;
+                    const bool mine = lane == __ffs(bal) - 1;
+                    if (mine) {
+                        skey[buf + warp] = (wmax & ~7) | (7 - warp);  // ties go to the lower warp
+                        spos[buf + warp] = pos;
+                        double2* sl = slot + (buf + warp) * 8;
+                        sl[0] = rinv;
+#pragma unroll
+                        for (int c = j + 1; c < 8; ++c) sl[c] = p[c];
                     }
-                }
-                __syncthreads();
-                int bk = -2, bt = 0;
-                for (int w = 0; w < nw; ++w) {
-                    const int kk = wkey[w];
-                    if (kk > bk) { bk = kk; bt = wtid[w]; }
-                }
-                if (tid == bt) {
-                    if (bk < 0x00100000) atomicOr(&misc[2], 2);  // zero (or subnormal) pivot
-                    prow[8] = crecip_fast(p[j]);
+                    BLK_PH(9)
+                    asm volatile("bar.sync 1, %0;" ::"r"(nw * 32) : "memory");
+                    BLK_PH(10)
+                    const int best = __reduce_max_sync(kFull, skey[buf + (lane & 7)]);
+                    const int bw = 7 - (best & 7);
+                    const double2* pr = slot + (buf + bw) * 8;
+                    BLK_PH(11)
+                    int nkey = -1;
+                    double2 nrinv = rinv;
+                    if (mine && warp == bw) {
+                        if ((best & ~7) < 0x00100000) atomicOr(&misc[2], 2);  // zero (or subnormal) pivot
+                        pos = k0 + j;
+                        done = true;
+                    } else if (have && !done) {
+                        if (pos == k0 + j) pos = spos[buf + bw];
+                        const double2 l = cmul(p[j], pr[0]);
+                        p[j] = l;
+                        if (j < 7) {
+                            // the next column first: its search starts while the other columns are updated
+                            cfnma(p[j + 1], l, pr[j + 1]);
+                            nkey = cand ? __double2hiint(fabs(p[j + 1].x) + fabs(p[j + 1].y)) : -1;
+                            nrinv = crecip_fast(p[j + 1]);
+                        }
 #pragma unroll
-                    for (int c = j + 1; c < 8; ++c) prow[c] = p[c];
-                    misc[0] = pos;
+                        for (int c = j + 2; c < 8; ++c) cfnma(p[c], l, pr[c]);
+                    }
+                    key = nkey;
+                    rinv = nrinv;
                 }
-                __syncthreads();
-                if (tid == bt) {
-                    pos = k0 + j;
-                    done = true;
-                } else if (have && !done) {
-                    if (pos == k0 + j) pos = misc[0];
-                    const double2 l = cmul(p[j], prow[8]);
-                    p[j] = l;
-#pragma unroll
-                    for (int c = j + 1; c < 8; ++c) cfnma(p[c], l, prow[c]);
+                if (have) {
+                    if (done) {
+                        const int r = pos - k0;
+                        src[r] = start;
+    #pragma unroll
+                        for (int c = 0; c < 8; ++c) L11[r * 8 + c] = p[c];
+                        if (A.coeffs) {
+                            double2* rowp = M + (size_t)pos * ld + k0;
+    #pragma unroll
+                            for (int c = 0; c < 8; ++c) rowp[c] = p[c];  // U11 on and right of the diagonal
+                        }
+                    } else {
+                        double2* lp = Lp + (pos - k0 - 8) * kBlkLpLd;
+    #pragma unroll
+                        for (int c = 0; c < 8; ++c) lp[c] = p[c];
+                        if (start < k0 + 8) {
+                            const int i = atomicAdd(&misc[1], 1);
+                            dfrom[i] = start;
+                            dto[i] = pos;
+                        }
+                    }
                 }
             }
-            if (have) {
-                if (done) {
-                    const int r = pos - k0;
-                    src[r] = start;
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) L11[r * 8 + c] = p[c];
-                    if (A.coeffs) {
-                        double2* rowp = M + (size_t)pos * ld + k0;
-#pragma unroll
-                        for (int c = 0; c < 8; ++c) rowp[c] = p[c];  // U11 on and right of the diagonal
-                    }
-                } else {
-                    double2* lp = Lp + (pos - k0 - 8) * kBlkLpLd;
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) lp[c] = p[c];
-                    if (start < k0 + 8) {
-                        const int i = atomicAdd(&misc[1], 1);
-                        dfrom[i] = start;
-                        dto[i] = pos;
-                    }
-                }
-            }
+            BLK_PH(1)
             __syncthreads();
+            BLK_PH(2)
             // ------------ phase U (+ the row moves of the trailing columns)
             const int wtr = PC - k0 - 8;
             if (tid < wtr) {
                 const int col = k0 + 8 + tid;
-                double2 av[8], dv[8];
+                double2 av[8];
                 const int nd = misc[1];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) av[j] = M[(size_t)src[j] * ld + col];
+                // displaced rows (they started inside the panel) go where the pivots came from
 #pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    if (i < nd) dv[i] = M[(size_t)dfrom[i] * ld + col];
+                for (int i0 = 0; i0 < 8; i0 += 4) {
+                    if (i0 < nd) {  // CTA-uniform
+                        double2 dv[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            if (i0 + i < nd) dv[i] = M[(size_t)dfrom[i0 + i] * ld + col];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            if (i0 + i < nd) M[(size_t)dto[i0 + i] * ld + col] = dv[i];
+                    }
+                }
 #pragma unroll
                 for (int kk = 1; kk < 8; ++kk)
 #pragma unroll
@@ -598,26 +776,21 @@ __global__ void __launch_bounds__(kBlkThreads, 2) block_solve_kernel(const GenAr
 #pragma unroll
                     for (int j = 0; j < 8; ++j) M[(size_t)(k0 + j) * ld + col] = av[j];
                 }
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    if (i < nd) M[(size_t)dto[i] * ld + col] = dv[i];
             }
             __syncthreads();
-            // ------------ phase T
-            {
-                const int ntr = (PR - k0 - 8) >> 3, ntc = wtr >> 3;
-                const int ncb = (ntc + 2) / 3;
-                const double* Lpd = reinterpret_cast<const double*>(Lp);
-                const double* Ubd = reinterpret_cast<const double*>(Ub);
-                for (int it = warp; it < ncb * ntr; it += NW) {
-                    const int cb = it / ntr, tr = it - cb * ntr;
-                    const int rem = ntc - 3 * cb;  // warp-uniform
-                    if (rem >= 3) blk_trailing_item<3>(M, ld, k0 + 8, tr, 3 * cb, Lpd, Ubd, G.ub_ld, lane);
-                    else if (rem == 2) blk_trailing_item<2>(M, ld, k0 + 8, tr, 3 * cb, Lpd, Ubd, G.ub_ld, lane);
-                    else blk_trailing_item<1>(M, ld, k0 + 8, tr, 3 * cb, Lpd, Ubd, G.ub_ld, lane);
-                }
-            }
+            BLK_PH(3)
+            // ------------ phase T: the next panel's columns now (-> Pn), the rest beside the next panel phase
+            if (k0 + 8 < P) {
+                blk_trailing_col0(M, ld, k0 + 8, (PR - k0 - 8) >> 3, reinterpret_cast<const double*>(Lp),
+                                  reinterpret_cast<const double*>(Ub), G.ub_ld, Pn, warp, lane, NW);
+                blk_trailing_simple(M, ld, k0 + 8, (PR - k0 - 8) >> 3, wtr >> 3, 1, reinterpret_cast<const double*>(Lp),
+                                    reinterpret_cast<const double*>(Ub), G.ub_ld, warp, lane, NW);
+            } else
+                blk_trailing_simple(M, ld, k0 + 8, (PR - k0 - 8) >> 3, wtr >> 3, 0, reinterpret_cast<const double*>(Lp),
+                             reinterpret_cast<const double*>(Ub), G.ub_ld, warp, lane, NW);
+            BLK_PH(4)
             __syncthreads();
+            BLK_PH(5)
         }
         // ---------------- R = -corner / a^2
         for (int ij = tid; ij < nch * nch; ij += kBlkThreads) {
@@ -627,48 +800,13 @@ __global__ void __launch_bounds__(kBlkThreads, 2) block_solve_kernel(const GenAr
         }
         __syncthreads();
         finish_system(A, sysi, a, misc[2], small, tid, kBlkThreads);
-        if (A.coeffs) {
-            // X = U^-1 Y for the nch right-hand sides (columns P..P+nch-1), eight rows at a time from the bottom
-            const double2* ue = small + 3 * kMaxCh * kMaxCh;
-#pragma unroll 1
-            for (int kb = P - 8; kb >= 0; kb -= 8) {
-                if (tid < nch) {
-                    double2 x[8];
-#pragma unroll
-                    for (int r = 7; r >= 0; --r) {
-                        double2 v = M[(size_t)(kb + r) * ld + P + tid];
-#pragma unroll
-                        for (int c = r + 1; c < 8; ++c) cfnma(v, M[(size_t)(kb + r) * ld + kb + c], x[c]);
-                        x[r] = cmul(v, crecip(M[(size_t)(kb + r) * ld + kb + r]));
-                        xs[r * kMaxCh + tid] = x[r];
-                        M[(size_t)(kb + r) * ld + P + tid] = x[r];
-                    }
-                }
-                __syncthreads();
-                for (int t = tid; t < kb * nch; t += kBlkThreads) {
-                    const int r = t / nch, j = t - r * nch;
-                    double2 v = M[(size_t)r * ld + P + j];
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) cfnma(v, M[(size_t)r * ld + kb + c], xs[c * kMaxCh + j]);
-                    M[(size_t)r * ld + P + j] = v;
-                }
-                __syncthreads();
-            }
-            // x = A^-1 vec_i(b u'_ext,i) = sum_i u'_ext,i X[:, i]    (core.py:81-82)
-            for (int r = tid; r < n; r += kBlkThreads) {
-                double2 acc = zero2;
-                for (int i = 0; i < nch; ++i) {
-                    const double2 t = cmul(ue[i], M[(size_t)r * ld + P + i]);
-                    acc.x += t.x; acc.y += t.y;
-                }
-                A.coeffs[(size_t)sysi * n + r] = acc;
-            }
-        }
+        if (A.coeffs) blk_coefficients(A, sysi, M, ld, P, xs, small + 3 * kMaxCh * kMaxCh);
         __syncthreads();
+        BLK_PH(6)
     }
 }
 
-static int blk_ctas_per_sm() { return 2; }
+static int blk_ctas_per_sm() { return JITR_BLK_CTAS; }
 
 static int launch_block_solve(const GenArgs& a, cudaStream_t st) {
     const BlkGeom g = blk_geom(a.n, a.nch);
@@ -679,7 +817,11 @@ static int launch_block_solve(const GenArgs& a, cudaStream_t st) {
             return set_cuda_error("cudaFuncSetAttribute(block_solve)");
         conf = smem;
     }
-    long long blocks = (long long)sm_count() * blk_ctas_per_sm();
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, block_solve_kernel, kBlkThreads, smem) != cudaSuccess || per_sm < 1)
+        return set_cuda_error("block_solve occupancy");
+    if (per_sm > blk_ctas_per_sm()) per_sm = blk_ctas_per_sm();  // the workspace holds that many slabs per SM
+    long long blocks = (long long)sm_count() * per_sm;
     if (blocks > a.batch) blocks = a.batch;
     block_solve_kernel<<<(unsigned)blocks, kBlkThreads, smem, st>>>(a, g);
     count_launch();
@@ -712,12 +854,23 @@ static int launch_warp_solve(const GenArgs& a, cudaStream_t st) {
 
 using namespace jitr;
 
+#ifdef JITR_BLK_PROFILE
+extern "C" int jitr_b200_debug_block_phases(unsigned long long* out16, int reset) {
+    if (out16 && cudaMemcpyFromSymbol(out16, g_blk_phase, sizeof(unsigned long long) * 16) != cudaSuccess) return -1;
+    if (reset) {
+        unsigned long long z[16] = {0};
+        if (cudaMemcpyToSymbol(g_blk_phase, z, sizeof(z)) != cudaSuccess) return -1;
+    }
+    return 0;
+}
+#endif
+
 extern "C" long long jitr_b200_solve_workspace_bytes(int nbasis, int nch, long long batch, int coeffs) {
     if (nbasis < 1 || nch < 1 || nch > kMaxCh || batch < 0) return -1;
     if (nch == 1 && !coeffs && ((nbasis + 7) & ~7) <= 64) return 0;  // warp-per-system: shared memory only
     const long long n = (long long)nbasis * nch;
     const BlkGeom g = blk_geom((int)n, nch);
-    if (g.PR <= kBlkThreads) {  // one slab per resident CTA
+    if (g.PR <= kBlkMaxRows) {  // one slab per resident CTA
         int sms = sm_count();
         if (sms <= 0) sms = 148;
         long long ctas = (long long)sms * blk_ctas_per_sm();
@@ -756,7 +909,7 @@ extern "C" int jitr_b200_solve_batched(int nbasis, int nch, long long batch, con
         if (((nbasis + 7) & ~7) + 1 <= 64) return launch_warp_solve<2>(a, st);
         return launch_warp_solve<3>(a, st);
     }
-    if (blk_geom(a.n, nch).PR <= kBlkThreads) {
+    if (blk_geom(a.n, nch).PR <= kBlkMaxRows) {
         if (!workspace) return set_error(JITR_B200_ERR_BAD_ARG, "solve_batched: workspace of jitr_b200_solve_workspace_bytes() bytes required");
         return launch_block_solve(a, st);
     }

@@ -63,6 +63,24 @@ def main():
     n = N * nch
     flops = 8 * n**3 / 3 + 8 * n**2 * nch
     out["config5_coupled_3x50"] = {"batch": B, "ms": ms, "solves_per_s": B / ms * 1e3, "tflops": B * flops / ms / 1e9}
+    ms = timeit(lambda: solver.solve_batch(a, 4.9, 0.48, nch, free, asym3, local_potential=Vt, wavefunction=True))
+    out["config5_coupled_3x50_wavefunction"] = {"batch": B, "ms": ms, "solves_per_s": B / ms * 1e3}
+    # optional per-phase clocks of the CTA-per-system kernel (library built with -DJITR_BLK_PROFILE)
+    import ctypes
+
+    from jitr_b200 import _cabi
+
+    L = _cabi.lib()
+    if hasattr(L, "jitr_b200_debug_block_phases"):
+        buf = (ctypes.c_ulonglong * 16)()
+        L.jitr_b200_debug_block_phases(buf, 1)
+        solver.solve_batch(a, 4.9, 0.48, nch, free, asym3, local_potential=Vt)
+        torch.cuda.synchronize()
+        L.jitr_b200_debug_block_phases(buf, 0)
+        tot = float(sum(buf)) or 1.0
+        names = ["assemble", "panel", "panel_store", "upper", "trailing", "trailing_barrier", "finish", "-",
+                 "col_update", "col_search_publish", "col_barrier", "col_select", "-", "-", "-", "-"]
+        out["config5_phase_share"] = {k: round(v / tot, 4) for k, v in zip(names, buf)}
     print(json.dumps(out))
 
 
