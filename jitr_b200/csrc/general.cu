@@ -602,19 +602,43 @@ __global__ void __launch_bounds__(kBlkThreads, JITR_BLK_CTAS) block_solve_kernel
             if (r < n) {
                 const double2* __restrict__ Fr = F + (size_t)r * n;
                 const double2* __restrict__ Ir = A.interaction ? A.interaction + ((size_t)sysi * n + r) * n : nullptr;
-                for (int c = lane; c < n; c += 32) {
-                    double2 v = Fr[c];
-                    if (Ir) {
-                        const double2 w = Ir[c];
-                        v.x += w.x; v.y += w.y;
-                    } else if (A.nonlocal_) {
-                        const int cj = c / N, mm = c - cj * N;
-                        const double2 w = A.nonlocal_[((((size_t)sysi * nch + ci) * nch + cj) * N + nn) * N + mm];
-                        const double sc = A.wsqrt[nn] * A.wsqrt[mm] * nl_scale;
-                        v.x += w.x * sc; v.y += w.y * sc;
+                // four independent 16-byte loads in flight per lane (the free matrix comes from L2)
+                for (int c0 = 0; c0 < n; c0 += 128) {
+                    double2 v[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int c = c0 + 32 * i + lane;
+                        v[i] = c < n ? Fr[c] : zero2;
                     }
-                    Mr[c] = v;
-                    if (c < 8) Pn[r * kBlkLpLd + c] = v;
+                    if (Ir) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int c = c0 + 32 * i + lane;
+                            if (c < n) {
+                                const double2 w = Ir[c];
+                                v[i].x += w.x; v[i].y += w.y;
+                            }
+                        }
+                    } else if (A.nonlocal_) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int c = c0 + 32 * i + lane;
+                            if (c < n) {
+                                const int cj = c / N, mm = c - cj * N;
+                                const double2 w = A.nonlocal_[((((size_t)sysi * nch + ci) * nch + cj) * N + nn) * N + mm];
+                                const double sc = A.wsqrt[nn] * A.wsqrt[mm] * nl_scale;
+                                v[i].x += w.x * sc; v[i].y += w.y * sc;
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int c = c0 + 32 * i + lane;
+                        if (c < n) {
+                            Mr[c] = v[i];
+                            if (c < 8) Pn[r * kBlkLpLd + c] = v[i];
+                        }
+                    }
                 }
                 for (int c = n + lane; c < PC; c += 32) {
                     const double2 v = make_double2((c >= P && c - P == ci) ? A.bvec[nn] : 0.0, 0.0);
