@@ -1,9 +1,12 @@
 // General batched R-matrix solve: any number of channels, local and/or nonlocal interaction,
-// optional wavefunction coefficients.  One CTA per system; the augmented matrix [A | B] lives in
-// shared memory when it fits (n <= ~115) and in the caller's device workspace otherwise.
-// Replaces Solver.solve (rmatrix/rmatrix.py:180-246) + rmatrix/core.py:7-82 for one system per
-// call in the reference.  The fused warp-per-system kernel in elastic.cu is the fast path for the
-// single-channel elastic sweep; this kernel is the fully general one.
+// optional wavefunction coefficients.  Replaces Solver.solve (rmatrix/rmatrix.py:180-246) +
+// rmatrix/core.py:7-82 for one system per call in the reference.  Three kernels, chosen by size:
+//   warp_solve_kernel     single channel, no coefficients, nbasis <= 48: one warp per system (lu_warp.cuh)
+//   block_solve_kernel    up to 256 bordered rows (config 4: N = 60 nonlocal; config 5: 3 x 50 coupled;
+//                         elastic workspaces with nbasis > 64): one CTA per system, blocked DMMA LU on an
+//                         L2-resident slab
+//   general_solve_kernel  anything larger: unblocked elimination, one CTA per system
+// The fused warp-per-system kernel in elastic.cu is the fast path of the single-channel elastic sweep.
 #include <cuda_runtime.h>
 #include <math.h>
 
@@ -40,14 +43,14 @@ constexpr int kGenThreads = 256;
 constexpr int kMaxCh = 16;
 
 // R (in small[0 .. nch^2)) -> Z+-, S = Z+^-1 Z-, u'_ext; writes R, S, uext, status of system sysi.  Called by the
-// whole CTA after a barrier that made R visible; ends with a barrier (ue = small + 3 kMaxCh^2 is then readable).
+// whole CTA after a barrier that made R visible; ends with a barrier (ue = small + 3 nch^2 is then readable).
 __device__ __forceinline__ void finish_system(const GenArgs& A, const long long sysi, const double a, const int bad_flags,
                                               double2* small, const int tid, const int nt) {
     const int nch = A.nch;
     double2* Rm = small;                          // [nch][nch]
-    double2* Zp = small + kMaxCh * kMaxCh;        // [nch][nch]
-    double2* Zm = small + 2 * kMaxCh * kMaxCh;    // [nch][nch] -> S
-    double2* ue = small + 3 * kMaxCh * kMaxCh;    // [nch]
+    double2* Zp = small + nch * nch;              // [nch][nch]
+    double2* Zm = small + 2 * nch * nch;          // [nch][nch] -> S
+    double2* ue = small + 3 * nch * nch;          // [nch]
     const double2* as = A.asym + (size_t)sysi * A.asym_stride;  // [4][nch]: Hp, Hm, Hpp, Hmp
     for (int ij = tid; ij < nch * nch; ij += nt) {
         const int i = ij / nch, j = ij - i * nch;
@@ -251,7 +254,7 @@ __global__ void __launch_bounds__(kGenThreads) general_solve_kernel(const GenArg
         }
         __syncthreads();
         finish_system(A, sysi, a, redi[33], small, tid, nt);
-        const double2* ue = small + 3 * kMaxCh * kMaxCh;
+        const double2* ue = small + 3 * nch * nch;
         if (A.coeffs) {
             // x = A^-1 vec_i(b u'_ext,i) = sum_i u'_ext,i X[:, i]    (core.py:81-82)
             for (int r = tid; r < n; r += nt) {
@@ -268,11 +271,10 @@ __global__ void __launch_bounds__(kGenThreads) general_solve_kernel(const GenArg
 }
 
 // ---------------------------------------------------------------------------------------------
-// Single-channel systems (nch = 1, no coefficients) up to P = 8 ceil(N/8) <= 64: one WARP per system, the
+// Single-channel systems (nch = 1, no coefficients) up to P = 8 ceil(N/8) <= JITR_WARP_SOLVE_MAXP: one WARP per system, the
 // bordered matrix [[F + V, b], [b^T, 0]] assembled in the warp's shared-memory region straight from the
 // global arrays (the nonlocal kernel is the HBM stream of this path: N^2 x 16 B per system) and eliminated
-// by the blocked partial-pivoting LU of lu_warp.cuh (register panel + DMMA trailing update).  This is
-// BASELINE config 4 (nonlocal Perey-Buck, N = 60): 7x the CTA-per-system kernel above.
+// by the blocked partial-pivoting LU of lu_warp.cuh (register panel + DMMA trailing update).
 // ---------------------------------------------------------------------------------------------
 template <int MAXNS>
 __global__ void __launch_bounds__(256, 1) warp_solve_kernel(const GenArgs A) {
@@ -373,14 +375,14 @@ __global__ void __launch_bounds__(256, 1) warp_solve_kernel(const GenArgs A) {
 //      lu_warp.cuh), L21 and U12 from shared memory, the C tiles streamed slab -> accumulators -> slab.
 // Wavefunction coefficients (core.py:63-82) add a blocked back substitution on the stored U.
 // ---------------------------------------------------------------------------------------------
-#ifndef JITR_BLK_THREADS
-#define JITR_BLK_THREADS 256
+// single-channel systems without coefficients up to this padded order go warp-per-system; beyond it the blocked
+// CTA-per-system kernel is faster (measured crossover between nbasis 48 and 56, tools/bench_general_sizes.py)
+#ifndef JITR_WARP_SOLVE_MAXP
+#define JITR_WARP_SOLVE_MAXP 48
 #endif
-#ifndef JITR_BLK_CTAS
-#define JITR_BLK_CTAS 2
-#endif
+// CTA sizes of the blocked kernel: one matrix row per thread in the panel phase, so systems with at most 128
+// bordered rows run on 128 threads (four CTAs per SM), larger ones on 256 (two per SM)
 
-constexpr int kBlkThreads = JITR_BLK_THREADS;
 constexpr int kBlkMaxRows = 256;  // one matrix row per thread of the first eight warps
 constexpr int kBlkLpLd = 9;
 
@@ -417,7 +419,7 @@ __host__ __device__ inline BlkGeom blk_geom(int n, int nch) {
     g.off_ub = o; o += 8 * g.ub_ld;
     g.off_pn = o; o += g.PR * kBlkLpLd;  // the next panel: rows by position, 8 columns
     g.off_prow = o; o += 2 * 8 * 8;  // [parity][warp][8]: 1/pivot, columns j+1..7 of the warp's candidate row
-    g.off_small = o; o += 4 * kMaxCh * kMaxCh;
+    g.off_small = o; o += 3 * nch * nch + nch + 1;  // R, Z+, Z- -> S, u'_ext
     g.off_xs = o; o += 8 * kMaxCh;
     g.off_int = o; o += 24;  // 96 ints
     return g;
@@ -503,7 +505,7 @@ __device__ __noinline__ void blk_coefficients(const GenArgs& A, const long long 
             }
         }
         __syncthreads();
-        for (int t = tid; t < kb * nch; t += kBlkThreads) {
+        for (int t = tid; t < kb * nch; t += blockDim.x) {
             const int r = t / nch, j = t - r * nch;
             double2 v = M[(size_t)r * ld + P + j];
 #pragma unroll
@@ -513,7 +515,7 @@ __device__ __noinline__ void blk_coefficients(const GenArgs& A, const long long 
         __syncthreads();
     }
     // x = A^-1 vec_i(b u'_ext,i) = sum_i u'_ext,i X[:, i]    (core.py:81-82)
-    for (int r = tid; r < n; r += kBlkThreads) {
+    for (int r = tid; r < n; r += blockDim.x) {
         double2 acc = zero2;
         for (int i = 0; i < nch; ++i) {
             const double2 t = cmul(ue[i], M[(size_t)r * ld + P + i]);
@@ -564,7 +566,8 @@ __device__ __forceinline__ void blk_trailing_col0(const double2* __restrict__ M,
     }
 }
 
-__global__ void __launch_bounds__(kBlkThreads, JITR_BLK_CTAS) block_solve_kernel(const GenArgs A, const BlkGeom G) {
+template <int kBlkThreads>
+__global__ void __launch_bounds__(kBlkThreads, 512 / kBlkThreads) block_solve_kernel(const GenArgs A, const BlkGeom G) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n = A.n, N = A.N, nch = A.nch;
     const int P = G.P, PR = G.PR, PC = G.PC, ld = G.PC;
@@ -824,33 +827,39 @@ __global__ void __launch_bounds__(kBlkThreads, JITR_BLK_CTAS) block_solve_kernel
         }
         __syncthreads();
         finish_system(A, sysi, a, misc[2], small, tid, kBlkThreads);
-        if (A.coeffs) blk_coefficients(A, sysi, M, ld, P, xs, small + 3 * kMaxCh * kMaxCh);
+        if (A.coeffs) blk_coefficients(A, sysi, M, ld, P, xs, small + 3 * nch * nch);
         __syncthreads();
         BLK_PH(6)
     }
 }
 
-static int blk_ctas_per_sm() { return JITR_BLK_CTAS; }
+static int blk_threads(const BlkGeom& g) { return g.PR <= 128 ? 128 : 256; }
+static int blk_ctas_per_sm(const BlkGeom& g) { return 512 / blk_threads(g); }
 
-static int launch_block_solve(const GenArgs& a, cudaStream_t st) {
-    const BlkGeom g = blk_geom(a.n, a.nch);
+template <int T>
+static int launch_block_solve_t(const GenArgs& a, const BlkGeom& g, cudaStream_t st) {
     const size_t smem = blk_smem_bytes(g);
     static size_t conf = 0;
     if (smem > conf) {
-        if (cudaFuncSetAttribute(block_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        if (cudaFuncSetAttribute(block_solve_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             return set_cuda_error("cudaFuncSetAttribute(block_solve)");
         conf = smem;
     }
     int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, block_solve_kernel, kBlkThreads, smem) != cudaSuccess || per_sm < 1)
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, block_solve_kernel<T>, T, smem) != cudaSuccess || per_sm < 1)
         return set_cuda_error("block_solve occupancy");
-    if (per_sm > blk_ctas_per_sm()) per_sm = blk_ctas_per_sm();  // the workspace holds that many slabs per SM
+    if (per_sm > blk_ctas_per_sm(g)) per_sm = blk_ctas_per_sm(g);  // the workspace holds that many slabs per SM
     long long blocks = (long long)sm_count() * per_sm;
     if (blocks > a.batch) blocks = a.batch;
-    block_solve_kernel<<<(unsigned)blocks, kBlkThreads, smem, st>>>(a, g);
+    block_solve_kernel<T><<<(unsigned)blocks, T, smem, st>>>(a, g);
     count_launch();
     if (cudaGetLastError() != cudaSuccess) return set_cuda_error("block_solve launch");
     return JITR_B200_OK;
+}
+
+static int launch_block_solve(const GenArgs& a, cudaStream_t st) {
+    const BlkGeom g = blk_geom(a.n, a.nch);
+    return blk_threads(g) == 128 ? launch_block_solve_t<128>(a, g, st) : launch_block_solve_t<256>(a, g, st);
 }
 
 template <int MAXNS>
@@ -891,13 +900,13 @@ extern "C" int jitr_b200_debug_block_phases(unsigned long long* out16, int reset
 
 extern "C" long long jitr_b200_solve_workspace_bytes(int nbasis, int nch, long long batch, int coeffs) {
     if (nbasis < 1 || nch < 1 || nch > kMaxCh || batch < 0) return -1;
-    if (nch == 1 && !coeffs && ((nbasis + 7) & ~7) <= 64) return 0;  // warp-per-system: shared memory only
+    if (nch == 1 && !coeffs && ((nbasis + 7) & ~7) <= JITR_WARP_SOLVE_MAXP) return 0;  // warp-per-system: shared memory only
     const long long n = (long long)nbasis * nch;
     const BlkGeom g = blk_geom((int)n, nch);
     if (g.PR <= kBlkMaxRows) {  // one slab per resident CTA
         int sms = sm_count();
         if (sms <= 0) sms = 148;
-        long long ctas = (long long)sms * blk_ctas_per_sm();
+        long long ctas = (long long)sms * blk_ctas_per_sm(g);
         if (ctas > batch) ctas = batch;
         return ctas * g.PR * g.PC * 16;
     }
@@ -928,10 +937,10 @@ extern "C" int jitr_b200_solve_batched(int nbasis, int nch, long long batch, con
     a.uext = reinterpret_cast<double2*>(uext); a.coeffs = reinterpret_cast<double2*>(coeffs);
     a.workspace = reinterpret_cast<double2*>(workspace); a.status = status;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    // single channel, no coefficients, P <= 64: warp-per-system blocked LU
-    if (nch == 1 && !coeffs && ((nbasis + 7) & ~7) <= 64) {
-        if (((nbasis + 7) & ~7) + 1 <= 64) return launch_warp_solve<2>(a, st);
-        return launch_warp_solve<3>(a, st);
+    // single channel, no coefficients, small P: warp-per-system blocked LU
+    if (nch == 1 && !coeffs && ((nbasis + 7) & ~7) <= JITR_WARP_SOLVE_MAXP) {
+        static_assert(JITR_WARP_SOLVE_MAXP + 1 <= 64, "warp_solve_kernel<2>: at most two row slots per lane");
+        return launch_warp_solve<2>(a, st);
     }
     if (blk_geom(a.n, nch).PR <= kBlkMaxRows) {
         if (!workspace) return set_error(JITR_B200_ERR_BAD_ARG, "solve_batched: workspace of jitr_b200_solve_workspace_bytes() bytes required");
