@@ -160,6 +160,26 @@ int jitr_b200_solve_batched(int nbasis, int nch, long long batch, const double* 
                             const double* weights, double* R, double* S, double* uext, double* coeffs,
                             double* workspace, int* status, void* stream);
 
+/*
+ * Quasi-elastic (p,n) DWBA, the steps after the distorted-wave solves (xs/quasielastic_pn.py).
+ *
+ * jitr_b200_qe_overlap: T_lj = scale * sum_n x_p[n] (U1c[n] + (l.s)_j U1so[n]) x_n[n]   (:317-322)
+ *   xp, xn      [nj][batch][nbasis] complex solution coefficients of the entrance / exit channel
+ *               (the coeffs output of jitr_b200_solve_batched, systems ordered j-major)
+ *   U1c, U1so   [batch][nbasis] complex isovector transition potentials (U1so may be NULL)
+ *   lds0, lds1  (l.s) of j = l+1/2 and l-1/2;  scale = 1 / (R_ch k_p k_n)
+ *   out         complex, element (b, j) at  b * out_sample_stride + j * out_j_stride  (complex units)
+ *
+ * jitr_b200_qe_xs: dsigma/dOmega = factor * sum_{m,m'} |sum_{l < lmax, j} G[m][m'][l][j][theta] T[b][l][j]|^2  (:375-392)
+ *   T [batch][lmax+1][2] complex,  G [2][2][lmax+1][2][n_angles] complex (:198-217),
+ *   factor = 10 * xs_factor,  out [batch][n_angles] in mb/sr
+ */
+int jitr_b200_qe_overlap(int nbasis, long long batch, int nj, const double* xp, const double* xn, const double* U1c,
+                         const double* U1so, double lds0, double lds1, double scale, double* out,
+                         long long out_sample_stride, long long out_j_stride, void* stream);
+int jitr_b200_qe_xs(int lmax, int n_angles, long long batch, const double* T, const double* G, double factor,
+                    double* out, void* stream);
+
 /* bytes of device scratch jitr_b200_solve_batched needs for this problem (0: none; -1: bad arguments) */
 long long jitr_b200_solve_workspace_bytes(int nbasis, int nch, long long batch, int coeffs);
 

@@ -37,17 +37,38 @@ def _particle(p, mass):
 
 
 class Reaction:
-    """Two-body entrance channel: ``target`` + ``projectile`` (reactions/reaction.py:343-556)."""
+    """Two-body reaction ``target(projectile, product)residual`` (reactions/reaction.py:343-623).  ``product`` and
+    ``residual`` are only needed for exit-channel kinematics (quasi-elastic (p,n)); rest masses are passed
+    explicitly, the Q value follows from them unless given."""
 
-    def __init__(self, target, projectile, process=None, mass_target=None, mass_projectile=None):
+    def __init__(self, target, projectile, product=None, residual=None, process=None, mass_target=None,
+                 mass_projectile=None, mass_product=None, mass_residual=None, Q=None):
         self.target = _particle(target, mass_target)
         self.projectile = _particle(projectile, mass_projectile)
+        self.product = None if product is None else _particle(product, mass_product)
+        self.residual = None if residual is None else _particle(residual, mass_residual)
         self.process = process
+        if Q is None and self.product is not None and self.residual is not None:
+            Q = self.target.m0 + self.projectile.m0 - self.product.m0 - self.residual.m0
+        self.Q = Q
 
     def kinematics(self, Elab):
         """reactions/reaction.py:540-556."""
         return semi_relativistic_kinematics(
             self.target.m0, self.projectile.m0, Elab, Zz=self.target.Z * self.projectile.Z
+        )
+
+    def kinematics_exit(self, entrance, residual_excitation_energy=0, product_excitation_energy=0):
+        """Exit-channel kinematics from the entrance channel's and the excitation energies.
+        reactions/reaction.py:580-623."""
+        if self.Q is None:
+            raise ValueError("kinematics_exit() requires a defined Q-value.")
+        if self.residual is None or self.product is None:
+            raise ValueError("kinematics_exit() requires both product and residual to be defined.")
+        Ecm = entrance.Ecm + self.Q - residual_excitation_energy - product_excitation_energy
+        Elab = (self.residual.m0 + self.product.m0) / self.residual.m0 * Ecm
+        return semi_relativistic_kinematics(
+            self.residual.m0 + residual_excitation_energy, self.product.m0, Elab, Zz=self.residual.Z * self.product.Z
         )
 
 

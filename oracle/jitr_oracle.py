@@ -535,6 +535,111 @@ def differential_elastic_xs(k, angles, sp, sm, P, P1, f_c, sigma_l, eps=1e-30):
     return d0 * 10.0, Ay, Q, tot * 10.0 * 2.0 * np.pi / k**2, rxn * 10.0 * np.pi / k**2
 
 
+# ----------------------------------------------------------------------------
+# quasi-elastic (p,n) in the DWBA  (xs/quasielastic_pn.py)
+# ----------------------------------------------------------------------------
+def exit_kinematics(kin_entrance, masses, Q, Ex_residual=0.0, Ex_product=0.0, Zz_exit=0):
+    """reactions/reaction.py:580-623.  masses = (target, projectile, product, residual) rest masses."""
+    _, Ecm_in, _, _, _ = kin_entrance
+    _, _, m_prod, m_res = masses
+    Ecm = Ecm_in + Q - Ex_residual - Ex_product
+    Elab = (m_res + m_prod) / m_res * Ecm
+    return semi_relativistic_kinematics(m_res + Ex_residual, m_prod, Elab, Zz=Zz_exit)
+
+
+class QuasielasticWorkspace:
+    """xs/quasielastic_pn.py:83-421: distorted waves of the entrance (p) and exit (n) channel with
+    wavefunction=True, T_lj = sum_n x_p U_1 x_n / (R k_p k_n) (:317-322), early break on |T| (:336-340),
+    angular sum with the precomputed geometric factors (:183-217, :375-392)."""
+
+    def __init__(self, nbasis, lmax, channel_radius_fm, kin_entrance, kin_exit, angles, A_target, Z_target,
+                 Zz_entrance, Zz_exit=0, tol=1e-6):
+        from scipy.special import gamma, sph_harm_y
+        from sympy.physics.wigner import clebsch_gordan
+
+        self.N, self.lmax, self.R, self.tol = nbasis, lmax, channel_radius_fm, tol
+        self.kin_p, self.kin_n = tuple(kin_entrance), tuple(kin_exit)
+        _, self.Ep, self.mup, self.kp, self.etap = self.kin_p
+        _, self.En, self.mun, self.kn, self.etan = self.kin_n
+        self.ap, self.an = channel_radius_fm * self.kp, channel_radius_fm * self.kn
+        self.angles = np.asarray(angles, dtype=np.float64)
+        Nn = A_target - Z_target
+        self.isovector_factor = np.sqrt(np.fabs(Nn - Z_target)) / (Nn - Z_target - 1)  # :144-147
+        eye = np.eye(nbasis)
+        self.free_p = [kinetic_bloch_matrix(nbasis, self.ap, l) - eye for l in range(lmax + 1)]  # :150-163
+        self.free_n = [kinetic_bloch_matrix(nbasis, self.an, l) - eye for l in range(lmax + 1)]
+        self.b = boundary_vector(nbasis)
+        self.asym_p = [coulomb_hankel(l, self.etap, self.ap) for l in range(lmax + 1)]
+        self.asym_n = [coulomb_hankel(l, self.etan, self.an) for l in range(lmax + 1)]
+        x, _ = legendre_mesh(nbasis)
+        self.rgrid = x * self.ap / self.kp  # :219-223
+        # :186-217
+        self.xs_factor = (self.kn / self.kp) * self.mup * self.mun / (4 * np.pi**2 * HBARC**4 * (2 * 1.0 / 2 + 1))
+        ls = np.arange(lmax + 1)
+        self.sigma_c = np.angle(gamma(1 + ls + 1j * self.etap))
+        G = np.zeros((2, 2, lmax + 1, 2, self.angles.shape[0]), dtype=np.complex128)
+        for im, m in enumerate([-0.5, 0.5]):
+            for imp, mp in enumerate([-0.5, 0.5]):
+                for l in range(lmax + 1):
+                    for ijp, jp in enumerate([l + 1 / 2, l - 1 / 2] if l > 0 else [l + 1 / 2]):
+                        if abs(m - mp) <= l and jp >= 0:
+                            ylm = sph_harm_y(l, int(m - mp), self.angles, 0)
+                            cg0 = clebsch_gordan(l, 1 / 2, jp, m - mp, m, mp)
+                            cg1 = clebsch_gordan(l, 1 / 2, jp, 0, m, m)
+                            G[im, imp, l, ijp, :] = (
+                                (4 * np.pi) ** (3.0 / 2.0) / (self.kp * self.kn) * np.exp(1j * self.sigma_c[l])
+                                * complex(cg1) * complex(cg0) * np.sqrt(2 * l + 1) * (-1) ** (2 * jp + 1) * ylm
+                            )
+        self.geometric_factor = G
+
+    def _wave(self, A, asym, a):
+        one = np.ones(1, dtype=np.float64)
+        H = [np.array([v], dtype=np.complex128) for v in asym]
+        _, S, Ainv, up = solve_smatrix(A, self.b, H[0], H[1], H[2], H[3], one, a, 1, self.N)
+        return S[0, 0], solution_coeffs(Ainv, self.b, up, 1, self.N)[0]
+
+    def tmatrix(self, U_p_coulomb, U_p_central, U_p_spin_orbit=None, U_n_central=None, U_n_spin_orbit=None):
+        """:225-342.  Returns (Tpn, Sn, Sp), each (lmax + 1, 2)."""
+        N, L1 = self.N, self.lmax + 1
+        z = np.zeros(N, dtype=np.complex128)
+        pc, pcoul = np.asarray(U_p_central, dtype=np.complex128), np.asarray(U_p_coulomb, dtype=np.complex128)
+        pso = z if U_p_spin_orbit is None else np.asarray(U_p_spin_orbit, dtype=np.complex128)
+        nc = np.asarray(U_n_central, dtype=np.complex128)
+        nso = z if U_n_spin_orbit is None else np.asarray(U_n_spin_orbit, dtype=np.complex128)
+        U1c = -(nc - pc) * self.isovector_factor
+        U1so = -(nso - pso) * self.isovector_factor
+        T = np.zeros((L1, 2), dtype=np.complex128)
+        Sn = np.zeros((L1, 2), dtype=np.complex128)
+        Sp = np.zeros((L1, 2), dtype=np.complex128)
+
+        def element(l, lds):
+            sn, xn = self._wave(self.free_n[l] + np.diag(nc + lds * nso) / self.En, self.asym_n[l], self.an)
+            sp, xp = self._wave(self.free_p[l] + np.diag(pc + pcoul + lds * pso) / self.Ep, self.asym_p[l], self.ap)
+            t = np.sum(xp * (U1c + lds * U1so) * xn) / self.R / self.kp / self.kn
+            return t, sn, sp
+
+        T[0, 0], Sn[0, 0], Sp[0, 0] = element(0, 0.0)
+        for l in range(1, L1):
+            lds = spin_half_orbit_couplings(l)
+            T[l, 0], Sn[l, 0], Sp[l, 0] = element(l, lds[0])
+            T[l, 1], Sn[l, 1], Sp[l, 1] = element(l, lds[1])
+            if abs(T[l, 0]) < self.tol and abs(T[l, 1]) < self.tol:
+                break
+        return T, Sn, Sp
+
+    def xs(self, *potentials):
+        """:344-392 (the angular sum stops at lmax - 1, as the reference's does)."""
+        T, _, _ = self.tmatrix(*potentials)
+        Tmmp = np.zeros((2, 2, self.angles.shape[0]), dtype=np.complex128)
+        for im, m in enumerate([-0.5, 0.5]):
+            for imp, mp in enumerate([-0.5, 0.5]):
+                for l in range(0, self.lmax):
+                    for ijp, jp in enumerate([l + 0.5, l - 0.5]):
+                        if abs(m - mp) <= l and jp >= 0:
+                            Tmmp[im, imp, :] += self.geometric_factor[im, imp, l, ijp, :] * T[l, ijp]
+        return self.xs_factor * 10 * np.sum(np.absolute(Tmmp) ** 2, axis=(0, 1))
+
+
 def interaction_range(A, rA=1.2, r0=0.0):
     """utils/utils.py:118-120."""
     return r0 + rA * A ** (1 / 3)

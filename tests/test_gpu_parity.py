@@ -486,3 +486,90 @@ def test_singular_system_reports_status():
     assert int(status[0]) != _cabi.STATUS_OK and int(status[1]) == _cabi.STATUS_OK
     with pytest.raises(np.linalg.LinAlgError):
         ws.smatrix(np.full(20, np.nan, dtype=complex))
+
+
+# ------------------------------------------------------------------------------------------------
+# quasi-elastic (p,n) DWBA workspace (xs/quasielastic_pn.py)
+# ------------------------------------------------------------------------------------------------
+def make_qe_ws(g, tol=None):
+    from jitr_b200 import reactions
+    from jitr_b200.xs.quasielastic_pn import Workspace
+
+    AZ, m = g["AZ"], g["masses"]
+    rx = reactions.Reaction((int(AZ[0]), int(AZ[1])), (int(AZ[2]), int(AZ[3])), (int(AZ[4]), int(AZ[5])), (int(AZ[6]), int(AZ[7])),
+                            mass_target=m[0], mass_projectile=m[1], mass_product=m[2], mass_residual=m[3])
+    ke = rx.kinematics(float(g["Elab"]))
+    kx = rx.kinematics_exit(ke, float(g["Ex"]))
+    return Workspace(rx, ke, kx, jitr_b200.Solver(int(g["N"])), g["angles"], int(g["lmax"]), float(g["Rch"]),
+                     tmatrix_abs_tol=float(g["tol"]) if tol is None else tol)
+
+
+@pytest.mark.parametrize("name", ["qe_reftest", "qe_48Ca_35MeV", "qe_48Ca_35MeV_nobreak"])
+def test_quasielastic_pn_vs_reference_golden(golden, name):
+    """Distorted waves of both channels with coefficients, T_lj overlap, early break and the angular sum against
+    the REAL reference: S to 1e-10, T_lj to 1e-9 of its largest element, dsigma/dOmega to 1e-8."""
+    g = golden(name)
+    ws = make_qe_ws(g)
+    U = [torch.tensor(np.ascontiguousarray(g["U"][:, i]), device="cuda") for i in range(5)]
+    so = bool(g["has_so"][0])
+    args = (U[0], U[1], U[2] if so else None, U[3], U[4] if so else None)
+    T, Sn, Sp, status = ws.tmatrix_batch(*args)
+    xs = ws.xs_batch(*args)
+    assert int(status.abs().sum()) == 0
+    for b in range(g["U"].shape[0]):
+        assert normerr(T[b].cpu().numpy(), g["Tpn"][b]) < 1e-9
+        assert np.abs(Sn[b].cpu().numpy() - g["Sn"][b]).max() < RTOL_S
+        assert np.abs(Sp[b].cpu().numpy() - g["Sp"][b]).max() < RTOL_S
+        assert relerr(xs[b].cpu().numpy(), g["xs"][b]) < RTOL_XS
+    # the break really happened where the reference's did (entries beyond it are exactly zero)
+    assert np.array_equal(T.cpu().numpy() == 0, g["Tpn"] == 0)
+
+
+def test_quasielastic_pn_single_sample_api_and_optional_spin_orbit(golden):
+    """The reference's own test (tests/test_xs_optional_spin_orbit.py:56-103): omitted spin-orbit terms equal
+    explicit zeros; numpy in, numpy out, same values as the reference."""
+    g = golden("qe_reftest")
+    ws = make_qe_ws(g)
+    U = g["U"][0]
+    zero = np.zeros_like(U[0])
+    om = ws.tmatrix(U[0], U[1], U_n_central=U[3])
+    ex = ws.tmatrix(U[0], U[1], zero, U[3], zero)
+    for a, b in zip(om, ex):
+        np.testing.assert_allclose(a, b)
+    np.testing.assert_allclose(ws.xs(U[0], U[1], U_n_central=U[3]), ws.xs(U[0], U[1], zero, U[3], zero))
+    assert normerr(om[0], g["Tpn"][0]) < 1e-9
+    assert relerr(ws.xs(U[0], U[1], U_n_central=U[3]), g["xs"][0]) < RTOL_XS
+    with pytest.raises(TypeError):
+        ws.tmatrix(U[0], U[1])
+    with pytest.raises(ValueError):
+        ws.tmatrix(U[0][:-1], U[1], U_n_central=U[3])
+
+
+def test_quasielastic_pn_vs_oracle_random_batch(golden):
+    """Seeded potentials outside the golden set, mixed early breaks inside one batch, against the CPU oracle."""
+    g = golden("qe_48Ca_35MeV")
+    ws = make_qe_ws(g, tol=1e-5)
+    AZ = g["AZ"]
+    ow = orc.QuasielasticWorkspace(int(g["N"]), int(g["lmax"]), float(g["Rch"]), g["kin_entrance"], g["kin_exit"], g["angles"],
+                                   int(AZ[0]), int(AZ[1]), int(AZ[1] * AZ[3]), 0, 1e-5)
+    rng = np.random.default_rng(7)
+    B = 6
+    U = np.repeat(g["U"][:1], B, axis=0).copy()  # (B, 5, N)
+    U[:, 1] *= (1 + 0.08 * rng.standard_normal((B, 1)))
+    U[:, 3] *= (1 + 0.08 * rng.standard_normal((B, 1)))
+    U[:, 2] *= (1 + 0.2 * rng.standard_normal((B, 1)))
+    U[3:, 3] = U[3:, 1] * (1 + 1e-4)  # nearly equal p and n potentials: tiny T, early break much sooner
+    Ut = [torch.tensor(np.ascontiguousarray(U[:, i]), device="cuda") for i in range(5)]
+    T, Sn, Sp, status = ws.tmatrix_batch(*Ut)
+    xs = ws.xs_batch(*Ut)
+    assert int(status.abs().sum()) == 0
+    breaks = set()
+    for b in range(B):
+        To, Sno, Spo = ow.tmatrix(*U[b])
+        breaks.add(int(np.max(np.nonzero(np.abs(To).sum(axis=1))[0])))
+        assert np.array_equal(T[b].cpu().numpy() == 0, To == 0)
+        assert normerr(T[b].cpu().numpy(), To) < 1e-9
+        assert np.abs(Sn[b].cpu().numpy() - Sno).max() < RTOL_S
+        assert np.abs(Sp[b].cpu().numpy() - Spo).max() < RTOL_S
+        assert relerr(xs[b].cpu().numpy(), ow.xs(*U[b])) < RTOL_XS
+    assert len(breaks) > 1

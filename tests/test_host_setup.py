@@ -125,3 +125,29 @@ def test_utils():
     assert abs(utils.interaction_range(208) - 1.2 * 208 ** (1 / 3)) < 1e-15
     k = utils.classical_kinematics(44657.0, 938.3, 42.1, 20)
     assert abs(k.Ecm - 44657.0 / (44657.0 + 938.3) * 42.1) < 1e-12
+
+
+def test_quasielastic_workspace_host_setup(golden):
+    """Host side of xs/quasielastic_pn.py:83-217 (no GPU): exit kinematics, isovector factor, kinematic
+    factor and the geometric factors (closed-form Clebsch-Gordan instead of sympy) against the reference's."""
+    from jitr_b200.xs.quasielastic_pn import Workspace
+
+    g = golden("qe_48Ca_35MeV")
+    AZ, m = g["AZ"], g["masses"]
+    rx = reactions.Reaction((int(AZ[0]), int(AZ[1])), (int(AZ[2]), int(AZ[3])), (int(AZ[4]), int(AZ[5])), (int(AZ[6]), int(AZ[7])),
+                            mass_target=m[0], mass_projectile=m[1], mass_product=m[2], mass_residual=m[3])
+    assert abs(rx.Q - float(g["Q"])) < 1e-9
+    ke = rx.kinematics(float(g["Elab"]))
+    kx = rx.kinematics_exit(ke, float(g["Ex"]))
+    assert np.allclose(np.array(tuple(ke)), g["kin_entrance"], rtol=1e-13)
+    assert np.allclose(np.array(tuple(kx)), g["kin_exit"], rtol=1e-12)
+    ws = Workspace(rx, ke, kx, jitr_b200.Solver(int(g["N"])), g["angles"], int(g["lmax"]), float(g["Rch"]))
+    gf = g["geometric_factor"]
+    assert np.abs(ws.geometric_factor - gf).max() <= 1e-12 * np.abs(gf).max()
+    assert abs(ws.xs_factor / g["xs_factor"] - 1) < 1e-12
+    assert abs(ws.isovector_factor - g["isovector_factor"]) < 1e-15
+    assert np.allclose(ws.radial_grid(), g["rgrid"], rtol=1e-12)
+    with pytest.raises(ValueError):
+        Workspace(reactions.Reaction((48, 20), (1, 1)), ke, kx, jitr_b200.Solver(8), g["angles"], 3, 8.0)
+    with pytest.raises(ValueError):
+        reactions.Reaction((48, 20), (1, 1)).kinematics_exit(ke)

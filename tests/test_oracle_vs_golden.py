@@ -191,3 +191,25 @@ def test_survey_anchor_values(golden):
     assert abs(g["dsdo"][0][90] - 8.6793242520790077) < 1e-8
     g = golden("nb_kduq_uq_demo")
     assert round(float(g["pct84_idx9"]), 6) == 1.163423  # kduq_uq_demo.ipynb cell 20
+
+
+@pytest.mark.parametrize("name", ["qe_reftest", "qe_48Ca_35MeV", "qe_48Ca_35MeV_nobreak"])
+def test_quasielastic_pn_workspace(golden, name):
+    """Restatement of xs/quasielastic_pn.py against the reference's own outputs (T_lj, S of both channels,
+    dsigma/dOmega; early break on and off)."""
+    g = golden(name)
+    AZ = g["AZ"]
+    kx = orc.exit_kinematics(g["kin_entrance"], g["masses"], float(g["Q"]), float(g["Ex"]), 0.0, Zz_exit=int(AZ[5] * AZ[7]))
+    assert np.allclose(np.array(kx), g["kin_exit"], rtol=1e-14, atol=0)
+    w = orc.QuasielasticWorkspace(int(g["N"]), int(g["lmax"]), float(g["Rch"]), g["kin_entrance"], g["kin_exit"], g["angles"],
+                                  int(AZ[0]), int(AZ[1]), int(AZ[1] * AZ[3]), 0, float(g["tol"]))
+    gf = g["geometric_factor"]
+    assert np.abs(w.geometric_factor - gf).max() <= 1e-14 * np.abs(gf).max()
+    assert abs(w.xs_factor - g["xs_factor"]) <= 1e-15 * g["xs_factor"]
+    assert abs(w.isovector_factor - g["isovector_factor"]) <= 1e-15
+    for b in range(min(3, g["U"].shape[0])):
+        T, Sn, Sp = w.tmatrix(*g["U"][b])
+        assert np.abs(T - g["Tpn"][b]).max() <= 1e-11 * np.abs(g["Tpn"][b]).max()
+        assert np.abs(Sn - g["Sn"][b]).max() <= 1e-11
+        assert np.abs(Sp - g["Sp"][b]).max() <= 1e-11
+        assert np.abs(w.xs(*g["U"][b]) / g["xs"][b] - 1).max() <= 1e-10
