@@ -4,8 +4,10 @@ Same definitions as the reference (utils/free_solutions.py:39-109): H+- = G +- i
 H' = ((l+1)/s + eta/(l+1)) H_l - sqrt(1 + eta^2/(l+1)^2) H_{l+1}.  Setup-side, host code.
 
 Differences in HOW (not what): a whole table l = 0..lmax is produced from F, G at l = 0..lmax+1
-(2(lmax+2) special-function evaluations instead of the reference's 12 per l), and for eta = 0 the
-Riccati-Bessel closed form s j_l(s), -s y_l(s) replaces the mpmath calls.
+(2(lmax+2) special-function evaluations instead of the reference's 12 per l); for eta = 0 the
+Riccati-Bessel closed form s j_l(s), -s y_l(s) replaces the mpmath calls; for eta > 0 the table comes from
+Steed's continued fractions (``coulomb_fg_steed``, ~0.3 ms instead of ~1 s per energy) wherever they hold
+1e-13 -- at or above the l = 0 turning point, judged a posteriori by |G_0 / F_0| -- and from mpmath below it.
 """
 from __future__ import annotations
 
@@ -63,6 +65,100 @@ def H_minus_prime(s, l, eta, dx=1e-6, asym=CoulombAsymptotics):
     return coulomb_func_deriv(lambda ss, ll, ee: H_minus(ss, ll, ee, asym=asym), s, l, eta)
 
 
+def coulomb_fg_steed(lmax, eta, rho, acc=1e-16, maxit=100000):
+    """Regular and irregular Coulomb functions F_l, G_l and their rho-derivatives for l = 0..lmax at rho > 0.
+
+    Steed's method (Barnett, Comput. Phys. Commun. 27 (1982) 147): F'/F at l = lmax from the continued fraction
+    CF1 (modified Lentz, sign of F from the denominators), downward recurrence to l = 0, p + iq = H+'/H+ at
+    l = 0 from CF2, normalisation by the Wronskian, upward recurrence for G.  Relative accuracy ~1e-14 at and
+    above the l = 0 turning point rho = 2 eta; below it the normalisation loses about |G_0 / F_0| ulps.
+    Returns (F, G, F', G') or None when a continued fraction does not converge."""
+    eta, rho, L = float(eta), float(rho), int(lmax)
+    tiny = 1e-300
+    xi = 1.0 / rho
+
+    def S(k):
+        return k * xi + eta / k
+
+    def R2(k):
+        return 1.0 + (eta / k) ** 2
+
+    k = L + 1
+    f = S(k) or tiny
+    C, D, sign = f, 0.0, 1.0
+    for _ in range(maxit):
+        a, b = -R2(k), S(k) + S(k + 1)
+        D = (b + a * D) or tiny
+        C = (b + a / C) or tiny
+        D = 1.0 / D
+        if D < 0.0:
+            sign = -sign
+        delta = C * D
+        f *= delta
+        k += 1
+        if abs(delta - 1.0) < acc:
+            break
+    else:
+        return None
+    F, Fp = np.zeros(L + 1), np.zeros(L + 1)
+    F[L] = sign * 1e-60
+    Fp[L] = f * F[L]
+    for l in range(L, 0, -1):
+        Sl, Rl = S(l), np.sqrt(R2(l))
+        F[l - 1] = (Sl * F[l] + Fp[l]) / Rl
+        Fp[l - 1] = Sl * F[l - 1] - Rl * F[l]
+        if abs(F[l - 1]) > 1e250:
+            F[l - 1 :] *= 1e-250
+            Fp[l - 1 :] *= 1e-250
+    f0 = Fp[0] / F[0]
+    # CF2 at l = 0 in real arithmetic (a b = (i eta)(i eta + 1))
+    P, Q = 0.0, 1.0 - eta * xi
+    ar, ai = -(eta * eta), eta
+    br, bi = 2.0 * (rho - eta), 2.0
+    den = br * br + bi * bi
+    dr, di = br / den, -bi / den
+    dp, dq = -xi * (ar * di + ai * dr), xi * (ar * dr - ai * di)
+    pk = 0.0
+    for _ in range(maxit):
+        P += dp
+        Q += dq
+        pk += 2.0
+        ar += pk
+        ai += 2.0 * eta
+        bi += 2.0
+        d_r = ar * dr - ai * di + br
+        d_i = ai * dr + ar * di + bi
+        c = 1.0 / (d_r * d_r + d_i * d_i)
+        dr, di = c * d_r, -c * d_i
+        a_, b_ = br * dr - bi * di - 1.0, bi * dr + br * di
+        dp, dq = dp * a_ - dq * b_, dp * b_ + dq * a_
+        if abs(dp) + abs(dq) < (abs(P) + abs(Q)) * acc:
+            break
+    else:
+        return None
+    P += dp
+    Q += dq
+    gam = (f0 - P) / Q
+    w2 = (f0 - P) * gam + Q
+    if not (w2 > 0.0 and np.isfinite(w2)):
+        return None
+    F0 = np.copysign(1.0 / np.sqrt(w2), F[0])
+    scale = F0 / F[0]
+    F *= scale
+    Fp *= scale
+    G, Gp = np.zeros(L + 1), np.zeros(L + 1)
+    G[0] = gam * F0
+    Gp[0] = (P * gam - Q) * F0
+    for l in range(L):
+        Sl, Rl = S(l + 1), np.sqrt(R2(l + 1))
+        G[l + 1] = (Sl * G[l] - Gp[l]) / Rl
+        Gp[l + 1] = Rl * G[l] - Sl * G[l + 1]
+    return F, G, Fp, Gp
+
+
+# Steed's normalisation loses about |G_0 / F_0| ulps below the turning point: beyond this ratio use mpmath
+STEED_MAX_G0_OVER_F0 = 1.0e2
+
 _TABLE_CACHE: dict = {}
 
 
@@ -76,8 +172,12 @@ def coulomb_hankel_table(lmax, eta, s):
         F = s * sc.spherical_jn(ls, s)
         G = -s * sc.spherical_yn(ls, s)
     else:
-        F = np.array([float(np.real(CoulombAsymptotics.F(s, int(l), eta))) for l in ls])
-        G = np.array([float(np.real(CoulombAsymptotics.G(s, int(l), eta))) for l in ls])
+        fg = coulomb_fg_steed(lmax + 1, eta, s) if eta > 0.0 else None
+        if fg is not None and abs(fg[1][0]) <= STEED_MAX_G0_OVER_F0 * abs(fg[0][0]) and np.all(np.isfinite(fg[1])):
+            F, G = fg[0], fg[1]
+        else:
+            F = np.array([float(np.real(CoulombAsymptotics.F(s, int(l), eta))) for l in ls])
+            G = np.array([float(np.real(CoulombAsymptotics.G(s, int(l), eta))) for l in ls])
     Hp = G + 1j * F
     Hm = G - 1j * F
     l = ls[:-1]

@@ -151,3 +151,33 @@ def test_quasielastic_workspace_host_setup(golden):
         Workspace(reactions.Reaction((48, 20), (1, 1)), ke, kx, jitr_b200.Solver(8), g["angles"], 3, 8.0)
     with pytest.raises(ValueError):
         reactions.Reaction((48, 20), (1, 1)).kinematics_exit(ke)
+
+
+def test_steed_coulomb_functions_match_mpmath():
+    """(f)2: the Coulomb-Hankel table off mpmath.  Steed's continued fractions against mpmath.coulombf/g (the
+    reference's source, utils/free_solutions.py:39-50) at and above the turning point; the a-posteriori switch
+    sends sub-barrier cases to mpmath, so the table is accurate everywhere."""
+    import mpmath
+
+    from jitr_b200 import free_solutions as fs
+
+    worst = 0.0
+    for eta, rho in [(0.05, 1.0), (0.59, 14.2), (1.3, 6.0), (3.0, 10.0), (5.6, 10.0), (5.6, 15.0), (9.0, 15.0), (15.0, 40.0)]:
+        F, G, Fp, Gp = fs.coulomb_fg_steed(30, eta, rho)
+        assert abs(G[0]) <= fs.STEED_MAX_G0_OVER_F0 * abs(F[0])
+        for l in (0, 1, 7, 18, 30):
+            Fm, Gm = float(mpmath.coulombf(l, eta, rho)), float(mpmath.coulombg(l, eta, rho))
+            # relative to |H| = |G + iF| (G_l crosses zero in l at fixed rho: its own relative error means nothing there)
+            worst = max(worst, abs((G[l] - Gm) + 1j * (F[l] - Fm)) / abs(Gm + 1j * Fm), abs(F[l] / Fm - 1))
+            # Wronskian F' G - F G' = 1
+            assert abs(Fp[l] * G[l] - F[l] * Gp[l] - 1) < 1e-11
+    assert worst < 2e-14
+    # table = the reference's definition (mpmath values, derivative by the l -> l+1 recurrence), both regimes
+    from oracle import jitr_oracle as orc
+
+    for eta, s in [(0.5903268765300718, 14.235372770878110), (2.2, 9.0), (6.0, 4.0)]:  # the last one is sub-barrier
+        fs._TABLE_CACHE.clear()
+        tab = fs.coulomb_hankel_table(12, eta, s)
+        for l in (0, 3, 12):
+            ref = np.array(orc.coulomb_hankel(l, eta, s))
+            assert np.max(np.abs(tab[l] - ref) / np.abs(ref)) < 2e-13
