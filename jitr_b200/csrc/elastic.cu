@@ -179,6 +179,7 @@ extern "C" int jitr_b200_elastic_sweep_params(int nbasis, int lmax, int model, l
                                               const double* etab, const double* asym, const double* params,
                                               int n_params, double tol, double* S_out, int* nl_out, int* status,
                                               void* stream) {
+    if (n_samples == 0) return JITR_B200_OK;  // empty batch (its tensors have null data pointers)
     if (lmax < 0 || n_samples < 0 || n_energies < 1 || !That || !mesh_x || !bvec || !etab || !asym || !params ||
         !S_out || !nl_out || !status)
         return set_error(JITR_B200_ERR_BAD_ARG, "elastic_sweep_params: null pointer or bad size");
@@ -203,6 +204,7 @@ extern "C" int jitr_b200_elastic_sweep_tensors(int nbasis, int lmax, long long n
                                                const double* etab, const double* asym, const double* central,
                                                const double* spin_orbit, const double* coulomb, double tol,
                                                double* S_out, int* nl_out, int* status, void* stream) {
+    if (n_samples == 0) return JITR_B200_OK;  // empty batch (its tensors have null data pointers)
     if (lmax < 0 || n_samples < 0 || n_energies < 1 || !That || !mesh_x || !bvec || !etab || !asym || !central ||
         !S_out || !nl_out || !status)
         return set_error(JITR_B200_ERR_BAD_ARG, "elastic_sweep_tensors: null pointer or bad size");
@@ -226,10 +228,10 @@ extern "C" int jitr_b200_elastic_observables(int lmax, int n_angles, long long n
                                              const double* S, const int* nl, const double* P, const double* P1,
                                              const double* phase, const double* f_c, const double* kvec,
                                              double* dsdo, double* Ay, double* Q, double* tot_rxn, void* stream) {
+    if (n_samples == 0) return JITR_B200_OK;  // empty batch (its tensors have null data pointers)
     if (lmax < 0 || lmax > 255 || n_angles < 1 || n_samples < 0 || n_energies < 1 || !S || !nl || !P || !P1 || !phase ||
         !f_c || !kvec || !dsdo || !tot_rxn)
         return set_error(JITR_B200_ERR_BAD_ARG, "elastic_observables: null pointer or bad size");
-    if (n_samples == 0) return JITR_B200_OK;
     ObsArgs a{};
     a.lmax = lmax; a.n_angles = n_angles; a.n_energies = n_energies; a.n_samples = n_samples;
     a.S = reinterpret_cast<const double2*>(S); a.nl = nl; a.P = P; a.P1 = P1;
@@ -262,6 +264,7 @@ extern "C" int jitr_b200_elastic_observables(int lmax, int n_angles, long long n
 extern "C" int jitr_b200_eval_potentials(int nbasis, int model, long long n_samples, int n_energies, const double* mesh_x,
                                          const double* etab, const double* params, int n_params, double* central,
                                          double* spin_orbit, double* coulomb, void* stream) {
+    if (n_samples == 0) return JITR_B200_OK;  // empty batch (its tensors have null data pointers)
     if (nbasis < 1 || n_samples < 0 || n_energies < 1 || !mesh_x || !etab || !params || !central || !spin_orbit || !coulomb)
         return set_error(JITR_B200_ERR_BAD_ARG, "eval_potentials: null pointer or bad size");
     const int need = model == JITR_B200_MODEL_KDUQ ? 40 : model == JITR_B200_MODEL_CHUQ ? 22 : model == JITR_B200_MODEL_LOCAL ? 15 : model == JITR_B200_MODEL_WLH ? 46 : 17;

@@ -920,6 +920,7 @@ extern "C" int jitr_b200_solve_batched(int nbasis, int nch, long long batch, con
                                        int sys_stride, const double* bvec, const double* asym, long long asym_stride,
                                        const double* weights, double* R, double* S, double* uext, double* coeffs,
                                        double* workspace, int* status, void* stream) {
+    if (batch == 0) return JITR_B200_OK;  // empty batch (its tensors have null data pointers)
     if (nbasis < 1 || nch < 1 || nch > kMaxCh || batch < 0 || !free_matrix || !sys || !bvec || !asym || !weights || !R ||
         !S || !uext || !status)
         return set_error(JITR_B200_ERR_BAD_ARG, "solve_batched: null pointer or bad size (nch <= 16)");

@@ -79,6 +79,7 @@ using namespace jitr;
 extern "C" int jitr_b200_qe_overlap(int nbasis, long long batch, int nj, const double* xp, const double* xn, const double* U1c,
                                     const double* U1so, double lds0, double lds1, double scale, double* out,
                                     long long out_sample_stride, long long out_j_stride, void* stream) {
+    if (batch == 0) return JITR_B200_OK;
     if (nbasis < 1 || batch < 0 || nj < 1 || nj > 2 || !xp || !xn || !U1c || !out)
         return set_error(JITR_B200_ERR_BAD_ARG, "qe_overlap: null pointer or bad size (nj = 1 or 2)");
     if (batch == 0) return JITR_B200_OK;
@@ -95,6 +96,7 @@ extern "C" int jitr_b200_qe_overlap(int nbasis, long long batch, int nj, const d
 
 extern "C" int jitr_b200_qe_xs(int lmax, int n_angles, long long batch, const double* T, const double* G, double factor,
                                double* out, void* stream) {
+    if (batch == 0) return JITR_B200_OK;
     if (lmax < 0 || n_angles < 1 || batch < 0 || !T || !G || !out)
         return set_error(JITR_B200_ERR_BAD_ARG, "qe_xs: null pointer or bad size");
     if (batch == 0) return JITR_B200_OK;

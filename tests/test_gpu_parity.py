@@ -573,3 +573,33 @@ def test_quasielastic_pn_vs_oracle_random_batch(golden):
         assert np.abs(Sp[b].cpu().numpy() - Spo).max() < RTOL_S
         assert relerr(xs[b].cpu().numpy(), ow.xs(*U[b])) < RTOL_XS
     assert len(breaks) > 1
+
+
+# ------------------------------------------------------------------------------------------------
+# edge cases: empty batches, a single partial wave, a single angle, the smallest and largest meshes
+# ------------------------------------------------------------------------------------------------
+def test_edge_cases_empty_and_minimal_shapes():
+    rx = ElasticReaction((40, 20), (1, 0), mass_target=37214.7, mass_projectile=939.5654983938299)
+    kin = rx.kinematics(14.0)
+    model = LocalOpticalPotential()
+    p = np.array([[45.0, 1.25, 0.65, 1.0, 1.25, 0.65, 6.0, 0.0, 1.25, 0.65, 5.5, 0.0, 1.1, 0.65, 1.3]])
+    # empty batch: well-formed empty outputs, no launch error
+    ws = jitr_b200.DifferentialWorkspace.build_from_system(rx, kin, 9.0, jitr_b200.Solver(24), 6, np.linspace(0.3, 2.8, 5))
+    x = ws._as_sweep().xs_params(model, torch.zeros((0, 15), dtype=torch.float64, device="cuda"))
+    assert tuple(x.dsdo.shape) == (0, 1, 5) and tuple(x.rxn.shape)[0] == 0
+    S, nl, st = ws.integral_workspace.smatrix_batch(torch.zeros((0, 24), dtype=torch.complex128, device="cuda"))
+    assert S.shape[0] == 0 and nl.shape[0] == 0
+    r0 = jitr_b200.Solver(24).solve_batch(7.0, 13.6, 0.8, 1, torch.zeros((24, 24), dtype=torch.complex128, device="cuda"),
+                                          torch.ones((4, 1), dtype=torch.complex128, device="cuda"),
+                                          local_potential=torch.zeros((0, 24), dtype=torch.complex128, device="cuda"))
+    assert r0["S"].shape[0] == 0
+    # lmax = 0 (one partial wave, j = 1/2 only), one angle; smallest useful mesh (N = 3) and the largest fused one (N = 64)
+    for N, lmax, nth in [(3, 0, 1), (5, 2, 1), (64, 0, 2), (24, 0, 1)]:
+        ang = np.linspace(0.7, 2.1, nth)
+        w = jitr_b200.DifferentialWorkspace.build_from_system(rx, kin, 9.0, jitr_b200.Solver(N), lmax, ang)
+        xs = w._as_sweep().xs_params(model, torch.tensor(p, device="cuda"))
+        ow = orc.ElasticWorkspace(N, lmax, 9.0, tuple(kin), ang, 0)
+        c, so, co = orc.local_omp_potentials(w.radial_grid(), 40, 0, p[0])
+        dsdo, Ay, Q, tot, rxn = ow.xs(c, so, co)
+        assert relerr(xs.dsdo[0, 0].cpu().numpy(), dsdo) < RTOL_XS, (N, lmax)
+        assert abs(float(xs.t[0, 0]) - tot) <= RTOL_XS * abs(tot), (N, lmax)
