@@ -811,7 +811,7 @@ __global__ void __launch_bounds__(kBlkThreads, 512 / kBlkThreads) block_solve_ke
                 blk_trailing_col0(M, ld, k0 + 8, (PR - k0 - 8) >> 3, reinterpret_cast<const double*>(Lp),
                                   reinterpret_cast<const double*>(Ub), G.ub_ld, Pn, warp, lane, NW);
                 blk_trailing_simple(M, ld, k0 + 8, (PR - k0 - 8) >> 3, wtr >> 3, 1, reinterpret_cast<const double*>(Lp),
-                                    reinterpret_cast<const double*>(Ub), G.ub_ld, warp, lane, NW);
+                             reinterpret_cast<const double*>(Ub), G.ub_ld, warp, lane, NW);
             } else
                 blk_trailing_simple(M, ld, k0 + 8, (PR - k0 - 8) >> 3, wtr >> 3, 0, reinterpret_cast<const double*>(Lp),
                              reinterpret_cast<const double*>(Ub), G.ub_ld, warp, lane, NW);
