@@ -37,6 +37,8 @@ struct GenArgs {
     double2* coeffs;
     double2* workspace;
     int* status;
+    const int* symflag;            // device int: 0 when the shared free matrix is symmetric (NULL: do not try the symmetric path)
+    unsigned long long* fallbacks;  // systems the symmetric path handed to partial pivoting
 };
 
 constexpr int kGenThreads = 256;
@@ -385,6 +387,7 @@ __global__ void __launch_bounds__(256, 1) warp_solve_kernel(const GenArgs A) {
 
 constexpr int kBlkMaxRows = 256;  // one matrix row per thread of the first eight warps
 constexpr int kBlkLpLd = 9;
+constexpr int kBlkHeader = 16;  // complex elements (256 bytes) in front of the slabs
 
 // -DJITR_BLK_PROFILE: per-phase clock accumulators (thread 0 of every CTA), read by jitr_b200_debug_block_phases
 #ifdef JITR_BLK_PROFILE
@@ -416,7 +419,7 @@ __host__ __device__ inline BlkGeom blk_geom(int n, int nch) {
     g.ub_ld = (g.PC - 8) | 1;
     int o = (g.PR - 8) * kBlkLpLd;  // Lp
     g.off_l11 = o; o += 64;
-    g.off_ub = o; o += 8 * g.ub_ld;
+    g.off_ub = o; o += (8 * g.ub_ld > (g.PR - 8) * kBlkLpLd) ? 8 * g.ub_ld : (g.PR - 8) * kBlkLpLd;  // U12, or W of the symmetric path
     g.off_pn = o; o += g.PR * kBlkLpLd;  // the next panel: rows by position, 8 columns
     g.off_prow = o; o += 2 * 8 * 8;  // [parity][warp][8]: 1/pivot, columns j+1..7 of the warp's candidate row
     g.off_small = o; o += 3 * nch * nch + nch + 1;  // R, Z+, Z- -> S, u'_ext
@@ -480,6 +483,97 @@ __device__ __forceinline__ void blk_trailing_simple(double2* __restrict__ M, con
         else if (kBlkNQ > 3 && rem == 3) blk_trailing_item<3>(M, ld, R0, tr, tc0, Lpd, Ubd, ub_ld, lane);
         else if (kBlkNQ > 2 && rem == 2) blk_trailing_item<2>(M, ld, R0, tr, tc0, Lpd, Ubd, ub_ld, lane);
         else blk_trailing_item<1>(M, ld, R0, tr, tc0, Lpd, Ubd, ub_ld, lane);
+    }
+}
+
+// ---- symmetric path (complex symmetric A: local couplings with V_ij = V_ji on the kinetic matrix) -----------------
+// A = L D L^T with the pivots on the diagonal, accepted while every multiplier stays below kBlkSymMaxMult (the
+// threshold-pivoting test |a_kk| >= max_i |a_ik| / 64 of the fused sweep, checked on the multipliers themselves).
+// Only the lower triangle of the bordered matrix is touched: half the trailing tiles, no U phase, no row moves --
+// and ONE barrier per panel instead of one per column: warp 0 factorises the 8 x 8 diagonal block (and its own
+// 24 rows below) with shuffles, publishes it, and every other row is forward-substituted against it.
+constexpr double kBlkSymMaxMult = 64.0;
+
+// tile (tr, tc0 .. tc0+NQ-1) -= L[tr] W[tc]^T with the B fragments taken from the rows of W
+template <int NQ>
+__device__ __forceinline__ void blk_sym_item(double2* __restrict__ M, const int ld, const int R0, const int tr, const int tc0,
+                                             const double* __restrict__ Lpd, const double* __restrict__ Wpd, const int lane) {
+    const int fr = lane >> 2, fk = lane & 3;
+    const int rho = (fr >> 1) + 4 * (fr & 1);
+    const int part = fk & 1, pn = fr & 1;
+    const int bflip = (part & (pn ^ 1)) ? 0x80000000 : 0;
+    double2* Crow = M + (size_t)(R0 + 8 * tr + rho) * ld + R0 + 8 * tc0 + fk;
+    double2 c[NQ][2];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+        c[q][0] = Crow[8 * q];
+        c[q][1] = Crow[8 * q + 4];
+    }
+    double a[4];
+#pragma unroll
+    for (int s = 0; s < 4; ++s) a[s] = dneg(Lpd[2 * ((8 * tr + rho) * kBlkLpLd + s + 4 * (fk >> 1)) + part]);
+#pragma unroll
+    for (int s = 0; s < 4; ++s)
+#pragma unroll
+        for (int q = 0; q < NQ; ++q)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const double v = Wpd[2 * ((8 * (tc0 + q) + 4 * h + (fr >> 1)) * kBlkLpLd + s + 4 * (fk >> 1)) + (part ^ pn)];
+                dmma884(c[q][h].x, c[q][h].y, a[s], __hiloint2double(__double2hiint(v) ^ bflip, __double2loint(v)));
+            }
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+        Crow[8 * q] = c[q][0];
+        Crow[8 * q + 4] = c[q][1];
+    }
+}
+
+// lower-triangle tiles (tc <= tr) of the trailing block; tile column 0 (the next panel) goes to Pn
+__device__ __forceinline__ void blk_sym_trailing(double2* __restrict__ M, const int ld, const int R0, const int ntr,
+                                                 const bool next_panel, const double* __restrict__ Lpd,
+                                                 const double* __restrict__ Wpd, double2* __restrict__ Pn, const int warp,
+                                                 const int lane, const int nwarps) {
+    const int fr = lane >> 2, fk = lane & 3;
+    const int rho = (fr >> 1) + 4 * (fr & 1);
+    const int part = fk & 1, pn = fr & 1;
+    const int bflip = (part & (pn ^ 1)) ? 0x80000000 : 0;
+    const int tcb = next_panel ? 1 : 0;
+    if (next_panel) {
+        double b[2][4];
+#pragma unroll
+        for (int s = 0; s < 4; ++s)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const double v = Wpd[2 * ((4 * h + (fr >> 1)) * kBlkLpLd + s + 4 * (fk >> 1)) + (part ^ pn)];
+                b[h][s] = __hiloint2double(__double2hiint(v) ^ bflip, __double2loint(v));
+            }
+        for (int tr = warp; tr < ntr; tr += nwarps) {
+            const double2* Crow = M + (size_t)(R0 + 8 * tr + rho) * ld + R0 + fk;
+            double2 c0 = Crow[0], c1 = Crow[4];
+            double a[4];
+#pragma unroll
+            for (int s = 0; s < 4; ++s) a[s] = dneg(Lpd[2 * ((8 * tr + rho) * kBlkLpLd + s + 4 * (fk >> 1)) + part]);
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+                dmma884(c0.x, c0.y, a[s], b[0][s]);
+                dmma884(c1.x, c1.y, a[s], b[1][s]);
+            }
+            double2* dst = Pn + (8 * tr + rho) * kBlkLpLd + fk;
+            dst[0] = c0;
+            dst[4] = c1;
+        }
+    }
+    // items (tile row tr, block of three tile columns starting at tcb + 3 cb) with at least one tile on or below
+    // the diagonal
+    const int ncb = (ntr - tcb + 2) / 3;
+    for (int it = warp; it < ntr * ncb; it += nwarps) {
+        const int tr = it / ncb, cb = it - tr * ncb;
+        const int tc0 = tcb + 3 * cb;
+        const int nq = tr - tc0 + 1;  // tile columns tc0 .. min(tc0 + 2, tr); warp-uniform
+        if (nq <= 0) continue;
+        if (nq >= 3) blk_sym_item<3>(M, ld, R0, tr, tc0, Lpd, Wpd, lane);
+        else if (nq == 2) blk_sym_item<2>(M, ld, R0, tr, tc0, Lpd, Wpd, lane);
+        else blk_sym_item<1>(M, ld, R0, tr, tc0, Lpd, Wpd, lane);
     }
 }
 
@@ -589,7 +683,7 @@ __global__ void __launch_bounds__(kBlkThreads, 512 / kBlkThreads) block_solve_ke
     int* dfrom = si + 56;                // [8]
     int* dto = si + 64;                  // [8]
     int* misc = si + 72;                 // [1] displaced count, [2] flags
-    double2* M = A.workspace + (size_t)blockIdx.x * PR * ld;
+    double2* M = A.workspace + kBlkHeader + (size_t)blockIdx.x * PR * ld;  // slabs follow a small header (symmetry flag)
     const double2 zero2 = make_double2(0.0, 0.0);
 
     BLK_PH_INIT
@@ -598,6 +692,11 @@ __global__ void __launch_bounds__(kBlkThreads, 512 / kBlkThreads) block_solve_ke
         const double a = sy[0], E0 = sy[1], k0s = sy[2];
         const double2* F = A.free_matrix + (size_t)sysi * A.free_stride;
         const double nl_scale = (a / k0s) / k0s / E0;  // kernel.py:202 (x radius), rmatrix.py:175-178 (/k0, /E0)
+        // complex symmetric systems (local couplings on the symmetric free matrix, no coefficients wanted) are tried
+        // with diagonal pivots first; a multiplier beyond the threshold sends the system to partial pivoting
+        bool try_sym = A.symflag != nullptr && *A.symflag == 0;
+#pragma unroll 1
+        for (int attempt = 0; attempt < 2; ++attempt) {
         // ---------------- assemble the bordered matrix into the slab
         for (int r = warp; r < PR; r += NW) {
             const int ci = r / N, nn = r - ci * N;
@@ -661,7 +760,7 @@ __global__ void __launch_bounds__(kBlkThreads, 512 / kBlkThreads) block_solve_ke
                 }
             }
         }
-        if (tid == 0) misc[2] = 0;
+        if (tid == 0) misc[2] = misc[3] = misc[4] = 0;
         if (!A.interaction && A.local) {
             // local (coupling) potentials sit on the diagonals of the channel blocks
             __syncthreads();
@@ -669,6 +768,10 @@ __global__ void __launch_bounds__(kBlkThreads, 512 / kBlkThreads) block_solve_ke
                 const int cij = t / N, nn = t - cij * N;
                 const int ci = cij / nch, cj = cij - ci * nch;
                 const double2 w = A.local[((size_t)sysi * nch * nch + cij) * N + nn];
+                if (try_sym && ci != cj) {
+                    const double2 wt = A.local[(((size_t)sysi * nch + cj) * nch + ci) * N + nn];
+                    if (wt.x != w.x || wt.y != w.y) misc[3] = 1;  // V_ij != V_ji: not a symmetric system
+                }
                 double2* e = M + (size_t)(ci * N + nn) * ld + cj * N + nn;
                 double2 v = *e;
                 v.x += w.x / E0; v.y += w.y / E0;
@@ -678,6 +781,82 @@ __global__ void __launch_bounds__(kBlkThreads, 512 / kBlkThreads) block_solve_ke
         }
         __syncthreads();
         BLK_PH(0)
+        if (try_sym && misc[3] == 0) {
+            // ---------------- symmetric elimination, one barrier per panel
+            double2* Wp = Ub;  // [(PR - 8)][9] unscaled multipliers (= D L^T transposed), rows by position
+#pragma unroll 1
+            for (int k0 = 0; k0 < P; k0 += 8) {
+                const int m = PR - k0;
+                const bool have = tid < m;
+                const int nw = (m + 31) >> 5;
+                if (warp < nw) {
+                    double2 p[8], w[8];
+                    {
+                        const double2* rowp = Pn + (have ? tid : 0) * kBlkLpLd;
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) p[c] = w[c] = rowp[c];
+                    }
+                    bool bad = false;
+                    // the growth bound applies to the rows of A; the border rows only have to stay finite
+                    const double lim = (k0 + tid < P) ? kBlkSymMaxMult : 1.0e300;
+                    if (warp == 0) {
+                        // the 8 x 8 diagonal block lives in lanes 0..7; the other 24 rows of this warp ride along
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const double2 rinv = crecip_fast(shfl2(p[j], j));
+                            double2 rowj[8];
+#pragma unroll
+                            for (int c = j + 1; c < 8; ++c) rowj[c] = shfl2(p[c], j);
+                            if (lane == 0) slot[j] = rinv;
+                            if (lane > j) {
+                                w[j] = p[j];
+                                const double2 l = cmul(p[j], rinv);
+                                p[j] = l;
+                                bad |= !(fabs(l.x) <= lim && fabs(l.y) <= lim);
+#pragma unroll
+                                for (int c = j + 1; c < 8; ++c) cfnma(p[c], l, rowj[c]);
+                            }
+                        }
+                        if (lane < 8) {
+#pragma unroll
+                            for (int c = 0; c < 8; ++c) L11[lane * 8 + c] = p[c];  // row j: d_j at c = j, d_j l_cj right of it
+                        }
+                    }
+                    asm volatile("bar.sync 1, %0;" ::"r"(nw * 32) : "memory");
+                    if (warp > 0 && have) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            w[j] = p[j];
+                            const double2 l = cmul(p[j], slot[j]);
+                            p[j] = l;
+                            bad |= !(fabs(l.x) <= lim && fabs(l.y) <= lim);
+#pragma unroll
+                            for (int c = j + 1; c < 8; ++c) cfnma(p[c], l, L11[j * 8 + c]);
+                        }
+                    }
+                    if (have && tid >= 8) {
+                        double2* lp = Lp + (tid - 8) * kBlkLpLd;
+                        double2* wp = Wp + (tid - 8) * kBlkLpLd;
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                            lp[c] = p[c];
+                            wp[c] = w[c];
+                        }
+                    }
+                    if (have && bad) misc[4] = 1;
+                }
+                __syncthreads();
+                if (misc[4]) break;  // CTA-uniform: a multiplier beyond the threshold (or not finite)
+                blk_sym_trailing(M, ld, k0 + 8, (PR - k0 - 8) >> 3, k0 + 8 < P, reinterpret_cast<const double*>(Lp),
+                                 reinterpret_cast<const double*>(Wp), Pn, warp, lane, NW);
+                __syncthreads();
+            }
+            if (misc[4] == 0) break;  // solved
+            if (tid == 0 && A.fallbacks) atomicAdd(A.fallbacks, 1ULL);
+            try_sym = false;
+            __syncthreads();
+            continue;  // assemble again, partial pivoting
+        }
         // ---------------- blocked elimination with look-ahead: while the warps that hold the rows of panel k0
         // factorise it, the other warps finish the trailing update of panel k0 - 8
 #pragma unroll 1
@@ -819,6 +998,8 @@ __global__ void __launch_bounds__(kBlkThreads, 512 / kBlkThreads) block_solve_ke
             __syncthreads();
             BLK_PH(5)
         }
+        break;
+        }  // attempt
         // ---------------- R = -corner / a^2
         for (int ij = tid; ij < nch * nch; ij += kBlkThreads) {
             const int i = ij / nch, j = ij - i * nch;
@@ -831,6 +1012,16 @@ __global__ void __launch_bounds__(kBlkThreads, 512 / kBlkThreads) block_solve_ke
         __syncthreads();
         BLK_PH(6)
     }
+}
+
+// 0 -> *flag stays 0 when the n x n matrix F equals its transpose bit for bit
+__global__ void symcheck_kernel(const double2* __restrict__ F, int n, int* __restrict__ flag) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n * n) return;
+    const int i = idx / n, j = idx - i * n;
+    if (j >= i) return;
+    const double2 x = F[idx], y = F[(size_t)j * n + i];
+    if (x.x != y.x || x.y != y.y) atomicOr(flag, 1);
 }
 
 static int blk_threads(const BlkGeom& g) { return g.PR <= 128 ? 128 : 256; }
@@ -857,8 +1048,21 @@ static int launch_block_solve_t(const GenArgs& a, const BlkGeom& g, cudaStream_t
     return JITR_B200_OK;
 }
 
-static int launch_block_solve(const GenArgs& a, cudaStream_t st) {
+static int launch_block_solve(const GenArgs& a_in, cudaStream_t st) {
+    GenArgs a = a_in;
     const BlkGeom g = blk_geom(a.n, a.nch);
+    // symmetric path: local couplings only, one free matrix for the whole batch, no coefficients
+    a.symflag = nullptr;
+    a.fallbacks = nullptr;
+    if (option(JITR_B200_OPT_SYMMETRIC) && a.local && !a.nonlocal_ && !a.interaction && !a.coeffs && a.free_stride == 0) {
+        int* flag = reinterpret_cast<int*>(a.workspace);
+        if (cudaMemsetAsync(flag, 0, sizeof(int), st) != cudaSuccess) return set_cuda_error("block_solve symmetry flag");
+        const int nn = a.n * a.n;
+        symcheck_kernel<<<(nn + 255) / 256, 256, 0, st>>>(a.free_matrix, a.n, flag);
+        count_launch();
+        a.symflag = flag;
+        a.fallbacks = fallback_counter();
+    }
     return blk_threads(g) == 128 ? launch_block_solve_t<128>(a, g, st) : launch_block_solve_t<256>(a, g, st);
 }
 
@@ -908,7 +1112,7 @@ extern "C" long long jitr_b200_solve_workspace_bytes(int nbasis, int nch, long l
         if (sms <= 0) sms = 148;
         long long ctas = (long long)sms * blk_ctas_per_sm(g);
         if (ctas > batch) ctas = batch;
-        return ctas * g.PR * g.PC * 16;
+        return (ctas * g.PR * g.PC + kBlkHeader) * 16;
     }
     const long long in_smem = (n * (n + nch) + 2 * n + nch) * 16 + 20000;
     return in_smem > 232448 ? batch * n * (n + nch) * 16 : 0;

@@ -603,3 +603,79 @@ def test_edge_cases_empty_and_minimal_shapes():
         dsdo, Ay, Q, tot, rxn = ow.xs(c, so, co)
         assert relerr(xs.dsdo[0, 0].cpu().numpy(), dsdo) < RTOL_XS, (N, lmax)
         assert abs(float(xs.t[0, 0]) - tot) <= RTOL_XS * abs(tot), (N, lmax)
+
+
+# ------------------------------------------------------------------------------------------------
+# blocked CTA-per-system kernel: symmetric (diagonal-pivot) path, its fall-back, asymmetric couplings
+# ------------------------------------------------------------------------------------------------
+def _coupled_case(rng, B, N, nch, W, symmetric=True):
+    solver = jitr_b200.Solver(N)
+    a, E0, k0 = 6 * np.pi, 4.9, 0.48
+    E = [4.9, 2.6, 1.8][:nch]
+    l = [0, 2, 2][:nch]
+    free = solver.free_matrix(a, l, E, [919.0] * nch)
+    r = solver.radial_grid(a, k0)
+    V = np.zeros((B, nch, nch, N), dtype=np.complex128)
+    ws = -(42.0 + 1j * W) / (1 + np.exp((r - 4.0) / 0.8))
+    for i in range(nch):
+        V[:, i, i] = ws[None] * (1 + 0.05 * rng.standard_normal((B, 1)))
+        for j in range(i + 1, nch):
+            c = 5.0 * np.exp(-((r - 4.0) / 1.2) ** 2)
+            V[:, i, j] = c[None] * (1 + 0.05 * rng.standard_normal((B, 1)))
+            V[:, j, i] = V[:, i, j] if symmetric else 0.7 * V[:, i, j]
+    asym = np.array([orc.coulomb_hankel(li, 0.0, a) for li in l]).T  # (4, nch)
+    return solver, a, E0, k0, l, E, free, V, asym
+
+
+def _oracle_coupled(N, a, l, E, V, asym, k0):
+    """A = F + V / E0 and the reference's solve (rmatrix/core.py) for one coupled set."""
+    nch = len(l)
+    F = orc.free_matrix(N, a, l, E, [919.0] * nch)
+    Vm = orc.interaction_matrix(N, k0, E[0], a, nch, local_potential=V)
+    w = np.zeros(nch)
+    w[0] = 1
+    R, S, _, _ = orc.solve_smatrix(F + Vm, orc.boundary_vector(N), *[np.ascontiguousarray(asym[i]) for i in range(4)], w, a, nch, N)
+    return R, S
+
+
+@pytest.mark.parametrize("N,nch", [(20, 2), (50, 3)])
+def test_blocked_solver_symmetric_path_and_fallback(N, nch):
+    lib = _cabi.lib()
+    rng = np.random.default_rng(11)
+    B = 64
+    try:
+        for W, expect_fallbacks in [(4.0, False), (0.0, None)]:
+            solver, a, E0, k0, l, E, free, V, asym = _coupled_case(rng, B, N, nch, W)
+            Ft, Vt, At = torch.tensor(free, device="cuda"), torch.tensor(V, device="cuda"), torch.tensor(asym, device="cuda")
+            lib.jitr_b200_set_option(_cabi.OPT_SYMMETRIC, 1)
+            f0 = lib.jitr_b200_sym_fallback_count()
+            rs = solver.solve_batch(a, E0, k0, nch, Ft, At, local_potential=Vt)
+            torch.cuda.synchronize()
+            nfb = lib.jitr_b200_sym_fallback_count() - f0
+            lib.jitr_b200_set_option(_cabi.OPT_SYMMETRIC, 0)
+            rp = solver.solve_batch(a, E0, k0, nch, Ft, At, local_potential=Vt)
+            torch.cuda.synchronize()
+            assert lib.jitr_b200_sym_fallback_count() - f0 == nfb  # partial pivoting only: no attempts
+            assert int(rs["status"].abs().sum()) == 0 and int(rp["status"].abs().sum()) == 0
+            assert float((rs["S"] - rp["S"]).abs().max()) < RTOL_S
+            if expect_fallbacks is False:
+                assert nfb == 0  # an absorptive potential keeps the diagonal pivots away from zero
+            for b in (0, B - 1):
+                R, S = _oracle_coupled(N, a, l, E, V[b], asym, k0)
+                assert np.abs(rs["S"][b].cpu().numpy() - S).max() < RTOL_S
+                assert normerr(rs["R"][b].cpu().numpy(), R) < 1e-9
+    finally:
+        lib.jitr_b200_set_option(_cabi.OPT_SYMMETRIC, 1)
+
+
+def test_blocked_solver_asymmetric_couplings_take_partial_pivoting():
+    """V_ij != V_ji: the in-kernel symmetry check must route the system to the partial-pivoting path."""
+    rng = np.random.default_rng(12)
+    N, nch, B = 20, 2, 8
+    solver, a, E0, k0, l, E, free, V, asym = _coupled_case(rng, B, N, nch, 3.0, symmetric=False)
+    r = solver.solve_batch(a, E0, k0, nch, torch.tensor(free, device="cuda"), torch.tensor(asym, device="cuda"),
+                           local_potential=torch.tensor(V, device="cuda"))
+    assert int(r["status"].abs().sum()) == 0
+    for b in range(B):
+        R, S = _oracle_coupled(N, a, l, E, V[b], asym, k0)
+        assert np.abs(r["S"][b].cpu().numpy() - S).max() < RTOL_S
