@@ -692,7 +692,7 @@ __global__ void __launch_bounds__(kBlkThreads, 512 / kBlkThreads) block_solve_ke
         const double a = sy[0], E0 = sy[1], k0s = sy[2];
         const double2* F = A.free_matrix + (size_t)sysi * A.free_stride;
         const double nl_scale = (a / k0s) / k0s / E0;  // kernel.py:202 (x radius), rmatrix.py:175-178 (/k0, /E0)
-        // complex symmetric systems (local couplings on the symmetric free matrix, no coefficients wanted) are tried
+        // complex symmetric systems (local couplings on the symmetric free matrix) are tried
         // with diagonal pivots first; a multiplier beyond the threshold sends the system to partial pivoting
         bool try_sym = A.symflag != nullptr && *A.symflag == 0;
 #pragma unroll 1
@@ -844,6 +844,18 @@ __global__ void __launch_bounds__(kBlkThreads, 512 / kBlkThreads) block_solve_ke
                         }
                     }
                     if (have && bad) misc[4] = 1;
+                    if (A.coeffs && have) {
+                        // U = D L^T for the back substitution of the coefficients: row k0 + c of U holds the unscaled
+                        // multipliers w_c of the rows below (the border rows give Y = L^-1 B in the RHS columns)
+                        if (tid >= 8) {
+#pragma unroll
+                            for (int c = 0; c < 8; ++c) M[(size_t)(k0 + c) * ld + k0 + tid] = w[c];
+                        } else {
+#pragma unroll
+                            for (int c = 0; c < 8; ++c)
+                                if (c >= tid) M[(size_t)(k0 + tid) * ld + k0 + c] = p[c];
+                        }
+                    }
                 }
                 __syncthreads();
                 if (misc[4]) break;  // CTA-uniform: a multiplier beyond the threshold (or not finite)
@@ -1051,10 +1063,10 @@ static int launch_block_solve_t(const GenArgs& a, const BlkGeom& g, cudaStream_t
 static int launch_block_solve(const GenArgs& a_in, cudaStream_t st) {
     GenArgs a = a_in;
     const BlkGeom g = blk_geom(a.n, a.nch);
-    // symmetric path: local couplings only, one free matrix for the whole batch, no coefficients
+    // symmetric path: local couplings only, one free matrix for the whole batch
     a.symflag = nullptr;
     a.fallbacks = nullptr;
-    if (option(JITR_B200_OPT_SYMMETRIC) && a.local && !a.nonlocal_ && !a.interaction && !a.coeffs && a.free_stride == 0) {
+    if (option(JITR_B200_OPT_SYMMETRIC) && a.local && !a.nonlocal_ && !a.interaction && a.free_stride == 0) {
         int* flag = reinterpret_cast<int*>(a.workspace);
         if (cudaMemsetAsync(flag, 0, sizeof(int), st) != cudaSuccess) return set_cuda_error("block_solve symmetry flag");
         const int nn = a.n * a.n;

@@ -652,10 +652,17 @@ def test_blocked_solver_symmetric_path_and_fallback(N, nch):
             rs = solver.solve_batch(a, E0, k0, nch, Ft, At, local_potential=Vt)
             torch.cuda.synchronize()
             nfb = lib.jitr_b200_sym_fallback_count() - f0
+            rsw = solver.solve_batch(a, E0, k0, nch, Ft, At, local_potential=Vt, wavefunction=True)
+            torch.cuda.synchronize()
+            f1 = lib.jitr_b200_sym_fallback_count()
             lib.jitr_b200_set_option(_cabi.OPT_SYMMETRIC, 0)
             rp = solver.solve_batch(a, E0, k0, nch, Ft, At, local_potential=Vt)
+            rpw = solver.solve_batch(a, E0, k0, nch, Ft, At, local_potential=Vt, wavefunction=True)
             torch.cuda.synchronize()
-            assert lib.jitr_b200_sym_fallback_count() - f0 == nfb  # partial pivoting only: no attempts
+            assert lib.jitr_b200_sym_fallback_count() == f1  # partial pivoting only: no attempts
+            # wavefunction coefficients from the LDL^T factors (U = D L^T stored transposed) = those from the LU
+            assert float((rsw["S"] - rp["S"]).abs().max()) < RTOL_S
+            assert normerr(rsw["coeffs"].cpu().numpy(), rpw["coeffs"].cpu().numpy()) < 1e-9
             assert int(rs["status"].abs().sum()) == 0 and int(rp["status"].abs().sum()) == 0
             assert float((rs["S"] - rp["S"]).abs().max()) < RTOL_S
             if expect_fallbacks is False:
