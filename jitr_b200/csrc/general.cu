@@ -682,7 +682,7 @@ __global__ void __launch_bounds__(kBlkThreads, 512 / kBlkThreads) block_solve_ke
     int* src = si + 48;                  // [8] old position of pivot row j
     int* dfrom = si + 56;                // [8]
     int* dto = si + 64;                  // [8]
-    int* misc = si + 72;                 // [1] displaced count, [2] flags
+    int* misc = si + 72;                 // [1] displaced count, [2] flags, [3] couplings not symmetric, [4] symmetric path failed, [5] at panel
     double2* M = A.workspace + kBlkHeader + (size_t)blockIdx.x * PR * ld;  // slabs follow a small header (symmetry flag)
     const double2 zero2 = make_double2(0.0, 0.0);
 
@@ -692,11 +692,11 @@ __global__ void __launch_bounds__(kBlkThreads, 512 / kBlkThreads) block_solve_ke
         const double a = sy[0], E0 = sy[1], k0s = sy[2];
         const double2* F = A.free_matrix + (size_t)sysi * A.free_stride;
         const double nl_scale = (a / k0s) / k0s / E0;  // kernel.py:202 (x radius), rmatrix.py:175-178 (/k0, /E0)
-        // complex symmetric systems (local couplings on the symmetric free matrix) are tried
-        // with diagonal pivots first; a multiplier beyond the threshold sends the system to partial pivoting
-        bool try_sym = A.symflag != nullptr && *A.symflag == 0;
-#pragma unroll 1
-        for (int attempt = 0; attempt < 2; ++attempt) {
+        // complex symmetric systems (local couplings on the symmetric free matrix) are eliminated with diagonal pivots;
+        // from the first panel with a multiplier beyond the threshold on, partial pivoting takes over
+        const bool try_sym = A.symflag != nullptr && *A.symflag == 0;
+        int kstart = 0;     // first panel of the partial-pivoting loop
+        bool solved = false;
         // ---------------- assemble the bordered matrix into the slab
         for (int r = warp; r < PR; r += NW) {
             const int ci = r / N, nn = r - ci * N;
@@ -858,21 +858,40 @@ __global__ void __launch_bounds__(kBlkThreads, 512 / kBlkThreads) block_solve_ke
                     }
                 }
                 __syncthreads();
-                if (misc[4]) break;  // CTA-uniform: a multiplier beyond the threshold (or not finite)
+                if (misc[4]) {  // CTA-uniform: a multiplier beyond the threshold (or not finite)
+                    if (tid == 0) misc[5] = k0;
+                    __syncthreads();
+                    break;
+                }
                 blk_sym_trailing(M, ld, k0 + 8, (PR - k0 - 8) >> 3, k0 + 8 < P, reinterpret_cast<const double*>(Lp),
                                  reinterpret_cast<const double*>(Wp), Pn, warp, lane, NW);
                 __syncthreads();
             }
-            if (misc[4] == 0) break;  // solved
-            if (tid == 0 && A.fallbacks) atomicAdd(A.fallbacks, 1ULL);
-            try_sym = false;
-            __syncthreads();
-            continue;  // assemble again, partial pivoting
+            solved = misc[4] == 0;
+            if (!solved) {
+                // panel kfail failed the test.  Everything eliminated so far stands; the trailing matrix is still
+                // symmetric, so its upper triangle (incl. the right-hand-side columns = the border rows transposed) is
+                // rebuilt from the lower one and from the panel in Pn, and partial pivoting continues from this panel.
+                const int kfail = misc[5];
+                const int R1 = kfail + 8;
+                if (tid == 0 && A.fallbacks) atomicAdd(A.fallbacks, 1ULL);
+                for (int r = R1 + warp; r < PR; r += NW) {
+                    const int cfirst = R1 + ((((r - R1) >> 3) + 1) << 3);  // tiles right of the diagonal tile
+                    for (int c = cfirst + lane; c < PC; c += 32) M[(size_t)r * ld + c] = M[(size_t)c * ld + r];
+                }
+                const int wt = PC - R1;
+                for (int t = tid; t < 8 * wt; t += kBlkThreads) {
+                    const int j = t / wt, c = R1 + (t - j * wt);
+                    M[(size_t)(kfail + j) * ld + c] = Pn[(c - kfail) * kBlkLpLd + j];
+                }
+                kstart = kfail;
+                __syncthreads();
+            }
         }
-        // ---------------- blocked elimination with look-ahead: while the warps that hold the rows of panel k0
-        // factorise it, the other warps finish the trailing update of panel k0 - 8
+        if (!solved) {
+        // ---------------- blocked elimination with partial pivoting
 #pragma unroll 1
-        for (int k0 = 0; k0 < P; k0 += 8) {
+        for (int k0 = kstart; k0 < P; k0 += 8) {
             const int m = PR - k0;
             const bool have = tid < m;
             const int start = k0 + tid;
@@ -1010,8 +1029,7 @@ __global__ void __launch_bounds__(kBlkThreads, 512 / kBlkThreads) block_solve_ke
             __syncthreads();
             BLK_PH(5)
         }
-        break;
-        }  // attempt
+        }  // !solved
         // ---------------- R = -corner / a^2
         for (int ij = tid; ij < nch * nch; ij += kBlkThreads) {
             const int i = ij / nch, j = ij - i * nch;
