@@ -780,6 +780,15 @@ __global__ void __launch_bounds__(kBlkThreads, 512 / kBlkThreads) block_solve_ke
             }
         }
         __syncthreads();
+        if (try_sym && (A.nonlocal_ || A.interaction)) {
+            // user matrices: symmetric only if the assembled block says so (read back from the slab, i.e. from L2)
+            for (int r = warp; r < n; r += NW)
+                for (int c = lane; c < r; c += 32) {
+                    const double2 x = M[(size_t)r * ld + c], y = M[(size_t)c * ld + r];
+                    if (x.x != y.x || x.y != y.y) misc[3] = 1;
+                }
+            __syncthreads();
+        }
         BLK_PH(0)
         if (try_sym && misc[3] == 0) {
             // ---------------- symmetric elimination, one barrier per panel
@@ -1081,10 +1090,10 @@ static int launch_block_solve_t(const GenArgs& a, const BlkGeom& g, cudaStream_t
 static int launch_block_solve(const GenArgs& a_in, cudaStream_t st) {
     GenArgs a = a_in;
     const BlkGeom g = blk_geom(a.n, a.nch);
-    // symmetric path: local couplings only, one free matrix for the whole batch
+    // symmetric path: one free matrix for the whole batch, checked here; the potentials are checked per system in the kernel
     a.symflag = nullptr;
     a.fallbacks = nullptr;
-    if (option(JITR_B200_OPT_SYMMETRIC) && a.local && !a.nonlocal_ && !a.interaction && a.free_stride == 0) {
+    if (option(JITR_B200_OPT_SYMMETRIC) && a.free_stride == 0) {
         int* flag = reinterpret_cast<int*>(a.workspace);
         if (cudaMemsetAsync(flag, 0, sizeof(int), st) != cudaSuccess) return set_cuda_error("block_solve symmetry flag");
         const int nn = a.n * a.n;
