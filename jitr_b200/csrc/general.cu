@@ -528,52 +528,101 @@ __device__ __forceinline__ void blk_sym_item(double2* __restrict__ M, const int 
     }
 }
 
-// lower-triangle tiles (tc <= tr) of the trailing block; tile column 0 (the next panel) goes to Pn
-__device__ __forceinline__ void blk_sym_trailing(double2* __restrict__ M, const int ld, const int R0, const int ntr,
-                                                 const bool next_panel, const double* __restrict__ Lpd,
-                                                 const double* __restrict__ Wpd, double2* __restrict__ Pn, const int warp,
-                                                 const int lane, const int nwarps) {
+// tile column 0 of the symmetric trailing update (= the next panel) for tile rows tr0, tr0 + step, ... -> Pn
+__device__ __forceinline__ void blk_sym_col0(const double2* __restrict__ M, const int ld, const int R0, const int ntr,
+                                             const int tr0, const int step, const double* __restrict__ Lpd,
+                                             const double* __restrict__ Wpd, double2* __restrict__ Pn, const int lane) {
+    if (tr0 >= ntr) return;
     const int fr = lane >> 2, fk = lane & 3;
     const int rho = (fr >> 1) + 4 * (fr & 1);
     const int part = fk & 1, pn = fr & 1;
     const int bflip = (part & (pn ^ 1)) ? 0x80000000 : 0;
-    const int tcb = next_panel ? 1 : 0;
-    if (next_panel) {
-        double b[2][4];
+    double b[2][4];
 #pragma unroll
-        for (int s = 0; s < 4; ++s)
+    for (int s = 0; s < 4; ++s)
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const double v = Wpd[2 * ((4 * h + (fr >> 1)) * kBlkLpLd + s + 4 * (fk >> 1)) + (part ^ pn)];
-                b[h][s] = __hiloint2double(__double2hiint(v) ^ bflip, __double2loint(v));
-            }
-        for (int tr = warp; tr < ntr; tr += nwarps) {
-            const double2* Crow = M + (size_t)(R0 + 8 * tr + rho) * ld + R0 + fk;
-            double2 c0 = Crow[0], c1 = Crow[4];
-            double a[4];
-#pragma unroll
-            for (int s = 0; s < 4; ++s) a[s] = dneg(Lpd[2 * ((8 * tr + rho) * kBlkLpLd + s + 4 * (fk >> 1)) + part]);
-#pragma unroll
-            for (int s = 0; s < 4; ++s) {
-                dmma884(c0.x, c0.y, a[s], b[0][s]);
-                dmma884(c1.x, c1.y, a[s], b[1][s]);
-            }
-            double2* dst = Pn + (8 * tr + rho) * kBlkLpLd + fk;
-            dst[0] = c0;
-            dst[4] = c1;
+        for (int h = 0; h < 2; ++h) {
+            const double v = Wpd[2 * ((4 * h + (fr >> 1)) * kBlkLpLd + s + 4 * (fk >> 1)) + (part ^ pn)];
+            b[h][s] = __hiloint2double(__double2hiint(v) ^ bflip, __double2loint(v));
         }
+    for (int tr = tr0; tr < ntr; tr += step) {
+        const double2* Crow = M + (size_t)(R0 + 8 * tr + rho) * ld + R0 + fk;
+        double2 c0 = Crow[0], c1 = Crow[4];
+        double a[4];
+#pragma unroll
+        for (int s = 0; s < 4; ++s) a[s] = dneg(Lpd[2 * ((8 * tr + rho) * kBlkLpLd + s + 4 * (fk >> 1)) + part]);
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            dmma884(c0.x, c0.y, a[s], b[0][s]);
+            dmma884(c1.x, c1.y, a[s], b[1][s]);
+        }
+        double2* dst = Pn + (8 * tr + rho) * kBlkLpLd + fk;
+        dst[0] = c0;
+        dst[4] = c1;
     }
-    // items (tile row tr, block of three tile columns starting at tcb + 3 cb) with at least one tile on or below
-    // the diagonal
+}
+
+// the remaining lower-triangle tiles (tc <= tr, tc >= tcb): items (tile row, block of three tile columns) handed out
+// through a shared counter, so that a warp that was busy elsewhere (warp 0: the next diagonal block) joins late
+__device__ __forceinline__ void blk_sym_rest(double2* __restrict__ M, const int ld, const int R0, const int ntr, const int tcb,
+                                             const double* __restrict__ Lpd, const double* __restrict__ Wpd,
+                                             int* __restrict__ counter, const int lane) {
     const int ncb = (ntr - tcb + 2) / 3;
-    for (int it = warp; it < ntr * ncb; it += nwarps) {
-        const int tr = it / ncb, cb = it - tr * ncb;
+    const int total = ntr * ncb;
+    while (true) {
+        int it = 0;
+        if (lane == 0) it = atomicAdd(counter, 1);
+        it = __shfl_sync(kFull, it, 0);
+        if (it >= total) break;
+        // large tile rows first: the last items handed out are the short ones
+        const int tr = ntr - 1 - it / ncb, cb = it % ncb;
         const int tc0 = tcb + 3 * cb;
         const int nq = tr - tc0 + 1;  // tile columns tc0 .. min(tc0 + 2, tr); warp-uniform
         if (nq <= 0) continue;
         if (nq >= 3) blk_sym_item<3>(M, ld, R0, tr, tc0, Lpd, Wpd, lane);
         else if (nq == 2) blk_sym_item<2>(M, ld, R0, tr, tc0, Lpd, Wpd, lane);
         else blk_sym_item<1>(M, ld, R0, tr, tc0, Lpd, Wpd, lane);
+    }
+}
+
+// 8 x 8 diagonal block of the panel whose columns are in Pn (rows 0..7), by ONE warp with shuffles: A11 = L11 D11 L11^T.
+// Publishes row j as  [l_j0 .. l_j,j-1, d_j, d_j l_j+1,j .. d_j l_7j]  in L11 and 1 / d_j in slot[j]; flags a multiplier
+// beyond the bound.  With coefficients the rows of U11 = D11 L11^T go to the slab (rows kp.., columns kp..).
+__device__ __forceinline__ void blk_sym_diag(const double2* __restrict__ Pn, double2* __restrict__ L11, double2* __restrict__ slot,
+                                             double2* __restrict__ M, const int ld, const int kp, const bool coeffs,
+                                             int* __restrict__ fail, const int lane) {
+    double2 p[8];
+    {
+        const double2* rowp = Pn + (lane < 8 ? lane : 0) * kBlkLpLd;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) p[c] = rowp[c];
+    }
+    bool bad = false;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const double2 rinv = crecip_fast(shfl2(p[j], j));
+        double2 rowj[8];
+#pragma unroll
+        for (int c = j + 1; c < 8; ++c) rowj[c] = shfl2(p[c], j);
+        if (lane == 0) slot[j] = rinv;
+        if (lane > j && lane < 8) {
+            const double2 l = cmul(p[j], rinv);
+            p[j] = l;
+            bad |= !(fabs(l.x) <= kBlkSymMaxMult && fabs(l.y) <= kBlkSymMaxMult);
+#pragma unroll
+            for (int c = j + 1; c < 8; ++c) cfnma(p[c], l, rowj[c]);
+        }
+        if (lane == j) bad |= !(isfinite(rinv.x) && isfinite(rinv.y));  // zero pivot
+    }
+    if (lane < 8) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) L11[lane * 8 + c] = p[c];
+        if (coeffs) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+                if (c >= lane) M[(size_t)(kp + lane) * ld + kp + c] = p[c];
+        }
+        if (bad) *fail = 1;
     }
 }
 
@@ -682,7 +731,7 @@ __global__ void __launch_bounds__(kBlkThreads, 512 / kBlkThreads) block_solve_ke
     int* src = si + 48;                  // [8] old position of pivot row j
     int* dfrom = si + 56;                // [8]
     int* dto = si + 64;                  // [8]
-    int* misc = si + 72;                 // [1] displaced count, [2] flags, [3] couplings not symmetric, [4] symmetric path failed, [5] at panel
+    int* misc = si + 72;                 // [1] displaced count, [2] flags, [3] couplings not symmetric, [4] symmetric path failed, [5] at panel, [6] trailing item counter
     double2* M = A.workspace + kBlkHeader + (size_t)blockIdx.x * PR * ld;  // slabs follow a small header (symmetry flag)
     const double2 zero2 = make_double2(0.0, 0.0);
 
@@ -697,26 +746,45 @@ __global__ void __launch_bounds__(kBlkThreads, 512 / kBlkThreads) block_solve_ke
         const bool try_sym = A.symflag != nullptr && *A.symflag == 0;
         int kstart = 0;     // first panel of the partial-pivoting loop
         bool solved = false;
+        if (tid == 0) misc[2] = misc[3] = misc[4] = 0;
+        const bool local_only = A.local && !A.nonlocal_ && !A.interaction;
+        if (try_sym && local_only && nch > 1) {
+            // V_ij = V_ji ?  (decides whether the lower triangle alone is assembled)
+            __syncthreads();
+            for (int t = tid; t < nch * nch * N; t += kBlkThreads) {
+                const int cij = t / N, nn = t - cij * N;
+                const int ci = cij / nch, cj = cij - ci * nch;
+                if (ci < cj) {
+                    const double2 w = A.local[((size_t)sysi * nch * nch + cij) * N + nn];
+                    const double2 wt = A.local[(((size_t)sysi * nch + cj) * nch + ci) * N + nn];
+                    if (wt.x != w.x || wt.y != w.y) misc[3] = 1;
+                }
+            }
+        }
+        __syncthreads();
+        // the symmetric path never reads the tiles right of the diagonal tile (a fall-back rebuilds them by symmetry)
+        const bool lower_only = try_sym && local_only && misc[3] == 0;
         // ---------------- assemble the bordered matrix into the slab
         for (int r = warp; r < PR; r += NW) {
             const int ci = r / N, nn = r - ci * N;
             double2* __restrict__ Mr = M + (size_t)r * ld;
             if (r < n) {
+                const int ncopy = lower_only ? min(n, ((r >> 3) + 1) << 3) : n;  // columns of A to assemble in this row
                 const double2* __restrict__ Fr = F + (size_t)r * n;
                 const double2* __restrict__ Ir = A.interaction ? A.interaction + ((size_t)sysi * n + r) * n : nullptr;
                 // four independent 16-byte loads in flight per lane (the free matrix comes from L2)
-                for (int c0 = 0; c0 < n; c0 += 128) {
+                for (int c0 = 0; c0 < ncopy; c0 += 128) {
                     double2 v[4];
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const int c = c0 + 32 * i + lane;
-                        v[i] = c < n ? Fr[c] : zero2;
+                        v[i] = c < ncopy ? Fr[c] : zero2;
                     }
                     if (Ir) {
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
                             const int c = c0 + 32 * i + lane;
-                            if (c < n) {
+                            if (c < ncopy) {
                                 const double2 w = Ir[c];
                                 v[i].x += w.x; v[i].y += w.y;
                             }
@@ -725,7 +793,7 @@ __global__ void __launch_bounds__(kBlkThreads, 512 / kBlkThreads) block_solve_ke
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
                             const int c = c0 + 32 * i + lane;
-                            if (c < n) {
+                            if (c < ncopy) {
                                 const int cj = c / N, mm = c - cj * N;
                                 const double2 w = A.nonlocal_[((((size_t)sysi * nch + ci) * nch + cj) * N + nn) * N + mm];
                                 const double sc = A.wsqrt[nn] * A.wsqrt[mm] * nl_scale;
@@ -736,13 +804,15 @@ __global__ void __launch_bounds__(kBlkThreads, 512 / kBlkThreads) block_solve_ke
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const int c = c0 + 32 * i + lane;
-                        if (c < n) {
+                        if (c < ncopy) {
                             Mr[c] = v[i];
                             if (c < 8) Pn[r * kBlkLpLd + c] = v[i];
                         }
                     }
                 }
-                for (int c = n + lane; c < PC; c += 32) {
+                // padding columns and right-hand sides (lower_only: only up to the end of the diagonal tile)
+                const int cend = lower_only ? min(PC, ((r >> 3) + 1) << 3) : PC;
+                for (int c = n + lane; c < cend; c += 32) {
                     const double2 v = make_double2((c >= P && c - P == ci) ? A.bvec[nn] : 0.0, 0.0);
                     Mr[c] = v;
                     if (c < 8) Pn[r * kBlkLpLd + c] = v;  // only when n < 8
@@ -760,19 +830,16 @@ __global__ void __launch_bounds__(kBlkThreads, 512 / kBlkThreads) block_solve_ke
                 }
             }
         }
-        if (tid == 0) misc[2] = misc[3] = misc[4] = 0;
         if (!A.interaction && A.local) {
             // local (coupling) potentials sit on the diagonals of the channel blocks
             __syncthreads();
             for (int t = tid; t < nch * nch * N; t += kBlkThreads) {
                 const int cij = t / N, nn = t - cij * N;
                 const int ci = cij / nch, cj = cij - ci * nch;
+                const int er = ci * N + nn, ec = cj * N + nn;
+                if (lower_only && ec >= (((er >> 3) + 1) << 3)) continue;  // right of the diagonal tile
                 const double2 w = A.local[((size_t)sysi * nch * nch + cij) * N + nn];
-                if (try_sym && ci != cj) {
-                    const double2 wt = A.local[(((size_t)sysi * nch + cj) * nch + ci) * N + nn];
-                    if (wt.x != w.x || wt.y != w.y) misc[3] = 1;  // V_ij != V_ji: not a symmetric system
-                }
-                double2* e = M + (size_t)(ci * N + nn) * ld + cj * N + nn;
+                double2* e = M + (size_t)er * ld + ec;
                 double2 v = *e;
                 v.x += w.x / E0; v.y += w.y / E0;
                 *e = v;
@@ -791,90 +858,78 @@ __global__ void __launch_bounds__(kBlkThreads, 512 / kBlkThreads) block_solve_ke
         }
         BLK_PH(0)
         if (try_sym && misc[3] == 0) {
-            // ---------------- symmetric elimination, one barrier per panel
+            // ---------------- symmetric elimination: two barriers per panel; the diagonal block of the next panel is
+            // factorised by warp 0 inside the trailing phase of the current one
             double2* Wp = Ub;  // [(PR - 8)][9] unscaled multipliers (= D L^T transposed), rows by position
+            if (warp == 0) blk_sym_diag(Pn, L11, slot, M, ld, 0, A.coeffs != nullptr, &misc[4], lane);
+            __syncthreads();
 #pragma unroll 1
             for (int k0 = 0; k0 < P; k0 += 8) {
                 const int m = PR - k0;
-                const bool have = tid < m;
-                const int nw = (m + 31) >> 5;
-                if (warp < nw) {
+                if (tid >= 8 && tid < m) {
+                    // rows below the diagonal block: forward substitution against the published block
                     double2 p[8], w[8];
                     {
-                        const double2* rowp = Pn + (have ? tid : 0) * kBlkLpLd;
+                        const double2* rowp = Pn + tid * kBlkLpLd;
 #pragma unroll
-                        for (int c = 0; c < 8; ++c) p[c] = w[c] = rowp[c];
+                        for (int c = 0; c < 8; ++c) p[c] = rowp[c];
                     }
-                    bool bad = false;
                     // the growth bound applies to the rows of A; the border rows only have to stay finite
                     const double lim = (k0 + tid < P) ? kBlkSymMaxMult : 1.0e300;
-                    if (warp == 0) {
-                        // the 8 x 8 diagonal block lives in lanes 0..7; the other 24 rows of this warp ride along
+                    bool bad = false;
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const double2 rinv = crecip_fast(shfl2(p[j], j));
-                            double2 rowj[8];
+                    for (int j = 0; j < 8; ++j) {
+                        w[j] = p[j];
+                        const double2 l = cmul(p[j], slot[j]);
+                        p[j] = l;
+                        bad |= !(fabs(l.x) <= lim && fabs(l.y) <= lim);
 #pragma unroll
-                            for (int c = j + 1; c < 8; ++c) rowj[c] = shfl2(p[c], j);
-                            if (lane == 0) slot[j] = rinv;
-                            if (lane > j) {
-                                w[j] = p[j];
-                                const double2 l = cmul(p[j], rinv);
-                                p[j] = l;
-                                bad |= !(fabs(l.x) <= lim && fabs(l.y) <= lim);
-#pragma unroll
-                                for (int c = j + 1; c < 8; ++c) cfnma(p[c], l, rowj[c]);
-                            }
-                        }
-                        if (lane < 8) {
-#pragma unroll
-                            for (int c = 0; c < 8; ++c) L11[lane * 8 + c] = p[c];  // row j: d_j at c = j, d_j l_cj right of it
-                        }
+                        for (int c = j + 1; c < 8; ++c) cfnma(p[c], l, L11[j * 8 + c]);
                     }
-                    asm volatile("bar.sync 1, %0;" ::"r"(nw * 32) : "memory");
-                    if (warp > 0 && have) {
+                    double2* lp = Lp + (tid - 8) * kBlkLpLd;
+                    double2* wp = Wp + (tid - 8) * kBlkLpLd;
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            w[j] = p[j];
-                            const double2 l = cmul(p[j], slot[j]);
-                            p[j] = l;
-                            bad |= !(fabs(l.x) <= lim && fabs(l.y) <= lim);
-#pragma unroll
-                            for (int c = j + 1; c < 8; ++c) cfnma(p[c], l, L11[j * 8 + c]);
-                        }
+                    for (int c = 0; c < 8; ++c) {
+                        lp[c] = p[c];
+                        wp[c] = w[c];
                     }
-                    if (have && tid >= 8) {
-                        double2* lp = Lp + (tid - 8) * kBlkLpLd;
-                        double2* wp = Wp + (tid - 8) * kBlkLpLd;
-#pragma unroll
-                        for (int c = 0; c < 8; ++c) {
-                            lp[c] = p[c];
-                            wp[c] = w[c];
-                        }
-                    }
-                    if (have && bad) misc[4] = 1;
-                    if (A.coeffs && have) {
+                    if (bad) misc[4] = 1;
+                    if (A.coeffs) {
                         // U = D L^T for the back substitution of the coefficients: row k0 + c of U holds the unscaled
                         // multipliers w_c of the rows below (the border rows give Y = L^-1 B in the RHS columns)
-                        if (tid >= 8) {
 #pragma unroll
-                            for (int c = 0; c < 8; ++c) M[(size_t)(k0 + c) * ld + k0 + tid] = w[c];
-                        } else {
-#pragma unroll
-                            for (int c = 0; c < 8; ++c)
-                                if (c >= tid) M[(size_t)(k0 + tid) * ld + k0 + c] = p[c];
-                        }
+                        for (int c = 0; c < 8; ++c) M[(size_t)(k0 + c) * ld + k0 + tid] = w[c];
                     }
                 }
+                if (tid == 0) misc[6] = 0;  // item counter of the trailing phase
+                BLK_PH(10)
                 __syncthreads();
-                if (misc[4]) {  // CTA-uniform: a multiplier beyond the threshold (or not finite)
+                BLK_PH(11)
+                if (misc[4]) {  // CTA-uniform: a multiplier beyond the threshold (or not finite) in panel k0
                     if (tid == 0) misc[5] = k0;
                     __syncthreads();
                     break;
                 }
-                blk_sym_trailing(M, ld, k0 + 8, (PR - k0 - 8) >> 3, k0 + 8 < P, reinterpret_cast<const double*>(Lp),
-                                 reinterpret_cast<const double*>(Wp), Pn, warp, lane, NW);
+                {
+                    const int R0 = k0 + 8, ntr = (PR - k0 - 8) >> 3;
+                    const double* Lpd = reinterpret_cast<const double*>(Lp);
+                    const double* Wpd = reinterpret_cast<const double*>(Wp);
+                    const bool next_panel = R0 < P;
+                    if (next_panel) {
+                        if (warp == 0) {
+                            blk_sym_col0(M, ld, R0, ntr, 0, ntr, Lpd, Wpd, Pn, lane);  // the next diagonal tile first
+                            __syncwarp();
+                            blk_sym_diag(Pn, L11, slot, M, ld, R0, A.coeffs != nullptr, &misc[4], lane);
+                            blk_sym_col0(M, ld, R0, ntr, NW, NW, Lpd, Wpd, Pn, lane);
+                        } else {
+                            blk_sym_col0(M, ld, R0, ntr, warp, NW, Lpd, Wpd, Pn, lane);
+                        }
+                    }
+                    blk_sym_rest(M, ld, R0, ntr, next_panel ? 1 : 0, Lpd, Wpd, &misc[6], lane);
+                }
+                BLK_PH(12)
                 __syncthreads();
+                BLK_PH(13)
             }
             solved = misc[4] == 0;
             if (!solved) {

@@ -74,12 +74,14 @@ def main():
     if hasattr(L, "jitr_b200_debug_block_phases"):
         buf = (ctypes.c_ulonglong * 16)()
         L.jitr_b200_debug_block_phases(buf, 1)
-        solver.solve_batch(a, 4.9, 0.48, nch, free, asym3, local_potential=Vt)
+        Vc = Vt * (1 + 0.1j)  # absorptive: the symmetric path end to end
+        solver.solve_batch(a, 4.9, 0.48, nch, free, asym3, local_potential=Vc)
         torch.cuda.synchronize()
         L.jitr_b200_debug_block_phases(buf, 0)
         tot = float(sum(buf)) or 1.0
         names = ["assemble", "panel", "panel_store", "upper", "trailing", "trailing_barrier", "finish", "-",
-                 "col_update", "col_search_publish", "col_barrier", "col_select", "-", "-", "-", "-"]
+                 "col_update|sym_diag_block", "col_search_publish|sym_wait_diag", "col_barrier|sym_forward_store", "col_select|sym_barrier",
+                 "sym_trailing", "sym_trailing_barrier", "-", "-"]
         out["config5_phase_share"] = {k: round(v / tot, 4) for k, v in zip(names, buf)}
     print(json.dumps(out))
 
