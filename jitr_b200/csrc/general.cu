@@ -408,6 +408,8 @@ struct BlkGeom {
     int P, PR, PC;       // padded order, rows (P + z rows), columns (P + RHS columns); PR == PC
     int ub_ld;           // odd leading dimension of the U12 buffer
     int off_l11, off_ub, off_pn, off_prow, off_small, off_xs, off_int;  // shared-memory offsets in double2 units
+    int smem_elems;
+    int fuse, off_lp2, off_wp2;  // symmetric path: two panels per pass over the trailing tiles (second L / W buffers)
 };
 
 __host__ __device__ inline BlkGeom blk_geom(int n, int nch) {
@@ -425,9 +427,18 @@ __host__ __device__ inline BlkGeom blk_geom(int n, int nch) {
     g.off_small = o; o += 3 * nch * nch + nch + 1;  // R, Z+, Z- -> S, u'_ext
     g.off_xs = o; o += 8 * kMaxCh;
     g.off_int = o; o += 24;  // 96 ints
+    // fused panel pairs: only for the 256-thread kernel (two CTAs per SM must still fit), two more row buffers
+    g.fuse = 0;
+    g.off_lp2 = g.off_wp2 = o;
+    if (g.PR > 128 && (size_t)(o + 2 * (g.PR - 16) * kBlkLpLd) * 16 <= 115000) {
+        g.fuse = 1;
+        g.off_lp2 = o; o += (g.PR - 16) * kBlkLpLd;
+        g.off_wp2 = o; o += (g.PR - 16) * kBlkLpLd;
+    }
+    g.smem_elems = o;
     return g;
 }
-static inline size_t blk_smem_bytes(const BlkGeom& g) { return (size_t)(g.off_int + 24) * 16; }
+static inline size_t blk_smem_bytes(const BlkGeom& g) { return (size_t)g.smem_elems * 16; }
 
 template <int NQ>
 __device__ __forceinline__ void blk_trailing_item(double2* __restrict__ M, const int ld, const int R0, const int tr,
@@ -582,6 +593,150 @@ __device__ __forceinline__ void blk_sym_rest(double2* __restrict__ M, const int 
         if (nq >= 3) blk_sym_item<3>(M, ld, R0, tr, tc0, Lpd, Wpd, lane);
         else if (nq == 2) blk_sym_item<2>(M, ld, R0, tr, tc0, Lpd, Wpd, lane);
         else blk_sym_item<1>(M, ld, R0, tr, tc0, Lpd, Wpd, lane);
+    }
+}
+
+// ---- two panels per pass (A = columns k0.., B = columns k0+8..): C -= L_A W_A^T + L_B W_B^T for the tiles at and below
+// R2 = k0 + 16.  L_A / W_A are indexed from R0 = k0 + 8 (one tile above R2), L_B / W_B from R2.
+template <int NQ>
+__device__ __forceinline__ void blk_sym_item2(double2* __restrict__ M, const int ld, const int R2, const int tr, const int tc0,
+                                              const double* __restrict__ LAd, const double* __restrict__ WAd,
+                                              const double* __restrict__ LBd, const double* __restrict__ WBd, const int lane) {
+    const int fr = lane >> 2, fk = lane & 3;
+    const int rho = (fr >> 1) + 4 * (fr & 1);
+    const int part = fk & 1, pn = fr & 1;
+    const int bflip = (part & (pn ^ 1)) ? 0x80000000 : 0;
+    double2* Crow = M + (size_t)(R2 + 8 * tr + rho) * ld + R2 + 8 * tc0 + fk;
+    double2 c[NQ][2];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+        c[q][0] = Crow[8 * q];
+        c[q][1] = Crow[8 * q + 4];
+    }
+#pragma unroll
+    for (int ab = 0; ab < 2; ++ab) {
+        const double* Ld = ab ? LBd : LAd + 2 * 8 * kBlkLpLd;  // L_A rows start one tile earlier
+        const double* Wd = ab ? WBd : WAd + 2 * 8 * kBlkLpLd;
+        double a[4];
+#pragma unroll
+        for (int s = 0; s < 4; ++s) a[s] = dneg(Ld[2 * ((8 * tr + rho) * kBlkLpLd + s + 4 * (fk >> 1)) + part]);
+#pragma unroll
+        for (int s = 0; s < 4; ++s)
+#pragma unroll
+            for (int q = 0; q < NQ; ++q)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const double v = Wd[2 * ((8 * (tc0 + q) + 4 * h + (fr >> 1)) * kBlkLpLd + s + 4 * (fk >> 1)) + (part ^ pn)];
+                    dmma884(c[q][h].x, c[q][h].y, a[s], __hiloint2double(__double2hiint(v) ^ bflip, __double2loint(v)));
+                }
+    }
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+        Crow[8 * q] = c[q][0];
+        Crow[8 * q + 4] = c[q][1];
+    }
+}
+
+// tile column 0 of the fused update (= the panel after the pair) for tile rows tr0, tr0 + step, ... -> Pn
+__device__ __forceinline__ void blk_sym_col0_2(const double2* __restrict__ M, const int ld, const int R2, const int ntr,
+                                               const int tr0, const int step, const double* __restrict__ LAd,
+                                               const double* __restrict__ WAd, const double* __restrict__ LBd,
+                                               const double* __restrict__ WBd, double2* __restrict__ Pn, const int lane) {
+    if (tr0 >= ntr) return;
+    const int fr = lane >> 2, fk = lane & 3;
+    const int rho = (fr >> 1) + 4 * (fr & 1);
+    const int part = fk & 1, pn = fr & 1;
+    const int bflip = (part & (pn ^ 1)) ? 0x80000000 : 0;
+    double b[2][2][4];
+#pragma unroll
+    for (int ab = 0; ab < 2; ++ab) {
+        const double* Wd = ab ? WBd : WAd + 2 * 8 * kBlkLpLd;
+#pragma unroll
+        for (int s = 0; s < 4; ++s)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const double v = Wd[2 * ((4 * h + (fr >> 1)) * kBlkLpLd + s + 4 * (fk >> 1)) + (part ^ pn)];
+                b[ab][h][s] = __hiloint2double(__double2hiint(v) ^ bflip, __double2loint(v));
+            }
+    }
+    for (int tr = tr0; tr < ntr; tr += step) {
+        const double2* Crow = M + (size_t)(R2 + 8 * tr + rho) * ld + R2 + fk;
+        double2 c0 = Crow[0], c1 = Crow[4];
+#pragma unroll
+        for (int ab = 0; ab < 2; ++ab) {
+            const double* Ld = ab ? LBd : LAd + 2 * 8 * kBlkLpLd;
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+                const double a = dneg(Ld[2 * ((8 * tr + rho) * kBlkLpLd + s + 4 * (fk >> 1)) + part]);
+                dmma884(c0.x, c0.y, a, b[ab][0][s]);
+                dmma884(c1.x, c1.y, a, b[ab][1][s]);
+            }
+        }
+        double2* dst = Pn + (8 * tr + rho) * kBlkLpLd + fk;
+        dst[0] = c0;
+        dst[4] = c1;
+    }
+}
+
+__device__ __forceinline__ void blk_sym_rest2(double2* __restrict__ M, const int ld, const int R2, const int ntr, const int tcb,
+                                              const double* __restrict__ LAd, const double* __restrict__ WAd,
+                                              const double* __restrict__ LBd, const double* __restrict__ WBd,
+                                              int* __restrict__ counter, const int lane) {
+    const int ncb = (ntr - tcb + 2) / 3;
+    const int total = ntr * ncb;
+    while (true) {
+        int it = 0;
+        if (lane == 0) it = atomicAdd(counter, 1);
+        it = __shfl_sync(kFull, it, 0);
+        if (it >= total) break;
+        const int tr = ntr - 1 - it / ncb, cb = it % ncb;
+        const int tc0 = tcb + 3 * cb;
+        const int nq = tr - tc0 + 1;
+        if (nq <= 0) continue;
+        if (nq >= 3) blk_sym_item2<3>(M, ld, R2, tr, tc0, LAd, WAd, LBd, WBd, lane);
+        else if (nq == 2) blk_sym_item2<2>(M, ld, R2, tr, tc0, LAd, WAd, LBd, WBd, lane);
+        else blk_sym_item2<1>(M, ld, R2, tr, tc0, LAd, WAd, LBd, WBd, lane);
+    }
+}
+
+// rows below the diagonal block of the panel at kp (its columns are in Pn, the factorised block in L11 / slot): forward
+// substitution, multipliers -> Lx (scaled) and Wx (unscaled), growth check, U rows for the coefficients
+__device__ __forceinline__ void blk_sym_rows(const double2* __restrict__ Pn, const double2* __restrict__ L11,
+                                             const double2* __restrict__ slot, double2* __restrict__ Lx, double2* __restrict__ Wx,
+                                             double2* __restrict__ M, const int ld, const int kp, const int P, const int PR,
+                                             const bool coeffs, int* __restrict__ fail, const int tid) {
+    if (tid < 8 || tid >= PR - kp) return;
+    double2 p[8], w[8];
+    {
+        const double2* rowp = Pn + tid * kBlkLpLd;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) p[c] = rowp[c];
+    }
+    // the growth bound applies to the rows of A; the border rows only have to stay finite
+    const double lim = (kp + tid < P) ? kBlkSymMaxMult : 1.0e300;
+    bool bad = false;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        w[j] = p[j];
+        const double2 l = cmul(p[j], slot[j]);
+        p[j] = l;
+        bad |= !(fabs(l.x) <= lim && fabs(l.y) <= lim);
+#pragma unroll
+        for (int c = j + 1; c < 8; ++c) cfnma(p[c], l, L11[j * 8 + c]);
+    }
+    double2* lp = Lx + (tid - 8) * kBlkLpLd;
+    double2* wp = Wx + (tid - 8) * kBlkLpLd;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        lp[c] = p[c];
+        wp[c] = w[c];
+    }
+    if (bad) *fail = 1;
+    if (coeffs) {
+        // U = D L^T for the back substitution of the coefficients: row kp + c of U holds the unscaled multipliers w_c
+        // of the rows below (the border rows give Y = L^-1 B in the RHS columns)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) M[(size_t)(kp + c) * ld + kp + tid] = w[c];
     }
 }
 
@@ -859,48 +1014,22 @@ __global__ void __launch_bounds__(kBlkThreads, 512 / kBlkThreads) block_solve_ke
         BLK_PH(0)
         if (try_sym && misc[3] == 0) {
             // ---------------- symmetric elimination: two barriers per panel; the diagonal block of the next panel is
-            // factorised by warp 0 inside the trailing phase of the current one
+            // factorised by warp 0 inside the trailing phase of the current one.  Where the extra row buffers fit
+            // (G.fuse), two panels A, B share one pass over the trailing tiles (half the slab traffic).
             double2* Wp = Ub;  // [(PR - 8)][9] unscaled multipliers (= D L^T transposed), rows by position
-            if (warp == 0) blk_sym_diag(Pn, L11, slot, M, ld, 0, A.coeffs != nullptr, &misc[4], lane);
+            double2* Lp2 = sm + G.off_lp2;
+            double2* Wp2 = sm + G.off_wp2;
+            const double* Lpd = reinterpret_cast<const double*>(Lp);
+            const double* Wpd = reinterpret_cast<const double*>(Wp);
+            const double* Lp2d = reinterpret_cast<const double*>(Lp2);
+            const double* Wp2d = reinterpret_cast<const double*>(Wp2);
+            const bool coeffs = A.coeffs != nullptr;
+            if (warp == 0) blk_sym_diag(Pn, L11, slot, M, ld, 0, coeffs, &misc[4], lane);
             __syncthreads();
+            int k0 = 0;
 #pragma unroll 1
-            for (int k0 = 0; k0 < P; k0 += 8) {
-                const int m = PR - k0;
-                if (tid >= 8 && tid < m) {
-                    // rows below the diagonal block: forward substitution against the published block
-                    double2 p[8], w[8];
-                    {
-                        const double2* rowp = Pn + tid * kBlkLpLd;
-#pragma unroll
-                        for (int c = 0; c < 8; ++c) p[c] = rowp[c];
-                    }
-                    // the growth bound applies to the rows of A; the border rows only have to stay finite
-                    const double lim = (k0 + tid < P) ? kBlkSymMaxMult : 1.0e300;
-                    bool bad = false;
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        w[j] = p[j];
-                        const double2 l = cmul(p[j], slot[j]);
-                        p[j] = l;
-                        bad |= !(fabs(l.x) <= lim && fabs(l.y) <= lim);
-#pragma unroll
-                        for (int c = j + 1; c < 8; ++c) cfnma(p[c], l, L11[j * 8 + c]);
-                    }
-                    double2* lp = Lp + (tid - 8) * kBlkLpLd;
-                    double2* wp = Wp + (tid - 8) * kBlkLpLd;
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) {
-                        lp[c] = p[c];
-                        wp[c] = w[c];
-                    }
-                    if (bad) misc[4] = 1;
-                    if (A.coeffs) {
-                        // U = D L^T for the back substitution of the coefficients: row k0 + c of U holds the unscaled
-                        // multipliers w_c of the rows below (the border rows give Y = L^-1 B in the RHS columns)
-#pragma unroll
-                        for (int c = 0; c < 8; ++c) M[(size_t)(k0 + c) * ld + k0 + tid] = w[c];
-                    }
-                }
+            while (k0 < P) {
+                blk_sym_rows(Pn, L11, slot, Lp, Wp, M, ld, k0, P, PR, coeffs, &misc[4], tid);
                 if (tid == 0) misc[6] = 0;  // item counter of the trailing phase
                 BLK_PH(10)
                 __syncthreads();
@@ -910,26 +1039,65 @@ __global__ void __launch_bounds__(kBlkThreads, 512 / kBlkThreads) block_solve_ke
                     __syncthreads();
                     break;
                 }
-                {
-                    const int R0 = k0 + 8, ntr = (PR - k0 - 8) >> 3;
-                    const double* Lpd = reinterpret_cast<const double*>(Lp);
-                    const double* Wpd = reinterpret_cast<const double*>(Wp);
+                const int R0 = k0 + 8, ntr = (PR - R0) >> 3;
+                const bool pair = G.fuse && R0 + 8 <= P;
+                if (!pair) {
                     const bool next_panel = R0 < P;
                     if (next_panel) {
                         if (warp == 0) {
                             blk_sym_col0(M, ld, R0, ntr, 0, ntr, Lpd, Wpd, Pn, lane);  // the next diagonal tile first
                             __syncwarp();
-                            blk_sym_diag(Pn, L11, slot, M, ld, R0, A.coeffs != nullptr, &misc[4], lane);
+                            blk_sym_diag(Pn, L11, slot, M, ld, R0, coeffs, &misc[4], lane);
                             blk_sym_col0(M, ld, R0, ntr, NW, NW, Lpd, Wpd, Pn, lane);
                         } else {
                             blk_sym_col0(M, ld, R0, ntr, warp, NW, Lpd, Wpd, Pn, lane);
                         }
                     }
                     blk_sym_rest(M, ld, R0, ntr, next_panel ? 1 : 0, Lpd, Wpd, &misc[6], lane);
+                    BLK_PH(12)
+                    __syncthreads();
+                    BLK_PH(13)
+                    k0 += 8;
+                    continue;
+                }
+                // ---- pair: panel B = the columns R0.. ; only they get panel A's update now
+                if (warp == 0) {
+                    blk_sym_col0(M, ld, R0, ntr, 0, ntr, Lpd, Wpd, Pn, lane);
+                    __syncwarp();
+                    blk_sym_diag(Pn, L11, slot, M, ld, R0, coeffs, &misc[4], lane);
+                    blk_sym_col0(M, ld, R0, ntr, NW, NW, Lpd, Wpd, Pn, lane);
+                } else {
+                    blk_sym_col0(M, ld, R0, ntr, warp, NW, Lpd, Wpd, Pn, lane);
+                }
+                __syncthreads();
+                blk_sym_rows(Pn, L11, slot, Lp2, Wp2, M, ld, R0, P, PR, coeffs, &misc[4], tid);
+                __syncthreads();
+                if (misc[4]) {
+                    // panel B failed: complete panel A's update of the slab, then partial pivoting from R0
+                    blk_sym_rest(M, ld, R0, ntr, 1, Lpd, Wpd, &misc[6], lane);
+                    if (tid == 0) misc[5] = R0;
+                    __syncthreads();
+                    break;
+                }
+                {
+                    const int R2 = R0 + 8, ntr2 = ntr - 1;
+                    const bool next_panel = R2 < P;
+                    if (next_panel) {
+                        if (warp == 0) {
+                            blk_sym_col0_2(M, ld, R2, ntr2, 0, ntr2, Lpd, Wpd, Lp2d, Wp2d, Pn, lane);
+                            __syncwarp();
+                            blk_sym_diag(Pn, L11, slot, M, ld, R2, coeffs, &misc[4], lane);
+                            blk_sym_col0_2(M, ld, R2, ntr2, NW, NW, Lpd, Wpd, Lp2d, Wp2d, Pn, lane);
+                        } else {
+                            blk_sym_col0_2(M, ld, R2, ntr2, warp, NW, Lpd, Wpd, Lp2d, Wp2d, Pn, lane);
+                        }
+                    }
+                    blk_sym_rest2(M, ld, R2, ntr2, next_panel ? 1 : 0, Lpd, Wpd, Lp2d, Wp2d, &misc[6], lane);
                 }
                 BLK_PH(12)
                 __syncthreads();
                 BLK_PH(13)
+                k0 += 16;
             }
             solved = misc[4] == 0;
             if (!solved) {
