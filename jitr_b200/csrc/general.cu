@@ -430,6 +430,7 @@ __host__ __device__ inline BlkGeom blk_geom(int n, int nch) {
     // fused panel pairs: only for the 256-thread kernel (two CTAs per SM must still fit), two more row buffers
     g.fuse = 0;
     g.off_lp2 = g.off_wp2 = o;
+    // (measured: a loss for the 128-thread kernel even where four CTAs per SM still fit)
     if (g.PR > 128 && (size_t)(o + 2 * (g.PR - 16) * kBlkLpLd) * 16 <= 115000) {
         g.fuse = 1;
         g.off_lp2 = o; o += (g.PR - 16) * kBlkLpLd;
