@@ -39,6 +39,9 @@ extern "C" {
 #define JITR_B200_MODEL_CHUQ 2   /* 22 global Chapel-Hill numbers */
 #define JITR_B200_MODEL_LOCAL 3  /* 15 LocalOpticalPotential numbers */
 #define JITR_B200_MODEL_WLH 4    /* 46 global Whitehead-Lim-Holt numbers (optical_potentials/wlh.py) */
+#define JITR_B200_MODEL_SHAPE_PAIR 5 /* 18 numbers (17 canonical + Vw, the real depth at the imaginary-volume geometry) PER
+                                        (sample, energy): params is [n_samples][n_energies][n_params]; for models whose
+                                        energy-dependent parameter map is evaluated on the host (optical_potentials/dom.py) */
 
 /* layout of one row of the per-energy table (doubles) */
 #define JITR_B200_ET_A 0        /* dimensionless channel radius a = k * R_ch */

@@ -15,8 +15,8 @@ LIB_PATH = os.environ.get("JITR_B200_LIB") or os.path.join(_HERE, "_lib", "libji
 OK, ERR_BAD_ARG, ERR_UNSUPPORTED, ERR_CUDA = 0, 1, 2, 3
 STATUS_OK, STATUS_NONFINITE, STATUS_SINGULAR = 0, 1, 2
 OPT_SYMMETRIC = 0
-MODEL_SHAPE, MODEL_KDUQ, MODEL_CHUQ, MODEL_LOCAL, MODEL_WLH = 0, 1, 2, 3, 4
-MODEL_NPARAMS = {MODEL_SHAPE: 17, MODEL_KDUQ: 40, MODEL_CHUQ: 22, MODEL_LOCAL: 15, MODEL_WLH: 46}
+MODEL_SHAPE, MODEL_KDUQ, MODEL_CHUQ, MODEL_LOCAL, MODEL_WLH, MODEL_SHAPE_PAIR = 0, 1, 2, 3, 4, 5
+MODEL_NPARAMS = {MODEL_SHAPE: 17, MODEL_KDUQ: 40, MODEL_CHUQ: 22, MODEL_LOCAL: 15, MODEL_WLH: 46, MODEL_SHAPE_PAIR: 18}
 # per-energy table layout (include/jitr_b200.h)
 ET_A, ET_ECM, ET_K, ET_ELAB, ET_RCH, ET_AT, ET_ZT, ET_ZP, ET_AP, ET_RSCALE = range(10)
 ET_A13, ET_AM13, ET_AM23, ET_AM53 = 10, 11, 12, 13

@@ -382,7 +382,8 @@ __global__ void __launch_bounds__(SweepPlan<MODE>::kThreads, 1) elastic_sweep_ke
             double2 vc0, vs0, vc1, vs1;
             if (PARAMS) {
                 const PairPotentials pp =
-                    eval_pair_potentials(A.model, A.params + (size_t)smp * A.n_params, et, x0 * radius, x1 * radius);
+                    eval_pair_potentials(A.model, A.params + (size_t)(A.model == JITR_B200_MODEL_SHAPE_PAIR ? pair : smp) * A.n_params,
+                                         et, x0 * radius, x1 * radius);
                 vc0 = pp.vc0; vs0 = pp.vs0; vc1 = pp.vc1; vs1 = pp.vs1;
             } else {
                 const size_t off = (size_t)pair * N;

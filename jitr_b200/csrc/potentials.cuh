@@ -19,11 +19,13 @@ constexpr double kKappa2 = 0.5000000000000001;  // WAVENUMBER_PION**2 = sqrt(1/2
 constexpr double kMaxArg = 36.841361487904734;  // log(1/1e-16), potential_forms.py:11
 
 // canonical shape vector:
-//  V_c  = -Vv f(Rv,av) - i Wv f(Rw,aw) + 4 ad (Vd + i Wd) f'(Rd,ad)
+//  V_c  = -Vv f(Rv,av) - (Vw + i Wv) f(Rw,aw) + 4 ad (Vd + i Wd) f'(Rd,ad)     (Vw: dispersive correction of the
+//         real depth at the imaginary-volume geometry, dom.py:100-104; 0 for the other models)
 //  V_so = Vso g(Rso,aso) + i Wso g(Rwso,awso)        (Vso, Wso already include 1/kappa^2 or 2)
 //  V_C  = Zz alpha hbarc * (r <= RC ? (3 - (r/RC)^2)/(2 RC) : 1/r)
 struct Shape {
     double Vv, Rv, av, Wv, Rw, aw, Vd, Wd, Rd, ad, Vso, Rso, aso, Wso, Rwso, awso, RC, Zz;
+    double Vw = 0.0;
 };
 
 __device__ __forceinline__ void ws_forms(double r, double R, double a, double& f, double& fp) {
@@ -52,6 +54,7 @@ __device__ __forceinline__ void eval_shape(const Shape& s, double r, double2& vc
     if (s.Rwso == s.Rso && s.awso == s.aso) { fws = fs; fpws = fps; } else ws_forms(r, s.Rwso, s.awso, fws, fpws);
     (void)fd; (void)fs; (void)fws;
     double re = -s.Vv * fv;
+    if (s.Vw != 0.0) re -= s.Vw * fw;  // warp-uniform
     double im = -s.Wv * fw;
     // - (-4 ad) Vd f'  - i (-4 ad) Wd f'   (omp.py:68-73, kduq.py:163-167)
     re -= (-4.0 * s.ad) * s.Vd * fpd;
@@ -204,8 +207,16 @@ __device__ __forceinline__ Shape shape_from_wlh(const double* __restrict__ p, co
     return s;
 }
 
+// 17 canonical numbers + Vw, one row per (sample, energy): models whose parameter map stays on the host (DOM)
+__device__ __forceinline__ Shape shape_from_canonical_pair(const double* __restrict__ p, const double* __restrict__ et) {
+    Shape s = shape_from_canonical(p, et);
+    s.Vw = p[17];
+    return s;
+}
+
 __device__ __forceinline__ Shape shape_from_model(int model, const double* __restrict__ p, const double* __restrict__ et) {
     switch (model) {
+        case JITR_B200_MODEL_SHAPE_PAIR: return shape_from_canonical_pair(p, et);
         case JITR_B200_MODEL_KDUQ: return shape_from_kduq(p, et);
         case JITR_B200_MODEL_CHUQ: return shape_from_chuq(p, et);
         case JITR_B200_MODEL_LOCAL: return shape_from_local(p, et);

@@ -42,7 +42,7 @@ class Reaction:
     explicitly, the Q value follows from them unless given."""
 
     def __init__(self, target, projectile, product=None, residual=None, process=None, mass_target=None,
-                 mass_projectile=None, mass_product=None, mass_residual=None, Q=None):
+                 mass_projectile=None, mass_product=None, mass_residual=None, Q=None, Ef=None):
         self.target = _particle(target, mass_target)
         self.projectile = _particle(projectile, mass_projectile)
         self.product = None if product is None else _particle(product, mass_product)
@@ -51,6 +51,7 @@ class Reaction:
         if Q is None and self.product is not None and self.residual is not None:
             Q = self.target.m0 + self.projectile.m0 - self.product.m0 - self.residual.m0
         self.Q = Q
+        self.Ef = Ef  # effective Fermi energy (reactions/reaction.py:528-538), used by the dispersive model only
 
     def kinematics(self, Elab):
         """reactions/reaction.py:540-556."""
@@ -75,5 +76,5 @@ class Reaction:
 class ElasticReaction(Reaction):
     """reactions/reaction.py:715-738."""
 
-    def __init__(self, target, projectile, mass_target=None, mass_projectile=None):
-        super().__init__(target, projectile, process="el", mass_target=mass_target, mass_projectile=mass_projectile)
+    def __init__(self, target, projectile, mass_target=None, mass_projectile=None, Ef=None):
+        super().__init__(target, projectile, process="el", mass_target=mass_target, mass_projectile=mass_projectile, Ef=Ef)

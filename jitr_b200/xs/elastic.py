@@ -329,7 +329,7 @@ class ElasticSweep:
         co = torch.empty((B, self.nE, self.N), dtype=torch.float64, device=self.device)
         rc = _cabi.lib().jitr_b200_eval_potentials(
             self.N, model.model_id, B, self.nE, _cabi.ptr(self.tabs["x"]), _cabi.ptr(self.etab), _cabi.ptr(params),
-            params.shape[1], _cabi.ptr(c), _cabi.ptr(so), _cabi.ptr(co), _cabi.stream_ptr(),
+            params.shape[-1], _cabi.ptr(c), _cabi.ptr(so), _cabi.ptr(co), _cabi.stream_ptr(),
         )
         _cabi.check(rc, "jitr_b200_eval_potentials")
         return c, so, co.to(torch.complex128)
@@ -395,7 +395,11 @@ class ElasticSweep:
         """Built-in potentials: params (B, n_params) CUDA float64 -> S (B, E, 2, lmax+1), nl (B, E), status (B, E)."""
         import torch
 
-        params = model.pack(params, self.device)
+        if hasattr(model, "pair_rows"):
+            # the model maps its parameters to shape numbers per (sample, energy) on the host (DOM): rows (B, E, 18)
+            params = model.pair_rows([(iw.reaction, iw.kinematics) for iw in self.integral], params, self.device)
+        else:
+            params = model.pack(params, self.device)
         if hasattr(model, "radius_factor") and getattr(self, "_rf_model", None) is not model:
             self.set_radius_factor(model)
             self._rf_model = model
@@ -406,7 +410,7 @@ class ElasticSweep:
         S, nl, status = self._alloc_S(B) if out is None else out
         rc = _cabi.lib().jitr_b200_elastic_sweep_params(
             self.N, self.lmax, model.model_id, B, self.nE, _cabi.ptr(self.tabs["That"]), _cabi.ptr(self.tabs["x"]),
-            _cabi.ptr(self.tabs["b"]), _cabi.ptr(self.etab), _cabi.ptr(self.asym), _cabi.ptr(params), params.shape[1],
+            _cabi.ptr(self.tabs["b"]), _cabi.ptr(self.etab), _cabi.ptr(self.asym), _cabi.ptr(params), params.shape[-1],
             float(self.tol), _cabi.ptr(S), _cabi.ptr(nl), _cabi.ptr(status), _cabi.stream_ptr(),
         )
         _cabi.check(rc, "jitr_b200_elastic_sweep_params")

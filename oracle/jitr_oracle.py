@@ -417,6 +417,58 @@ def wlh_potentials(r, projectile, target, Elab, p):
     return central.astype(np.complex128), so.astype(np.complex128), coulomb_charged_sphere(r, zz, RC)
 
 
+def dom_delta_Vs(dE, Ws0, ws1, ws2):
+    """Analytic surface-dispersion correction of the DOM for a scalar energy offset.  optical_potentials/dom.py:399-455."""
+    from scipy.special import exp1, expi
+
+    if dE == 0.0:
+        return 0.0
+    x = float(dE)
+    ax = abs(x)
+    if ws2 == 0.0:
+        J1 = 0.0
+        J2 = np.pi * (ws1**2 + x**2) / (2.0 * np.sqrt(2.0) * ws1**3)
+    else:
+        z1 = ws2 * ax
+        J1 = (-np.exp(-z1) * expi(z1) - np.exp(z1) * exp1(z1)) / (2.0 * ax)
+        roots = ws1 * np.array([np.exp(1j * np.pi / 4), np.exp(1j * 3 * np.pi / 4)])
+        F = np.exp(-ws2 * roots) * exp1(-ws2 * roots)
+        J2 = 2.0 * np.real(np.sum((roots**2 + x**2) / (4.0 * roots**3) * F))
+    pre1 = x**4 / (x**4 + ws1**4)
+    pre2 = ws1**4 / (x**4 + ws1**4)
+    return (2.0 * Ws0 * x / np.pi) * (pre1 * J1 + pre2 * J2)
+
+
+def dom_shape_params(projectile, target, Ecm, Ef, p):
+    """(central 11, spin-orbit 4, coulomb 2) numbers of the dispersive model.  optical_potentials/dom.py:287-382 with
+    the depth functions :151-283."""
+    (v0, v1, rv, av, wv0, wv1, rw, aw, ws0, ws1, ws2, rd, ad, vso0, wso0, wso1, rso, aso, rC) = p
+    A, Z = target
+    Ap, Zp = projectile
+    A13 = A ** (1 / 3)
+    R0, Rw, Rd, Rso, RC = rv * A13, rw * A13, rd * A13, rso * A13, rC * A13
+    Ec = 6.0 * Z * Zp * ALPHA * HBARC / (5 * RC) if Zp == 1 else 0.0
+    dE = Ecm - Ec - Ef
+    V0 = v0 * np.exp(-v1 * dE)
+    Vso = vso0 * np.exp(-v1 * dE)
+    Wv = wv0 * dE**2 / (dE**2 + wv1**2)
+    Ws = ws0 * dE**4 / (dE**4 + ws1**4) * np.exp(-ws2 * np.abs(dE))
+    Wso = wso0 * dE**2 / (dE**2 + wso1**2)
+    dVv = wv0 * wv1 * dE / (dE**2 + wv1**2)
+    dVso = wso0 * wso1 * dE / (dE**2 + wso1**2)
+    dVs = dom_delta_Vs(dE, ws0, ws1, ws2)
+    return (V0, R0, av, Wv, dVv, Rw, aw, Ws, dVs, Rd, ad), (Vso + dVso, Wso, Rso, aso), (float(Z * Zp), RC)
+
+
+def dom_potentials(r, projectile, target, Ecm, Ef, p):
+    """(central, spin_orbit, coulomb) on r.  optical_potentials/dom.py:63-128, 492-529."""
+    (V, R, a, Wv, dVv, Rw, aw, Ws, dVs, Rd, ad), (Vso, Wso, Rso, aso), (zz, RC) = dom_shape_params(projectile, target, Ecm, Ef, p)
+    central = -V * woods_saxon_safe(r, R, a) - (dVv + 1j * Wv) * woods_saxon_safe(r, Rw, aw) \
+        + (4 * ad * (dVs + 1j * Ws)) * woods_saxon_prime_safe(r, Rd, ad)
+    spin_orbit = 2 * (Vso + 1j * Wso) * thomas_safe(r, Rso, aso)
+    return central, spin_orbit, coulomb_charged_sphere(r, zz, RC)
+
+
 def local_omp_potentials(r, A_target, zz, p, A_proj=None):
     """LocalOpticalPotential.  omp.py:54-149 (15 parameters)."""
     Vv, rv, av, Wv, rw, aw, Wd, Vd, rd, ad, Vso, Wso, rso, aso, rC = p

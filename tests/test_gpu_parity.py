@@ -688,3 +688,54 @@ def test_blocked_solver_asymmetric_couplings_take_partial_pivoting():
     for b in range(B):
         R, S = _oracle_coupled(N, a, l, E, V[b], asym, k0)
         assert np.abs(r["S"][b].cpu().numpy() - S).max() < RTOL_S
+
+
+# ------------------------------------------------------------------------------------------------
+# dispersive optical model: host parameter map per (sample, energy) + device forms (MODEL_SHAPE_PAIR)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["dom_n40Ca_14MeV", "dom_p208Pb_30MeV"])
+def test_dom_sweep_vs_reference_golden(golden, name):
+    from jitr_b200.optical_potentials import dom
+
+    g = golden(name)
+    rx = ElasticReaction(tuple(int(v) for v in g["target"]), tuple(int(v) for v in g["projectile"]),
+                         mass_target=float(g["masses"][0]), mass_projectile=float(g["masses"][1]), Ef=float(g["Ef"]))
+    kin = rx.kinematics(float(g["kin"][0]))
+    ws = jitr_b200.DifferentialWorkspace.build_from_system(rx, kin, float(g["Rch"]), jitr_b200.Solver(int(g["N"])), int(g["lmax"]), g["angles"])
+    model = dom.DOM()
+    x, status = ws._as_sweep().xs_params(model, g["params"], return_status=True)
+    S, nl, _ = ws.integral_workspace.smatrix_params(model, g["params"])
+    assert int(status.abs().sum()) == 0
+    for i in range(g["params"].shape[0]):
+        L = int(g["nl"][i])
+        assert int(nl[i]) == L
+        assert relerr(S[i, 0, :L].cpu().numpy(), g["Splus"][i, :L]) < RTOL_S
+        assert relerr(S[i, 1, 1:L].cpu().numpy(), g["Sminus"][i, 1:L]) < RTOL_S
+        assert relerr(x.dsdo[i, 0].cpu().numpy(), g["dsdo"][i]) < RTOL_XS
+        assert abs(float(x.rxn[i, 0]) - g["rxn"][i]) <= RTOL_XS * abs(g["rxn"][i])
+    # the reference's single-sample contract: evaluate(rgrid, reaction, kinematics, *params) -> mesh arrays
+    c, so, co = model(g["rgrid"], rx, kin, *g["params"][2])
+    assert normerr(c, g["central"][2]) < 1e-12 and normerr(so, g["so"][2]) < 1e-12
+    assert np.max(np.abs(co - g["coul"][2])) <= 1e-12 * max(1.0, np.max(np.abs(g["coul"][2])))
+    with pytest.raises(ValueError):
+        model(g["rgrid"], rx, kin, *g["params"][2][:-1])
+
+
+def test_dom_multi_energy_sweep_vs_oracle():
+    """Rows differ per energy: a three-energy sweep of the same samples against the oracle energy by energy."""
+    from jitr_b200.optical_potentials import dom
+
+    g = np.load("tests/golden/dom_n40Ca_14MeV.npz")
+    rx = ElasticReaction((40, 20), (1, 0), mass_target=float(g["masses"][0]), mass_projectile=float(g["masses"][1]), Ef=float(g["Ef"]))
+    ang = np.linspace(0.2, 3.0, 31)
+    solver = jitr_b200.Solver(32)
+    wss = [jitr_b200.DifferentialWorkspace.build_from_system(rx, rx.kinematics(E), 10.5, solver, 16, ang) for E in (6.0, 14.0, 27.0)]
+    sweep = jitr_b200.ElasticSweep(wss)
+    x = sweep.xs_params(dom.DOM(), g["params"][:3])
+    for e, w in enumerate(wss):
+        ow = orc.ElasticWorkspace(32, 16, 10.5, tuple(w.kinematics), ang, 0)
+        for b in range(3):
+            c, so, co = orc.dom_potentials(w.radial_grid(), (1, 0), (40, 20), w.kinematics.Ecm, float(g["Ef"]), g["params"][b])
+            dsdo, Ay, Q, tot, rxn = ow.xs(c, so, co)
+            assert relerr(x.dsdo[b, e].cpu().numpy(), dsdo) < RTOL_XS
+            assert abs(float(x.rxn[b, e]) - rxn) <= RTOL_XS * abs(rxn)

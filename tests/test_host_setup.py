@@ -181,3 +181,27 @@ def test_steed_coulomb_functions_match_mpmath():
         for l in (0, 3, 12):
             ref = np.array(orc.coulomb_hankel(l, eta, s))
             assert np.max(np.abs(tab[l] - ref) / np.abs(ref)) < 2e-13
+
+
+def test_dom_host_parameter_rows(golden):
+    """optical_potentials/dom.py on the host: calculate_params and the vectorised per-(sample, energy) canonical rows the
+    device consumes, against the reference's calculate_params."""
+    from jitr_b200.optical_potentials import dom
+
+    g = golden("dom_params")
+    assert dom.get_param_names() == [str(n) for n in g["names"]]
+    k = 0
+    for case in g["cases"]:
+        prj, tgt, Ecm, Ef = (int(case[0]), int(case[1])), (int(case[2]), int(case[3])), float(case[4]), float(case[5])
+        rows = dom.shape_rows(prj, tgt, np.array([Ecm, Ecm + 1.0]), Ef, g["params"])  # (B, 2, 18)
+        for b, p in enumerate(g["params"]):
+            c, s, co = dom.calculate_params(prj, tgt, Ecm, Ef, *p)
+            ref = g["shapes"][k]
+            got = np.array(list(c) + list(s) + list(co))
+            assert np.max(np.abs(got - ref) / np.maximum(np.abs(ref), 1e-12)) < 1e-12
+            V, R0, av, Wv, dVv, Rw, aw, Ws, dVs, Rd, ad, Vso, Wso, Rso, aso, zz, RC = ref
+            want = np.array([V, R0, av, Wv, Rw, aw, dVs, Ws, Rd, ad, 2 * Vso, Rso, aso, 2 * Wso, Rso, aso, RC, dVv])
+            assert np.max(np.abs(rows[b, 0] - want) / np.maximum(np.abs(want), 1e-12)) < 1e-12
+            k += 1
+    with pytest.raises(ValueError):
+        dom.shape_rows((1, 0), (40, 20), np.array([10.0]), -8.0, np.zeros((2, 5)))

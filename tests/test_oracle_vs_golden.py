@@ -213,3 +213,37 @@ def test_quasielastic_pn_workspace(golden, name):
         assert np.abs(Sn - g["Sn"][b]).max() <= 1e-11
         assert np.abs(Sp - g["Sp"][b]).max() <= 1e-11
         assert np.abs(w.xs(*g["U"][b]) / g["xs"][b] - 1).max() <= 1e-10
+
+
+def test_dom_parameter_map_and_forms(golden):
+    """Dispersive optical model: depth functions, analytic surface dispersion integral (both ws2 branches) and the
+    radial forms against the reference's dom.calculate_params / central / spin_orbit."""
+    g = golden("dom_params")
+    k = 0
+    for case in g["cases"]:
+        prj, tgt, Ecm, Ef = (int(case[0]), int(case[1])), (int(case[2]), int(case[3])), float(case[4]), float(case[5])
+        for p in g["params"]:
+            c, s, co = orc.dom_shape_params(prj, tgt, Ecm, Ef, p)
+            got, ref = np.array(list(c) + list(s) + list(co)), g["shapes"][k]
+            assert np.max(np.abs(got - ref) / np.maximum(np.abs(ref), 1e-12)) < 1e-12
+            k += 1
+    c, so, _ = orc.dom_potentials(g["r"], (1, 1), (48, 20), 44.0, -8.4, g["params"][2])
+    assert np.max(np.abs(c - g["central"])) < 1e-12 * np.max(np.abs(g["central"]))
+    assert np.max(np.abs(so - g["spin_orbit"])) < 1e-12 * np.max(np.abs(g["spin_orbit"]))
+    got = np.array([orc.dom_delta_Vs(x, 15.0, 12.5, w2) for x in (-40.0, -3.0, 0.0, 0.7, 12.5, 80.0) for w2 in (0.0, 0.021)])
+    assert np.allclose(got, g["dVs"], rtol=1e-12, atol=1e-14)
+
+
+@pytest.mark.parametrize("name", ["dom_n40Ca_14MeV", "dom_p208Pb_30MeV"])
+def test_dom_elastic_workspace(golden, name):
+    g = golden(name)
+    prj, tgt = tuple(int(v) for v in g["projectile"]), tuple(int(v) for v in g["target"])
+    ow = orc.ElasticWorkspace(int(g["N"]), int(g["lmax"]), float(g["Rch"]), tuple(g["kin"]), g["angles"], prj[1] * tgt[1], asym_table=g["asym"])
+    for i in (0, 1, 4):
+        c, so, co = orc.dom_potentials(g["rgrid"], prj, tgt, float(g["kin"][1]), float(g["Ef"]), g["params"][i])
+        assert np.max(np.abs(c - g["central"][i])) < 1e-11 * np.max(np.abs(g["central"][i]))
+        sp, sm = ow.smatrix(c, so, co)
+        assert len(sp) == int(g["nl"][i])
+        assert np.max(np.abs(sp - g["Splus"][i, : len(sp)])) < 1e-10
+        dsdo = ow.xs(c, so, co)[0]
+        assert np.max(np.abs(dsdo / g["dsdo"][i] - 1)) < 1e-9
