@@ -493,9 +493,13 @@ class ElasticSweep:
             b = bufs[i % 2]
             if b["done"] is not None:
                 cur.wait_event(b["done"])  # previous D2H out of this buffer set has finished
-            b["p"][:n].copy_(params_host[s0 : s0 + n], non_blocking=True)
             S, nl, status = (t[:n] for t in b["S"])
-            self.smatrix_params(model, b["p"][:n], out=(S, nl, status))
+            if hasattr(model, "pair_rows"):
+                # parameter map on the host (one row per sample and energy): hand it the host rows
+                self.smatrix_params(model, params_host[s0 : s0 + n], out=(S, nl, status))
+            else:
+                b["p"][:n].copy_(params_host[s0 : s0 + n], non_blocking=True)
+                self.smatrix_params(model, b["p"][:n], out=(S, nl, status))
             dsdo, _, _, tr = b["obs"]
             self.observables(S, nl, want_Ay=False, want_Q=False, out=(dsdo[:n], None, None, tr[:n]))
             nsolve += (2 * nl.to(torch.int64) - 1).sum()
