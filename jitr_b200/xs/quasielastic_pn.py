@@ -83,19 +83,18 @@ class Workspace:
         ke, kx = kinematics_entrance, kinematics_exit
         self.xs_factor = (kx.k / ke.k) * ke.mu * kx.mu / (4 * np.pi**2 * HBARC**4 * (2 * 1.0 / 2 + 1))
         self.sigma_c = np.angle(gamma(1 + self.sys.l + 1j * ke.eta))
+        # G[m, m', l, j', theta] of :198-217.  The reference's Clebsch-Gordan product <l m-m' 1/2 m | j' m'><l 0 1/2 m | j' m>
+        # vanishes unless m = m' (its first factor needs (m - m') + m = m'), and (-1)^(2j'+1) = +1 for half-integer j':
+        # only the spin-diagonal entries are non-zero, each the square of one closed-form coefficient times Y_l0.
         G = np.zeros((2, 2, lmax + 1, 2, self.angles.shape[0]), dtype=np.complex128)
-        for im, m in enumerate([-0.5, 0.5]):
-            for imp, mp in enumerate([-0.5, 0.5]):
-                for l in range(0, lmax + 1):
-                    for ijp, jp in enumerate([l + 1 / 2, l - 1 / 2] if l > 0 else [l + 1 / 2]):
-                        if abs(m - mp) <= l and jp >= 0:
-                            ylm = sph_harm_y(l, int(m - mp), self.angles, 0)
-                            cg0 = _cg_half(l, m - mp, m, jp, mp)
-                            cg1 = _cg_half(l, 0, m, jp, m)
-                            G[im, imp, l, ijp, :] = (
-                                (4 * np.pi) ** (3.0 / 2.0) / (ke.k * kx.k) * np.exp(1j * self.sigma_c[l])
-                                * cg1 * cg0 * np.sqrt(2 * l + 1) * (-1) ** (2 * jp + 1) * ylm
-                            )
+        pref = (4 * np.pi) ** 1.5 / (ke.k * kx.k)
+        for l in range(lmax + 1):
+            yl0 = sph_harm_y(l, 0, self.angles, 0)
+            common = pref * np.exp(1j * self.sigma_c[l]) * np.sqrt(2 * l + 1) * yl0
+            for im, m in enumerate((-0.5, 0.5)):
+                G[im, im, l, 0] = common * _cg_half(l, 0, m, l + 0.5, m) ** 2
+                if l > 0:
+                    G[im, im, l, 1] = common * _cg_half(l, 0, m, l - 0.5, m) ** 2
         self.geometric_factor = G
         self._dev = {}
 
