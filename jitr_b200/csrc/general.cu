@@ -1266,7 +1266,8 @@ __global__ void __launch_bounds__(kBlkThreads, 512 / kBlkThreads) block_solve_ke
         // ---------------- R = -corner / a^2
         for (int ij = tid; ij < nch * nch; ij += kBlkThreads) {
             const int i = ij / nch, j = ij - i * nch;
-            const double2 cv = M[(size_t)(P + i) * ld + P + j];
+            // the symmetric path maintains the lower triangle only (matters when the border spans two tiles, nch > 8)
+            const double2 cv = (solved && i < j) ? M[(size_t)(P + j) * ld + P + i] : M[(size_t)(P + i) * ld + P + j];
             small[ij] = make_double2(-cv.x / (a * a), -cv.y / (a * a));
         }
         __syncthreads();

@@ -739,3 +739,42 @@ def test_dom_multi_energy_sweep_vs_oracle():
             dsdo, Ay, Q, tot, rxn = ow.xs(c, so, co)
             assert relerr(x.dsdo[b, e].cpu().numpy(), dsdo) < RTOL_XS
             assert abs(float(x.rxn[b, e]) - rxn) <= RTOL_XS * abs(rxn)
+
+
+def test_blocked_solver_many_channels_two_border_tiles():
+    """nch = 9 > 8: two tiles of border rows / right-hand sides, on the symmetric path, on partial pivoting, and with
+    coefficients, against the reference algorithm."""
+    lib = _cabi.lib()
+    rng = np.random.default_rng(21)
+    N, nch, B = 6, 9, 5
+    solver = jitr_b200.Solver(N)
+    a, k0 = 9.0, 0.7
+    E = list(12.0 - 0.8 * np.arange(nch))
+    l = [int(v) for v in (np.arange(nch) % 3)]
+    mu = [900.0] * nch
+    free = solver.free_matrix(a, l, E, mu)
+    V = np.zeros((B, nch, nch, N), dtype=np.complex128)
+    for i in range(nch):
+        for j in range(i, nch):
+            v = (rng.standard_normal((B, N)) + 0.4j * rng.standard_normal((B, N))) * (20.0 if i == j else 3.0) - (25.0 + 3j) * (i == j)
+            V[:, i, j] = v
+            V[:, j, i] = v
+    asym = np.array([orc.coulomb_hankel(li, 0.0, a) for li in l]).T
+    Ft, Vt, At = torch.tensor(free, device="cuda"), torch.tensor(V, device="cuda"), torch.tensor(asym, device="cuda")
+    try:
+        for opt in (1, 0):
+            lib.jitr_b200_set_option(_cabi.OPT_SYMMETRIC, opt)
+            r = solver.solve_batch(a, E[0], k0, nch, Ft, At, local_potential=Vt, wavefunction=True)
+            assert int(r["status"].abs().sum()) == 0
+            for b in range(B):
+                Fm = orc.free_matrix(N, a, l, E, mu)
+                Vm = orc.interaction_matrix(N, k0, E[0], a, nch, local_potential=V[b])
+                w = np.zeros(nch)
+                w[0] = 1
+                R, S, Ainv, up = orc.solve_smatrix(Fm + Vm, orc.boundary_vector(N), *[np.ascontiguousarray(asym[i]) for i in range(4)], w, a, nch, N)
+                x = orc.solution_coeffs(Ainv, orc.boundary_vector(N), up, nch, N)
+                assert np.abs(r["S"][b].cpu().numpy() - S).max() < RTOL_S
+                assert normerr(r["R"][b].cpu().numpy(), R) < 1e-9
+                assert normerr(r["coeffs"][b].cpu().numpy(), x) < 1e-9
+    finally:
+        lib.jitr_b200_set_option(_cabi.OPT_SYMMETRIC, 1)
