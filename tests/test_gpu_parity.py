@@ -778,3 +778,55 @@ def test_blocked_solver_many_channels_two_border_tiles():
                 assert normerr(r["coeffs"][b].cpu().numpy(), x) < 1e-9
     finally:
         lib.jitr_b200_set_option(_cabi.OPT_SYMMETRIC, 1)
+
+
+@pytest.mark.parametrize("N,nch,kind", [(3, 2, "local"), (5, 16, "local"), (60, 4, "local"), (7, 3, "nonlocal_sym"), (7, 3, "nonlocal_asym"),
+                                        (9, 2, "interaction"), (6, 3, "per_system_free")])
+def test_blocked_solver_shapes_and_inputs_vs_oracle(N, nch, kind):
+    """Corners of the blocked kernel: fewer rows than one panel, 16 channels, 248 bordered rows, coupled nonlocal
+    kernels (symmetric and not), a ready interaction matrix, one free matrix per system -- all with coefficients."""
+    rng = np.random.default_rng(100 + N + nch)
+    B = 3
+    solver = jitr_b200.Solver(N)
+    a, k0 = 8.0, 0.9
+    E = list(10.0 - 0.45 * np.arange(nch))
+    l = [int(v) for v in (np.arange(nch) % 3)]
+    mu = [930.0] * nch
+    n = N * nch
+    free = solver.free_matrix(a, l, E, mu)
+    asym = np.array([orc.coulomb_hankel(li, 0.0, a) for li in l]).T
+    cplx = lambda *sh: rng.standard_normal(sh) + 0.3j * rng.standard_normal(sh)  # noqa: E731
+    loc = np.zeros((B, nch, nch, N), dtype=np.complex128)
+    for i in range(nch):
+        for j in range(i, nch):
+            v = cplx(B, N) * (8.0 if i == j else 1.5) - (20.0 + 2j) * (i == j)
+            loc[:, i, j] = v
+            loc[:, j, i] = v
+    kw, nl, Fb = {}, None, None
+    if kind.startswith("nonlocal"):
+        nl = cplx(B, nch, nch, N, N) * 3.0
+        if kind == "nonlocal_sym":
+            nl = 0.5 * (nl + nl.transpose(0, 2, 1, 4, 3))
+        kw = dict(local_potential=torch.tensor(loc, device="cuda"), nonlocal_potential=torch.tensor(nl, device="cuda"))
+    elif kind == "interaction":
+        kw = dict(interaction_matrix=torch.tensor(np.stack([orc.interaction_matrix(N, k0, E[0], a, nch, local_potential=loc[b]) for b in range(B)]), device="cuda"))
+    else:
+        kw = dict(local_potential=torch.tensor(loc, device="cuda"))
+    if kind == "per_system_free":
+        Fb = np.stack([free * (1 + 0.01 * b) for b in range(B)])
+    Ft = torch.tensor(free if Fb is None else Fb, device="cuda")
+    r = solver.solve_batch(a, E[0], k0, nch, Ft, torch.tensor(asym, device="cuda"), wavefunction=True, batch=None if kind != "interaction" else B, **kw)
+    assert int(r["status"].abs().sum()) == 0
+    w = np.zeros(nch)
+    w[0] = 1
+    bvec = orc.boundary_vector(N)
+    for b in range(B):
+        Fm = orc.free_matrix(N, a, l, E, mu) if Fb is None else Fb[b]
+        Vm = orc.interaction_matrix(N, k0, E[0], a, nch, local_potential=loc[b], nonlocal_potential=None if nl is None else nl[b])
+        R, S, Ainv, up = orc.solve_smatrix(Fm + Vm, bvec, *[np.ascontiguousarray(asym[i]) for i in range(4)], w, a, nch, N)
+        x = orc.solution_coeffs(Ainv, bvec, up, nch, N)
+        assert np.abs(r["S"][b].cpu().numpy() - S).max() < RTOL_S, (kind, b)
+        assert normerr(r["R"][b].cpu().numpy(), R) < 1e-9
+        assert normerr(r["coeffs"][b].cpu().numpy(), x) < 1e-9
+        assert r["S"].shape == (B, nch, nch) and r["coeffs"].shape == (B, nch, N)
+    assert n == N * nch
