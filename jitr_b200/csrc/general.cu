@@ -1142,7 +1142,9 @@ __global__ void __launch_bounds__(kBlkThreads, 512 / kBlkThreads) block_solve_ke
                 if (tid == 0) misc[1] = 0;
                 if (warp == 0 && lane >= nw && lane < 8) skey[lane] = skey[8 + lane] = -2;
                 // pivot key (high word of |re| + |im|, LAPACK izamax) and speculative reciprocal of column 0
-                int key = cand ? __double2hiint(fabs(p[0].x) + fabs(p[0].y)) : -1;
+                // (sign bit cleared: the canonical FP64 NaN of the GPU is negative and must still win the search, so that a
+                // non-finite column is eliminated like any other and flagged at the end)
+                int key = cand ? (__double2hiint(fabs(p[0].x) + fabs(p[0].y)) & 0x7fffffff) : -1;
                 double2 rinv = crecip_fast(p[0]);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
@@ -1180,7 +1182,7 @@ __global__ void __launch_bounds__(kBlkThreads, 512 / kBlkThreads) block_solve_ke
                         if (j < 7) {
                             // the next column first: its search starts while the other columns are updated
                             cfnma(p[j + 1], l, pr[j + 1]);
-                            nkey = cand ? __double2hiint(fabs(p[j + 1].x) + fabs(p[j + 1].y)) : -1;
+                            nkey = cand ? (__double2hiint(fabs(p[j + 1].x) + fabs(p[j + 1].y)) & 0x7fffffff) : -1;
                             nrinv = crecip_fast(p[j + 1]);
                         }
 #pragma unroll

@@ -99,22 +99,26 @@ __device__ __forceinline__ void panel_eliminate(double2 (&p)[NS][9], int (&pos)[
 #pragma unroll
     for (int kk = 0; kk < 8; ++kk) {
         // pivot search over the candidate rows: max |re| + |im|
+        // (a NaN entry counts as the largest: the column is then eliminated like any other and the system is flagged
+        // non-finite at the end; a lane without candidate rows never wins the search)
         double best = -1.0;
         int bs = 0;
+        bool any = false;
         double2 cbest = p[0][kk];
 #pragma unroll
         for (int s = 0; s < NS; ++s) {
             const double m = fabs(p[s][kk].x) + fabs(p[s][kk].y);
-            if (cand[s] && m > best) {
+            if (cand[s] && !(m <= best)) {
                 best = m;
                 bs = s;
                 cbest = p[s][kk];
+                any = true;
             }
         }
         // speculative reciprocal of this lane's own candidate: runs beside the search instead of
         // after the broadcast (it is the longest dependent chain of the step)
         const double2 myrinv = crecip_fast(cbest);
-        const int key = __double2hiint(best);
+        const int key = any ? (__double2hiint(best) & 0x7fffffff) : -1;  // the GPU's canonical FP64 NaN is negative
         const int kmax = __reduce_max_sync(kFull, key);
         const int pl = __ffs(__ballot_sync(kFull, key == kmax)) - 1;
         if (kmax <= 0) singular = 1;  // pivot is zero/denormal (or there is no finite candidate)

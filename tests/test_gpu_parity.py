@@ -484,6 +484,26 @@ def test_singular_system_reports_status():
     c[1] = -40.0
     S, nl, status = ws.smatrix_batch(c)
     assert int(status[0]) != _cabi.STATUS_OK and int(status[1]) == _cabi.STATUS_OK
+    # neighbours of a non-finite system are untouched, on the symmetric path and on partial pivoting
+    lib = _cabi.lib()
+    big = torch.full((64, 20), -40.0 - 2.0j, dtype=torch.complex128, device="cuda")
+    big *= torch.linspace(0.8, 1.2, 64, device="cuda")[:, None]
+    clean = ws.smatrix_batch(big)[0].clone()
+    dirty_in = big.clone()
+    dirty_in[::5] = float("nan")
+    dirty_in[7, 3] = float("inf")
+    keep = [i for i in range(64) if i % 5 and i != 7]
+    try:
+        for opt in (1, 0):
+            lib.jitr_b200_set_option(_cabi.OPT_SYMMETRIC, opt)
+            ref = ws.smatrix_batch(big)[0]
+            Sd, _, st = ws.smatrix_batch(dirty_in)
+            assert all(int(st[i]) != _cabi.STATUS_OK for i in range(0, 64, 5)) and int(st[7]) != _cabi.STATUS_OK
+            assert all(int(st[i]) == _cabi.STATUS_OK for i in keep)
+            assert float((Sd[keep] - ref[keep]).abs().max()) == 0.0
+    finally:
+        lib.jitr_b200_set_option(_cabi.OPT_SYMMETRIC, 1)
+    assert float((clean - ws.smatrix_batch(big)[0]).abs().max()) == 0.0
     with pytest.raises(np.linalg.LinAlgError):
         ws.smatrix(np.full(20, np.nan, dtype=complex))
 
@@ -830,3 +850,32 @@ def test_blocked_solver_shapes_and_inputs_vs_oracle(N, nch, kind):
         assert normerr(r["coeffs"][b].cpu().numpy(), x) < 1e-9
         assert r["S"].shape == (B, nch, nch) and r["coeffs"].shape == (B, nch, N)
     assert n == N * nch
+
+
+@pytest.mark.parametrize("N,nch", [(30, 1), (56, 1), (50, 3)])
+def test_general_solver_status_codes(N, nch):
+    """Non-finite and singular systems are flagged per system (numba's LinAlgError in the reference), on the
+    warp-per-system kernel (N = 30) and on both CTA sizes of the blocked kernel; their neighbours are unaffected."""
+    rng = np.random.default_rng(5)
+    solver = jitr_b200.Solver(N)
+    a, k0 = 9.0, 0.8
+    E = [9.0, 7.5, 6.0][:nch]
+    l = [0, 1, 2][:nch]
+    free = solver.free_matrix(a, l, E, [930.0] * nch)
+    asym = np.array([orc.coulomb_hankel(li, 0.0, a) for li in l]).T
+    B = 6
+    V = np.zeros((B, nch, nch, N), dtype=np.complex128)
+    for i in range(nch):
+        V[:, i, i] = -(30.0 + 3j) * (1 + 0.1 * rng.standard_normal((B, 1))) / (1 + np.exp((np.linspace(0.3, 11, N) - 4.5) / 0.6))
+    V[1] = np.nan
+    V[4, 0, 0, N // 2] = np.inf
+    Ft = torch.tensor(free, device="cuda")
+    r = solver.solve_batch(a, E[0], k0, nch, Ft, torch.tensor(asym, device="cuda"), local_potential=torch.tensor(V, device="cuda"))
+    st = r["status"].cpu().numpy()
+    assert st[1] != _cabi.STATUS_OK and st[4] != _cabi.STATUS_OK
+    assert all(st[b] == _cabi.STATUS_OK for b in (0, 2, 3, 5))
+    good = solver.solve_batch(a, E[0], k0, nch, Ft, torch.tensor(asym, device="cuda"), local_potential=torch.tensor(V[[0, 2, 3, 5]], device="cuda"))
+    assert float((r["S"][[0, 2, 3, 5]] - good["S"]).abs().max()) == 0.0
+    # exactly singular: a zero matrix (free matrix cancelled by the interaction)
+    zero = solver.solve_batch(a, E[0], k0, nch, Ft, torch.tensor(asym, device="cuda"), interaction_matrix=(-Ft)[None].contiguous(), batch=1)
+    assert int(zero["status"][0]) != _cabi.STATUS_OK
