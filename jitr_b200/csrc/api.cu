@@ -4,6 +4,7 @@
 #include <string.h>
 
 #include <atomic>
+#include <mutex>
 
 #include "common.cuh"
 #include "jitr_b200.h"
@@ -21,42 +22,57 @@ int set_cuda_error(const char* where) {
     snprintf(g_err, sizeof(g_err), "%s: %s", where, cudaGetErrorString(e));
     return JITR_B200_ERR_CUDA;
 }
+// Per-device state (one process may drive several devices from several threads): indexed by the current device.
+constexpr int kMaxDevices = 64;
+static std::mutex g_dev_mutex;
+static int current_device() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return 0;
+    return dev;
+}
 int sm_count() {
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess) return 1;
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (sms <= 0) sms = 1;
+    static std::atomic<int> sms[kMaxDevices];
+    const int dev = current_device();
+    int v = sms[dev].load();
+    if (!v) {
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+        if (v <= 0) v = 1;
+        sms[dev].store(v);
     }
-    return sms;
+    return v;
 }
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 static std::atomic<int> g_options[JITR_B200_OPT_COUNT] = {{1}};
 int option(int key) { return (key >= 0 && key < JITR_B200_OPT_COUNT) ? g_options[key].load() : 0; }
 unsigned long long* fallback_counter() {
-    static unsigned long long* ctr = nullptr;
-    if (!ctr) {
-        if (cudaMalloc(&ctr, sizeof(unsigned long long)) != cudaSuccess) {
+    static unsigned long long* ctr[kMaxDevices] = {nullptr};
+    const int dev = current_device();
+    std::lock_guard<std::mutex> lock(g_dev_mutex);
+    if (!ctr[dev]) {
+        if (cudaMalloc(&ctr[dev], sizeof(unsigned long long)) != cudaSuccess) {
             cudaGetLastError();
-            ctr = nullptr;
+            ctr[dev] = nullptr;
             return nullptr;
         }
-        cudaMemset(ctr, 0, sizeof(unsigned long long));
+        cudaMemset(ctr[dev], 0, sizeof(unsigned long long));
     }
-    return ctr;
+    return ctr[dev];
 }
 unsigned long long* next_work_counter(cudaStream_t st) {
     constexpr int kRing = 256;
-    static unsigned long long* ring = nullptr;
+    static unsigned long long* ring[kMaxDevices] = {nullptr};
     static std::atomic<unsigned> seq{0};
-    if (!ring) {
-        if (cudaMalloc(&ring, kRing * sizeof(unsigned long long)) != cudaSuccess) {
-            ring = nullptr;
-            return nullptr;
+    const int dev = current_device();
+    {
+        std::lock_guard<std::mutex> lock(g_dev_mutex);
+        if (!ring[dev]) {
+            if (cudaMalloc(&ring[dev], kRing * sizeof(unsigned long long)) != cudaSuccess) {
+                ring[dev] = nullptr;
+                return nullptr;
+            }
         }
     }
-    unsigned long long* c = ring + (seq.fetch_add(1) % kRing);
+    unsigned long long* c = ring[dev] + (seq.fetch_add(1) % kRing);
     if (cudaMemsetAsync(c, 0, sizeof(unsigned long long), st) != cudaSuccess) return nullptr;
     return c;
 }

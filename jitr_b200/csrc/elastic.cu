@@ -242,12 +242,8 @@ extern "C" int jitr_b200_elastic_observables(int lmax, int n_angles, long long n
     const int L1 = lmax + 1;
     const size_t smem = (size_t)2 * L1 * n_angles * 8 + (size_t)kObsWarps * 2 * L1 * 16;
     if (smem > 232448) return set_error(JITR_B200_ERR_UNSUPPORTED, "elastic_observables: (lmax+1)*n_angles tables exceed shared memory");
-    static size_t configured = 0;
-    if (smem > configured) {
-        if (cudaFuncSetAttribute(elastic_observables_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-            return set_cuda_error("cudaFuncSetAttribute(observables)");
-        configured = smem;
-    }
+    if (cudaFuncSetAttribute(elastic_observables_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        return set_cuda_error("cudaFuncSetAttribute(observables)");
     // chunk the sample axis so that the grid is a few waves of the SM count
     const int sms = sm_count();
     long long target_blocks_x = (4LL * sms + n_energies - 1) / n_energies;

@@ -485,12 +485,8 @@ int launch_sweep_mode(const SweepArgs& a, cudaStream_t st) {
     if (warps < 1) return set_error(JITR_B200_ERR_UNSUPPORTED, "elastic sweep: system does not fit in shared memory");
     const int smem = Plan::smem(a.N, warps);
     auto kern = elastic_sweep_kernel<PARAMS, MODE>;
-    static int configured = 0;
-    if (smem > configured) {
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
-            return set_cuda_error("cudaFuncSetAttribute(elastic_sweep)");
-        configured = smem;
-    }
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+        return set_cuda_error("cudaFuncSetAttribute(elastic_sweep)");
     const int sms = sm_count();
     long long blocks = (a.n_pairs + warps - 1) / warps;
     if (blocks > sms) blocks = sms;

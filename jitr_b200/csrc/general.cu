@@ -1296,12 +1296,8 @@ static int blk_ctas_per_sm(const BlkGeom& g) { return 512 / blk_threads(g); }
 template <int T>
 static int launch_block_solve_t(const GenArgs& a, const BlkGeom& g, cudaStream_t st) {
     const size_t smem = blk_smem_bytes(g);
-    static size_t conf = 0;
-    if (smem > conf) {
-        if (cudaFuncSetAttribute(block_solve_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-            return set_cuda_error("cudaFuncSetAttribute(block_solve)");
-        conf = smem;
-    }
+    if (cudaFuncSetAttribute(block_solve_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        return set_cuda_error("cudaFuncSetAttribute(block_solve)");
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, block_solve_kernel<T>, T, smem) != cudaSuccess || per_sm < 1)
         return set_cuda_error("block_solve occupancy");
@@ -1339,12 +1335,8 @@ static int launch_warp_solve(const GenArgs& a, cudaStream_t st) {
     if (warps > 8) warps = 8;
     if (warps < 1) return set_error(JITR_B200_ERR_UNSUPPORTED, "warp_solve: system does not fit in shared memory");
     const int smem = warps * msz * 16;
-    static int conf = 0;
-    if (smem > conf) {
-        if (cudaFuncSetAttribute(warp_solve_kernel<MAXNS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
-            return set_cuda_error("cudaFuncSetAttribute(warp_solve)");
-        conf = smem;
-    }
+    if (cudaFuncSetAttribute(warp_solve_kernel<MAXNS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+        return set_cuda_error("cudaFuncSetAttribute(warp_solve)");
     long long blocks = (a.batch + warps - 1) / warps;
     if (blocks > sm_count()) blocks = sm_count();
     warp_solve_kernel<MAXNS><<<(unsigned)blocks, warps * 32, smem, st>>>(a);
@@ -1430,20 +1422,12 @@ extern "C" int jitr_b200_solve_batched(int nbasis, int nch, long long batch, con
     if (per_sm > 8) per_sm = 8;
     long long blocks = batch < (long long)sms * per_sm ? batch : (long long)sms * per_sm;
     if (use_smem) {
-        static size_t conf = 0;
-        if (smem > conf) {
-            if (cudaFuncSetAttribute(general_solve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-                return set_cuda_error("cudaFuncSetAttribute(general_solve<smem>)");
-            conf = smem;
-        }
+        if (cudaFuncSetAttribute(general_solve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return set_cuda_error("cudaFuncSetAttribute(general_solve<smem>)");
         general_solve_kernel<true><<<(unsigned)blocks, kGenThreads, smem, st>>>(a);
     } else {
-        static size_t conf = 0;
-        if (smem > conf) {
-            if (cudaFuncSetAttribute(general_solve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-                return set_cuda_error("cudaFuncSetAttribute(general_solve<global>)");
-            conf = smem;
-        }
+        if (cudaFuncSetAttribute(general_solve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return set_cuda_error("cudaFuncSetAttribute(general_solve<global>)");
         general_solve_kernel<false><<<(unsigned)blocks, kGenThreads, smem, st>>>(a);
     }
     count_launch();

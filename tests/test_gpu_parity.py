@@ -879,3 +879,40 @@ def test_general_solver_status_codes(N, nch):
     # exactly singular: a zero matrix (free matrix cancelled by the interaction)
     zero = solver.solve_batch(a, E[0], k0, nch, Ft, torch.tensor(asym, device="cuda"), interaction_matrix=(-Ft)[None].contiguous(), batch=1)
     assert int(zero["status"][0]) != _cabi.STATUS_OK
+
+
+def test_two_devices_from_two_threads_in_one_process(golden):
+    """The library keeps its state per device (SM count, work counters, fall-back counter, kernel attributes): two
+    threads drive cuda:0 and cuda:1 at once and both reproduce the reference.  Skipped on a single-GPU box."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import threading
+
+    g0 = golden("config1_n208Pb_30MeV")
+    g = {k: g0[k] for k in g0.files}  # NpzFile reads lazily and is not thread-safe
+    out, err = {}, []
+
+    def work(dev):
+        try:
+            with torch.cuda.device(dev):
+                rx, kin, ws = make_ws(g)
+                model = model_for("config1", g)
+                for _ in range(3):
+                    x = ws._as_sweep().xs_params(model, torch.tensor(np.tile(g["params"][:1], (4096, 1)), device=f"cuda:{dev}"))
+                N = int(g["N"])
+                solver = jitr_b200.Solver(N)
+                free = torch.tensor(solver.free_matrix(12.0, [0]), device=f"cuda:{dev}")
+                asym = torch.tensor(np.array(orc.coulomb_hankel(0, 0.0, 12.0)).reshape(4, 1), device=f"cuda:{dev}")
+                V = torch.full((256, 1, 1, N), -30.0 - 2j, dtype=torch.complex128, device=f"cuda:{dev}")
+                r = solver.solve_batch(12.0, 20.0, 1.0, 1, free, asym, local_potential=V, wavefunction=True)
+                torch.cuda.synchronize(dev)
+                out[dev] = (x.dsdo[0, 0].cpu().numpy(), r["S"].cpu().numpy())
+        except Exception as e:  # noqa: BLE001
+            err.append((dev, repr(e)))
+
+    ts = [threading.Thread(target=work, args=(d,)) for d in (0, 1)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not err, err
+    assert relerr(out[0][0], g["dsdo"][0]) < RTOL_XS and relerr(out[1][0], g["dsdo"][0]) < RTOL_XS
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
