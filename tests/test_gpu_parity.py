@@ -916,3 +916,30 @@ def test_two_devices_from_two_threads_in_one_process(golden):
     assert not err, err
     assert relerr(out[0][0], g["dsdo"][0]) < RTOL_XS and relerr(out[1][0], g["dsdo"][0]) < RTOL_XS
     assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
+
+
+def test_large_lmax_proton_and_odd_batch_sizes():
+    """lmax = 100 (the reference's Frescox regression cases go that high) for a charged projectile -- Coulomb-Hankel
+    table up to l = 101, early break far below lmax -- and batch sizes that do not fill the last CTA / warp."""
+    rx = ElasticReaction((58, 28), (1, 1), mass_target=53966.4, mass_projectile=938.271653086152)
+    kin = rx.kinematics(35.0)
+    ang = np.linspace(0.15, 3.0, 11)
+    N, lmax = 48, 100
+    ws = jitr_b200.DifferentialWorkspace.build_from_system(rx, kin, 14.0, jitr_b200.Solver(N), lmax, ang)
+    model = LocalOpticalPotential()
+    base = np.array([50.0, 1.2, 0.7, 3.0, 1.25, 0.6, 6.5, 0.0, 1.25, 0.6, 5.9, -0.2, 1.05, 0.65, 1.25])
+    ow = orc.ElasticWorkspace(N, lmax, 14.0, tuple(kin), ang, 28)
+    r = ws.radial_grid()
+    for B in (1, 13, 385):
+        rng = np.random.default_rng(B)
+        p = np.tile(base, (B, 1)) * (1 + 0.03 * rng.standard_normal((B, base.size)))
+        x, status = ws._as_sweep().xs_params(model, torch.tensor(p, device="cuda"), return_status=True)
+        S, nl, _ = ws.integral_workspace.smatrix_params(model, torch.tensor(p, device="cuda"))
+        assert int(status.abs().sum()) == 0
+        for b in sorted({0, B // 2, B - 1}):
+            c, so, co = orc.local_omp_potentials(r, 58, 28, p[b])
+            sp, sm = ow.smatrix(c, so, co)
+            assert int(nl[b]) == len(sp) and len(sp) < lmax
+            assert relerr(S[b, 0, : len(sp)].cpu().numpy(), sp) < RTOL_S
+            dsdo = ow.xs(c, so, co)[0]
+            assert relerr(x.dsdo[b, 0].cpu().numpy(), dsdo) < RTOL_XS
