@@ -367,14 +367,17 @@ __global__ void __launch_bounds__(256, 1) warp_solve_kernel(const GenArgs A) {
 // whose corner block is left as -B^T A^-1 B = -a^2 R (rmatrix/core.py:15-22 without the inverse).  The matrix
 // (PR x PC complex128, 410 KB for config 5 -- more than one SM's shared memory) lives in a per-CTA slab of
 // the device workspace, i.e. in L2 (148 x 2 slabs = 121 MB of the 126 MB); what is reused stays on chip:
-//   P  the 8-column panel in REGISTERS, one matrix row per thread; pivot search REDUX per warp + one
-//      shared-memory exchange per column (two CTA barriers per column); rows are not moved, each thread
-//      tracks the position of its row;
+//   P  the 8-column panel in REGISTERS, one matrix row per thread; per column every warp publishes its best
+//      candidate row (REDUX search, speculative reciprocal, packed key) and one barrier of the panel warps later
+//      a second REDUX over the eight keys elects the pivot; rows are not moved, each thread tracks the position
+//      of its row;
 //   U  thread c owns trailing column c: gathers the eight pivot rows from their OLD positions, moves the
 //      (at most eight) displaced rows to the positions the pivots left, forward-substitutes with L11 from
 //      shared memory, leaves U12 in shared memory (and in the slab when coefficients are wanted);
 //   T  A22 -= L21 U12 on DMMA m8n8k4 in the real representation of the complex product (fragment mapping of
-//      lu_warp.cuh), L21 and U12 from shared memory, the C tiles streamed slab -> accumulators -> slab.
+//      lu_warp.cuh), L21 and U12 from shared memory, the C tiles streamed slab -> accumulators -> slab; tile
+//      column 0 (the next panel) is produced first and stays in shared memory.
+// Complex symmetric systems take the LDL^T path further down (diagonal pivots, lower triangle only, panel pairs).
 // Wavefunction coefficients (core.py:63-82) add a blocked back substitution on the stored U.
 // ---------------------------------------------------------------------------------------------
 // single-channel systems without coefficients up to this padded order go warp-per-system; beyond it the blocked
@@ -498,12 +501,15 @@ __device__ __forceinline__ void blk_trailing_simple(double2* __restrict__ M, con
     }
 }
 
-// ---- symmetric path (complex symmetric A: local couplings with V_ij = V_ji on the kinetic matrix) -----------------
+// ---- symmetric path (complex symmetric A: couplings with V_ij = V_ji or a symmetric user matrix on the symmetric free
+// matrix) ----------------------------------------------------------------------------------------------------------
 // A = L D L^T with the pivots on the diagonal, accepted while every multiplier stays below kBlkSymMaxMult (the
 // threshold-pivoting test |a_kk| >= max_i |a_ik| / 64 of the fused sweep, checked on the multipliers themselves).
-// Only the lower triangle of the bordered matrix is touched: half the trailing tiles, no U phase, no row moves --
-// and ONE barrier per panel instead of one per column: warp 0 factorises the 8 x 8 diagonal block (and its own
-// 24 rows below) with shuffles, publishes it, and every other row is forward-substituted against it.
+// Only the lower triangle of the bordered matrix is assembled and touched: half the trailing tiles, no U phase, no
+// row moves -- and two barriers per panel instead of one per column: warp 0 factorises the 8 x 8 diagonal block of the
+// NEXT panel with shuffles inside the trailing phase (blk_sym_diag), publishes it, and every other row is
+// forward-substituted against it (blk_sym_rows).  Panel pairs share one pass over the trailing tiles where the extra
+// row buffers fit (BlkGeom::fuse).  A failed test hands the rest of the system to partial pivoting (kernel body).
 constexpr double kBlkSymMaxMult = 64.0;
 
 // tile (tr, tc0 .. tc0+NQ-1) -= L[tr] W[tc]^T with the B fragments taken from the rows of W
@@ -825,8 +831,7 @@ __device__ __noinline__ void blk_coefficients(const GenArgs& A, const long long 
 }
 
 // Tile column 0 of the trailing update = the columns of the NEXT panel: computed first, by all warps, and left
-// in shared memory (Pn, rows by position) so that the panel warps can start on it while the other warps
-// finish the rest of the trailing update (look-ahead).
+// in shared memory (Pn, rows by position): panels never reload from the slab.
 __device__ __forceinline__ void blk_trailing_col0(const double2* __restrict__ M, const int ld, const int R0,
                                                   const int ntr, const double* __restrict__ Lpd,
                                                   const double* __restrict__ Ubd, const int ub_ld,
