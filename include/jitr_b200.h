@@ -164,6 +164,21 @@ int jitr_b200_solve_batched(int nbasis, int nch, long long batch, const double* 
                             double* workspace, int* status, void* stream);
 
 /*
+ * Weighted misfit of the angular distributions against data, reduced on the device (the batched likelihood of a
+ * calibration loop, e.g. the log-likelihood of the reference's quickstart notebook): same inputs as
+ * jitr_b200_elastic_observables, plus
+ *   y, w, scale [n_energies][n_angles]   data, weights (1/sigma^2 for chi^2) and an optional factor applied to
+ *                                         dsigma/dOmega before the comparison (1/Rutherford for ratio data; NULL = 1)
+ *   misfit      [n_samples][n_energies]  sum_theta w (scale * dsdo - y)^2
+ *   dsdo        optional output as in jitr_b200_elastic_observables (NULL: nothing but misfit and tot_rxn leaves
+ *               the kernel -- 24 bytes per (sample, energy) instead of 8 n_angles)
+ */
+int jitr_b200_elastic_misfit(int lmax, int n_angles, long long n_samples, int n_energies, const double* S,
+                             const int* nl, const double* P, const double* P1, const double* phase,
+                             const double* f_c, const double* kvec, const double* y, const double* w,
+                             const double* scale, double* misfit, double* tot_rxn, double* dsdo, void* stream);
+
+/*
  * Quasi-elastic (p,n) DWBA, the steps after the distorted-wave solves (xs/quasielastic_pn.py).
  *
  * jitr_b200_qe_overlap: T_lj = scale * sum_n x_p[n] (U1c[n] + (l.s)_j U1so[n]) x_n[n]   (:317-322)

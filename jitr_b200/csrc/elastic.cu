@@ -31,6 +31,11 @@ struct ObsArgs {
     double* Ay;
     double* Q;
     double* tot_rxn;
+    // optional weighted misfit against data (jitr_b200_elastic_misfit): sum_theta w (scale dsdo - y)^2 per (sample, energy)
+    const double* data_y;
+    const double* data_w;
+    const double* data_scale;
+    double* misfit;
 };
 
 constexpr int kObsWarps = 8;
@@ -39,6 +44,7 @@ constexpr int kObsAnglesPerLane = 8;  // angles a lane sums at once (register bl
 // One WARP per (sample, energy) pair, no CTA barrier in the sample loop: lanes l form the 2 L coefficient
 // pairs of the sample (staged in the warp's slice of shared memory), then every lane sums up to eight
 // angles at once over l, so a coefficient is fetched once per eight angles.
+template <bool MISFIT>
 __global__ void __launch_bounds__(kObsWarps * 32) elastic_observables_kernel(const ObsArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int L1 = A.lmax + 1, NA = A.n_angles;
@@ -85,6 +91,7 @@ __global__ void __launch_bounds__(kObsWarps * 32) elastic_observables_kernel(con
             A.tot_rxn[2 * pair + 1] = rx * (10.0 * M_PI / (k * k));
         }
         __syncwarp();
+        double mis = 0.0;
         for (int t0 = 0; t0 < NA; t0 += 32 * kObsAnglesPerLane) {
             double2 fa[kObsAnglesPerLane], fb[kObsAnglesPerLane];
             int tj[kObsAnglesPerLane];
@@ -119,11 +126,20 @@ __global__ void __launch_bounds__(kObsWarps * 32) elastic_observables_kernel(con
                     // conj(a) b = (a.x - i a.y)(b.x + i b.y)
                     const double re = fa[j].x * fb[j].x + fa[j].y * fb[j].y, im = fa[j].x * fb[j].y - fa[j].y * fb[j].x;
                     const size_t o = (size_t)pair * NA + t;
-                    A.dsdo[o] = d0 * 10.0;
+                    if (!MISFIT || A.dsdo) A.dsdo[o] = d0 * 10.0;
                     if (A.Ay) A.Ay[o] = 2.0 * im / den;
                     if (A.Q) A.Q[o] = 2.0 * re / den;
+                    if (MISFIT) {
+                        const size_t d = (size_t)e * NA + t;
+                        const double v = d0 * 10.0 * (A.data_scale ? A.data_scale[d] : 1.0) - A.data_y[d];
+                        mis = fma(A.data_w[d] * v, v, mis);
+                    }
                 }
             }
+        }
+        if (MISFIT) {
+            for (int o = 16; o > 0; o >>= 1) mis += __shfl_down_sync(0xffffffffu, mis, o);
+            if (lane == 0) A.misfit[pair] = mis;
         }
         __syncwarp();  // the coefficients of this sample are consumed before the next one overwrites them
     }
@@ -225,6 +241,27 @@ extern "C" int jitr_b200_elastic_sweep_tensors(int nbasis, int lmax, long long n
     return launch_sweep<false>(a, static_cast<cudaStream_t>(stream));
 }
 
+static int launch_observables(ObsArgs a, const char* what, cudaStream_t st) {
+    const int L1 = a.lmax + 1;
+    const size_t smem = (size_t)2 * L1 * a.n_angles * 8 + (size_t)kObsWarps * 2 * L1 * 16;
+    if (smem > 232448) return set_error(JITR_B200_ERR_UNSUPPORTED, "elastic_observables: (lmax+1)*n_angles tables exceed shared memory");
+    auto kern = a.misfit ? elastic_observables_kernel<true> : elastic_observables_kernel<false>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        return set_cuda_error("cudaFuncSetAttribute(observables)");
+    // chunk the sample axis so that the grid is a few waves of the SM count
+    const int sms = sm_count();
+    long long target_blocks_x = (4LL * sms + a.n_energies - 1) / a.n_energies;
+    if (target_blocks_x < 1) target_blocks_x = 1;
+    long long chunk = (a.n_samples + target_blocks_x - 1) / target_blocks_x;
+    if (chunk < 1) chunk = 1;
+    a.chunk = (int)(chunk > (1 << 30) ? (1 << 30) : chunk);
+    dim3 grid((unsigned)((a.n_samples + a.chunk - 1) / a.chunk), (unsigned)a.n_energies);
+    kern<<<grid, kObsWarps * 32, smem, st>>>(a);
+    count_launch();
+    if (cudaGetLastError() != cudaSuccess) return set_cuda_error(what);
+    return JITR_B200_OK;
+}
+
 extern "C" int jitr_b200_elastic_observables(int lmax, int n_angles, long long n_samples, int n_energies,
                                              const double* S, const int* nl, const double* P, const double* P1,
                                              const double* phase, const double* f_c, const double* kvec,
@@ -239,23 +276,25 @@ extern "C" int jitr_b200_elastic_observables(int lmax, int n_angles, long long n
     a.phase = reinterpret_cast<const double2*>(phase);
     a.f_c = reinterpret_cast<const double2*>(f_c);
     a.kvec = kvec; a.dsdo = dsdo; a.Ay = Ay; a.Q = Q; a.tot_rxn = tot_rxn;
-    const int L1 = lmax + 1;
-    const size_t smem = (size_t)2 * L1 * n_angles * 8 + (size_t)kObsWarps * 2 * L1 * 16;
-    if (smem > 232448) return set_error(JITR_B200_ERR_UNSUPPORTED, "elastic_observables: (lmax+1)*n_angles tables exceed shared memory");
-    if (cudaFuncSetAttribute(elastic_observables_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-        return set_cuda_error("cudaFuncSetAttribute(observables)");
-    // chunk the sample axis so that the grid is a few waves of the SM count
-    const int sms = sm_count();
-    long long target_blocks_x = (4LL * sms + n_energies - 1) / n_energies;
-    if (target_blocks_x < 1) target_blocks_x = 1;
-    long long chunk = (n_samples + target_blocks_x - 1) / target_blocks_x;
-    if (chunk < 1) chunk = 1;
-    a.chunk = (int)(chunk > (1 << 30) ? (1 << 30) : chunk);
-    dim3 grid((unsigned)((n_samples + a.chunk - 1) / a.chunk), (unsigned)n_energies);
-    elastic_observables_kernel<<<grid, kObsWarps * 32, smem, static_cast<cudaStream_t>(stream)>>>(a);
-    count_launch();
-    if (cudaGetLastError() != cudaSuccess) return set_cuda_error("elastic_observables launch");
-    return JITR_B200_OK;
+    return launch_observables(a, "elastic_observables launch", static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int jitr_b200_elastic_misfit(int lmax, int n_angles, long long n_samples, int n_energies, const double* S,
+                                        const int* nl, const double* P, const double* P1, const double* phase,
+                                        const double* f_c, const double* kvec, const double* y, const double* w,
+                                        const double* scale, double* misfit, double* tot_rxn, double* dsdo, void* stream) {
+    if (n_samples == 0) return JITR_B200_OK;
+    if (lmax < 0 || lmax > 255 || n_angles < 1 || n_samples < 0 || n_energies < 1 || !S || !nl || !P || !P1 || !phase ||
+        !f_c || !kvec || !y || !w || !misfit || !tot_rxn)
+        return set_error(JITR_B200_ERR_BAD_ARG, "elastic_misfit: null pointer or bad size");
+    ObsArgs a{};
+    a.lmax = lmax; a.n_angles = n_angles; a.n_energies = n_energies; a.n_samples = n_samples;
+    a.S = reinterpret_cast<const double2*>(S); a.nl = nl; a.P = P; a.P1 = P1;
+    a.phase = reinterpret_cast<const double2*>(phase);
+    a.f_c = reinterpret_cast<const double2*>(f_c);
+    a.kvec = kvec; a.dsdo = dsdo; a.tot_rxn = tot_rxn;
+    a.data_y = y; a.data_w = w; a.data_scale = scale; a.misfit = misfit;
+    return launch_observables(a, "elastic_misfit launch", static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int jitr_b200_eval_potentials(int nbasis, int model, long long n_samples, int n_energies, const double* mesh_x,

@@ -466,6 +466,44 @@ class ElasticSweep:
         _cabi.check(rc, "jitr_b200_elastic_observables")
         return ElasticXS(dsdo, Ay, Q, tr[..., 0], tr[..., 1])
 
+    def misfit(self, S, nl, y, weights, scale=None, want_dsdo=False):
+        """Weighted misfit against data, reduced on the device: sum_theta w (scale * dsdo - y)^2 per (sample, energy).
+
+        ``y``, ``weights``, ``scale``: (E, n_angles) arrays (``scale`` e.g. 1 / Rutherford for ratio data, None = 1).
+        Returns ``(misfit (B, E), sigma_tot (B, E), sigma_rxn (B, E)[, dsdo (B, E, n_angles)])`` CUDA tensors; without
+        ``want_dsdo`` the angular distributions never leave the kernel."""
+        import torch
+
+        if not self.has_obs:
+            raise ValueError("observables need DifferentialWorkspace objects for every energy")
+        B = S.shape[0]
+
+        def tab(v, name):
+            if v is None:
+                return None
+            t = torch.as_tensor(np.asarray(v.cpu() if isinstance(v, torch.Tensor) else v, dtype=np.float64), device=self.device)
+            if tuple(t.shape) != (self.nE, self.n_angles):
+                raise ValueError(f"{name} must have shape ({self.nE}, {self.n_angles})")
+            return t.contiguous()
+
+        yt, wt, st = tab(y, "y"), tab(weights, "weights"), tab(scale, "scale")
+        mis = torch.empty((B, self.nE), dtype=torch.float64, device=self.device)
+        tr = torch.empty((B, self.nE, 2), dtype=torch.float64, device=self.device)
+        dsdo = torch.empty((B, self.nE, self.n_angles), dtype=torch.float64, device=self.device) if want_dsdo else None
+        rc = _cabi.lib().jitr_b200_elastic_misfit(
+            self.lmax, self.n_angles, B, self.nE, _cabi.ptr(S), _cabi.ptr(nl), _cabi.ptr(self.P), _cabi.ptr(self.P1),
+            _cabi.ptr(self.phase), _cabi.ptr(self.f_c), _cabi.ptr(self.kvec), _cabi.ptr(yt), _cabi.ptr(wt), _cabi.ptr(st),
+            _cabi.ptr(mis), _cabi.ptr(tr), _cabi.ptr(dsdo), _cabi.stream_ptr(),
+        )
+        _cabi.check(rc, "jitr_b200_elastic_misfit")
+        out = (mis, tr[..., 0], tr[..., 1])
+        return out + (dsdo,) if want_dsdo else out
+
+    def misfit_params(self, model, params, y, weights, scale=None):
+        """Built-in potentials -> misfit (B, E): the batched likelihood kernel of a calibration loop."""
+        S, nl, status = self.smatrix_params(model, params)
+        return self.misfit(S, nl, y, weights, scale) + (status,)
+
     def xs_params_to_host(self, model, params_host, dsdo_host, tr_host, chunk=8192):
         """End-to-end sweep with HOST buffers: ``params_host`` (B, n_params) pinned float64 ->
         ``dsdo_host`` (B, E, n_angles) and ``tr_host`` (B, E, 2) pinned float64.  The sample axis is

@@ -943,3 +943,43 @@ def test_large_lmax_proton_and_odd_batch_sizes():
             assert relerr(S[b, 0, : len(sp)].cpu().numpy(), sp) < RTOL_S
             dsdo = ow.xs(c, so, co)[0]
             assert relerr(x.dsdo[b, 0].cpu().numpy(), dsdo) < RTOL_XS
+
+
+def test_device_misfit_matches_notebook_log_likelihood(golden):
+    """(f)4: the batched likelihood.  The reference's quickstart notebook (cells 11-13) forms
+    y_pred = dsdo / rutherford, chi2 = sum((y_pred - y)**2 / y_err * 2), logl = -0.5 (chi2 + sum(log(2 pi y_err)));
+    here chi2 is reduced inside the observable kernel (weights 2 / y_err, scale 1 / rutherford) without writing the
+    angular distributions.  Checked against the oracle's dsdo for a proton case, and against the kernel's own dsdo."""
+    g = golden("config3_p48Ca_30MeV")
+    rx, kin, ws = make_ws(g)
+    model = model_for("config3", g)
+    sweep = ws._as_sweep()
+    B = 24
+    rng = np.random.default_rng(4)
+    p = np.tile(g["params"][:1], (B, 1)) * (1 + 0.02 * rng.standard_normal((B, g["params"].shape[1])))
+    p[:, -2:] = g["params"][0, -2:]
+    ruth = np.asarray(ws.rutherford, dtype=np.float64)
+    y = (g["dsdo"][0] / ruth) * (1 + 0.05 * rng.standard_normal(ruth.shape))
+    y_err = 0.05 * np.abs(y) + 1e-3
+    mis, tot, rxn, status = sweep.misfit_params(model, torch.tensor(p, device="cuda"), y[None], (2.0 / y_err)[None], (1.0 / ruth)[None])
+    x = sweep.xs_params(model, torch.tensor(p, device="cuda"))
+    assert int(status.abs().sum()) == 0
+    dsdo = x.dsdo[:, 0].cpu().numpy()
+    chi2_k = np.sum((dsdo / ruth - y) ** 2 / y_err * 2, axis=1)
+    assert relerr(mis[:, 0].cpu().numpy(), chi2_k) < 1e-12
+    assert float((rxn - x.rxn).abs().max()) == 0.0
+    ow = orc.ElasticWorkspace(int(g["N"]), int(g["lmax"]), float(g["Rch"]), tuple(g["kin"]), g["angles"], 20, asym_table=g["asym"])
+    log_err_term = np.sum(np.log(2 * np.pi * y_err))
+    for b in (0, B - 1):
+        c, so, co = orc.kduq_potentials(ws.radial_grid(), (1, 1), (48, 20), float(g["kin"][0]), p[b])
+        y_pred = ow.xs(c, so, co)[0] / ruth
+        chi2 = np.sum((y_pred - y) ** 2 / y_err * 2)
+        logl_ref = -0.5 * (chi2 + log_err_term)
+        logl = -0.5 * (float(mis[b, 0]) + log_err_term)
+        assert abs(logl - logl_ref) <= 1e-8 * abs(logl_ref)
+    # with the angular distributions requested as well: identical numbers to the observable kernel's
+    S, nl, _ = sweep.smatrix_params(model, torch.tensor(p, device="cuda"))
+    m2, _, _, d2 = sweep.misfit(S, nl, y[None], (2.0 / y_err)[None], (1.0 / ruth)[None], want_dsdo=True)
+    assert float((d2 - x.dsdo).abs().max()) == 0.0 and float((m2 - mis).abs().max()) == 0.0
+    with pytest.raises(ValueError):
+        sweep.misfit(S, nl, y, (2.0 / y_err)[None], None)
