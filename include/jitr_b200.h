@@ -179,6 +179,15 @@ int jitr_b200_elastic_misfit(int lmax, int n_angles, long long n_samples, int n_
                              const double* scale, double* misfit, double* tot_rxn, double* dsdo, void* stream);
 
 /*
+ * Percentiles over the sample axis, on the device: numpy.percentile(values, q, axis=0) with the default linear
+ * interpolation (the uncertainty bands of the reference's kduq_uq_demo notebook, cell 18).
+ *   values [n_samples][n_columns] f64 device (e.g. dsdo viewed as [S][E * n_angles]);  q: HOST array of nq <= 8
+ *   percentages in [0, 100];  out [nq][n_columns] f64 device.  Exact order statistics (radix selection).
+ */
+int jitr_b200_percentiles(const double* values, long long n_samples, long long n_columns, const double* q_host, int nq,
+                          double* out, void* stream);
+
+/*
  * Quasi-elastic (p,n) DWBA, the steps after the distorted-wave solves (xs/quasielastic_pn.py).
  *
  * jitr_b200_qe_overlap: T_lj = scale * sum_n x_p[n] (U1c[n] + (l.s)_j U1so[n]) x_n[n]   (:317-322)

@@ -5,12 +5,12 @@
 Host code is Python; every solve runs in hand-written sm_100a CUDA kernels behind the C ABI in
 ``include/jitr_b200.h`` (``jitr_b200/_lib/libjitr_b200.so``).  There is no CPU fallback.
 """
-from . import constants, free_solutions, optical_potentials, quadrature, reactions, rmatrix, utils, xs
+from . import constants, free_solutions, optical_potentials, quadrature, reactions, rmatrix, uq, utils, xs
 from .rmatrix import Solver
 from .xs.elastic import DifferentialWorkspace, ElasticSweep, ElasticXS, IntegralWorkspace
 
 __version__ = "0.1.0"
 __all__ = [
     "DifferentialWorkspace", "ElasticSweep", "ElasticXS", "IntegralWorkspace", "Solver", "constants",
-    "free_solutions", "optical_potentials", "quadrature", "reactions", "rmatrix", "utils", "xs",
+    "free_solutions", "optical_potentials", "quadrature", "reactions", "rmatrix", "uq", "utils", "xs",
 ]

@@ -40,6 +40,7 @@ SIGNATURES = {
     "jitr_b200_eval_potentials": (_i, [_i, _i, _ll, _i, _p, _p, _p, _i, _p, _p, _p, _p]),
     "jitr_b200_elastic_observables": (_i, [_i, _i, _ll, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "jitr_b200_elastic_misfit": (_i, [_i, _i, _ll, _i] + [_p] * 14),
+    "jitr_b200_percentiles": (_i, [_p, _ll, _ll, _p, _i, _p, _p]),
     "jitr_b200_qe_overlap": (_i, [_i, _ll, _i, _p, _p, _p, _p, _d, _d, _d, _p, _ll, _ll, _p]),
     "jitr_b200_qe_xs": (_i, [_i, _i, _ll, _p, _p, _d, _p, _p]),
     "jitr_b200_solve_workspace_bytes": (_ll, [_i, _i, _ll, _i]),

@@ -983,3 +983,42 @@ def test_device_misfit_matches_notebook_log_likelihood(golden):
     assert float((d2 - x.dsdo).abs().max()) == 0.0 and float((m2 - mis).abs().max()) == 0.0
     with pytest.raises(ValueError):
         sweep.misfit(S, nl, y, (2.0 / y_err)[None], None)
+
+
+def test_device_percentiles_match_numpy_bit_for_bit():
+    """(f)4: uncertainty bands on the device = numpy.percentile(values, q, axis=0) (kduq_uq_demo cell 18), exact order
+    statistics and numpy's linear interpolation: heavy ties, negative numbers and zeros of both signs, one and two samples,
+    column counts that do not fill the last CTA, q at both ends."""
+    from jitr_b200 import uq
+
+    rng = np.random.default_rng(8)
+    cases = [rng.standard_normal((1000, 37)) * 10.0, np.round(rng.standard_normal((513, 16)) * 2.0) / 2.0, rng.random((1, 5)),
+             rng.random((2, 33)) - 0.5, np.abs(rng.standard_normal((4097, 3))) * 1e-300, rng.standard_normal((64, 2, 7)) * 1e6]
+    cases[1][::7, 3] = -0.0
+    cases[1][1::7, 3] = 0.0
+    for v in cases:
+        for q in ([16.0, 84.0], [0.0, 2.5, 50.0, 97.5, 100.0], [33.3]):
+            got = uq.percentiles(torch.tensor(v, device="cuda"), q).cpu().numpy()
+            want = np.percentile(v, q, axis=0)
+            assert got.shape == want.shape
+            assert np.array_equal(got, want), (v.shape, q, np.abs(got - want).max())
+    with pytest.raises(ValueError):
+        uq.percentiles(torch.zeros((4, 4), device="cuda", dtype=torch.float64), [101.0])
+
+
+def test_device_percentile_bands_of_a_sweep(golden):
+    """The notebook's band computation on real sweep output: np.percentile(dsdo / rutherford, [16, 84], axis=samples)."""
+    from jitr_b200 import uq
+
+    g = golden("config3_p48Ca_30MeV")
+    rx, kin, ws = make_ws(g)
+    model = model_for("config3", g)
+    rng = np.random.default_rng(9)
+    B = 600
+    p = np.tile(g["params"][:1], (B, 1)) * (1 + 0.02 * rng.standard_normal((B, g["params"].shape[1])))
+    p[:, -2:] = g["params"][0, -2:]
+    x = ws._as_sweep().xs_params(model, torch.tensor(p, device="cuda"))
+    ratio = x.dsdo[:, 0] / torch.tensor(np.asarray(ws.rutherford), device="cuda")
+    bands = uq.percentiles(ratio, [16, 84]).cpu().numpy()
+    assert np.array_equal(bands, np.percentile(ratio.cpu().numpy(), [16, 84], axis=0))
+    assert np.all(bands[0] <= bands[1])
