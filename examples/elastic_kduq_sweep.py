@@ -29,7 +29,7 @@ rows[:, -2:] = central[-2:]  # Fermi-energy parameters stay fixed (kduq.py:231-2
 xs = ws.xs_params(kduq.KDUQ((1, 0)), torch.tensor(rows, device="cuda"))
 
 # uncertainty bands on the device (= np.percentile(dsdo, [16, 50, 84], axis=0)): only 3 x 180 numbers leave the GPU
-lo, med, hi = jitr_b200.uq.percentiles(xs.dsdo[:, 0], [16, 50, 84]).cpu().numpy()
+lo, med, hi = jitr_b200.uq.percentiles(xs.dsdo, [16, 50, 84]).cpu().numpy()
 print(f"{B} samples; sigma_rxn = {float(xs.rxn.mean()):.1f} +- {float(xs.rxn.std()):.1f} mb")
 for i in (0, 45, 90, 179):
     print(f"theta = {np.degrees(angles[i]):6.1f} deg   dsigma/dOmega = {med[i]:12.4e}  [{lo[i]:.4e}, {hi[i]:.4e}] mb/sr")
