@@ -62,12 +62,23 @@ __global__ void __launch_bounds__(kPctCols* kPctRows) percentile_kernel(const do
         for (int i = threadIdx.x; i < nq * kPctCols * 256; i += blockDim.x) (&hist[0][0][0])[i] = 0u;
         __syncthreads();
         if (live) {
-            for (long long r = tr; r < S; r += kPctRows) {
-                const unsigned long long k = pct_key(x[r * M + col]);
-                for (int t = 0; t < nq; ++t) {
-                    // same leading digits as the class that holds the wanted rank?
-                    if (pass == 0 || (k >> (shift + 8)) == (prefix[t][tc] >> (shift + 8)))
-                        atomicAdd(&hist[t][tc][(unsigned)(k >> shift) & 255u], 1u);
+            unsigned long long want[kPctMaxQ];  // leading digits of the class that holds the wanted rank
+            for (int t = 0; t < nq; ++t) want[t] = pass == 0 ? 0ULL : prefix[t][tc] >> (shift + 8);
+            // four independent rows in flight per thread
+            for (long long r0 = tr; r0 < S; r0 += 4 * kPctRows) {
+                double v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const long long r = r0 + (long long)u * kPctRows;
+                    v[u] = r < S ? x[r * M + col] : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (r0 + (long long)u * kPctRows >= S) break;
+                    const unsigned long long k = pct_key(v[u]);
+                    const unsigned long long lead = pass == 0 ? 0ULL : k >> (shift + 8);
+                    for (int t = 0; t < nq; ++t)
+                        if (lead == want[t]) atomicAdd(&hist[t][tc][(unsigned)(k >> shift) & 255u], 1u);
                 }
             }
         }
@@ -93,13 +104,33 @@ __global__ void __launch_bounds__(kPctCols* kPctRows) percentile_kernel(const do
     }
     __syncthreads();
     if (live) {
-        for (long long r = tr; r < S; r += kPctRows) {
-            const unsigned long long k = pct_key(x[r * M + col]);
-            for (int t = 0; t < nq; ++t) {
-                const unsigned long long sel = prefix[t][tc];
-                if (k <= sel) atomicAdd(&n_le[t][tc], 1ULL);
-                else atomicMin(&above[t][tc], k);
+        // per-thread partial results first: one shared-memory atomic per thread and target at the end
+        unsigned long long sel[kPctMaxQ], cnt[kPctMaxQ], mn[kPctMaxQ];
+        for (int t = 0; t < nq; ++t) {
+            sel[t] = prefix[t][tc];
+            cnt[t] = 0ULL;
+            mn[t] = ~0ULL;
+        }
+        for (long long r0 = tr; r0 < S; r0 += 4 * kPctRows) {
+            double v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const long long r = r0 + (long long)u * kPctRows;
+                v[u] = r < S ? x[r * M + col] : 0.0;
             }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (r0 + (long long)u * kPctRows >= S) break;
+                const unsigned long long k = pct_key(v[u]);
+                for (int t = 0; t < nq; ++t) {
+                    if (k <= sel[t]) ++cnt[t];
+                    else if (k < mn[t]) mn[t] = k;
+                }
+            }
+        }
+        for (int t = 0; t < nq; ++t) {
+            atomicAdd(&n_le[t][tc], cnt[t]);
+            atomicMin(&above[t][tc], mn[t]);
         }
     }
     __syncthreads();
