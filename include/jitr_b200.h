@@ -233,6 +233,13 @@ int jitr_b200_set_option(int key, int value);
 /* systems the symmetric path handed to the partial-pivoting path since load (-1: no device) */
 long long jitr_b200_sym_fallback_count(void);
 
+/*
+ * Diagnostic for the parity gate: when a device array mask[n_samples * n_energies] of 64-bit words is registered
+ * (NULL = off, the default), the fused sweep ORs bit (2 l + (j == l - 1/2)) into mask[pair] for every system the
+ * symmetric path handed to partial pivoting, so a test can restrict its error statistics to those systems.
+ */
+int jitr_b200_debug_set_fallback_mask(unsigned long long* mask);
+
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 long long jitr_b200_launch_count(void);
 

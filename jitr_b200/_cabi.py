@@ -35,6 +35,7 @@ SIGNATURES = {
     "jitr_b200_launch_count": (_ll, []),
     "jitr_b200_set_option": (_i, [_i, _i]),
     "jitr_b200_sym_fallback_count": (_ll, []),
+    "jitr_b200_debug_set_fallback_mask": (_i, [_p]),
     "jitr_b200_elastic_sweep_params": (_i, [_i, _i, _i, _ll, _i, _p, _p, _p, _p, _p, _p, _i, _d, _p, _p, _p, _p]),
     "jitr_b200_elastic_sweep_tensors": (_i, [_i, _i, _ll, _i, _p, _p, _p, _p, _p, _p, _p, _p, _d, _p, _p, _p, _p]),
     "jitr_b200_eval_potentials": (_i, [_i, _i, _ll, _i, _p, _p, _p, _i, _p, _p, _p, _p]),

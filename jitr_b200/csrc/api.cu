@@ -58,6 +58,8 @@ unsigned long long* fallback_counter() {
     }
     return ctr[dev];
 }
+static std::atomic<unsigned long long*> g_fallback_mask{nullptr};
+unsigned long long* fallback_mask() { return g_fallback_mask.load(); }
 unsigned long long* next_work_counter(cudaStream_t st) {
     constexpr int kRing = 256;
     static unsigned long long* ring[kMaxDevices] = {nullptr};
@@ -84,6 +86,10 @@ extern "C" long long jitr_b200_launch_count(void) { return jitr::g_launches.load
 extern "C" int jitr_b200_set_option(int key, int value) {
     if (key < 0 || key >= JITR_B200_OPT_COUNT) return jitr::set_error(JITR_B200_ERR_BAD_ARG, "set_option: unknown key");
     jitr::g_options[key].store(value);
+    return JITR_B200_OK;
+}
+extern "C" int jitr_b200_debug_set_fallback_mask(unsigned long long* mask) {
+    jitr::g_fallback_mask.store(mask);
     return JITR_B200_OK;
 }
 extern "C" long long jitr_b200_sym_fallback_count(void) {

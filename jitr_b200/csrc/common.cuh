@@ -9,6 +9,7 @@ int sm_count();
 void count_launch();
 int option(int key);                    // jitr_b200_set_option values
 unsigned long long* fallback_counter();
+unsigned long long* fallback_mask();    // jitr_b200_debug_set_fallback_mask (nullptr: off)
 // a zeroed (stream-ordered) device counter for one launch; a ring of 256, so launches in flight on
 // different streams do not share one
 unsigned long long* next_work_counter(cudaStream_t st);  // device counter (lazily allocated), nullptr on failure

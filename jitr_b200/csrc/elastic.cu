@@ -213,6 +213,7 @@ extern "C" int jitr_b200_elastic_sweep_params(int nbasis, int lmax, int model, l
     a.N = nbasis;
     a.symmetric = option(JITR_B200_OPT_SYMMETRIC);
     a.fallbacks = a.symmetric ? fallback_counter() : nullptr;
+    a.fallback_mask = a.symmetric ? fallback_mask() : nullptr;
     return launch_sweep<true>(a, static_cast<cudaStream_t>(stream));
 }
 
@@ -238,6 +239,7 @@ extern "C" int jitr_b200_elastic_sweep_tensors(int nbasis, int lmax, long long n
     a.N = nbasis;
     a.symmetric = option(JITR_B200_OPT_SYMMETRIC);
     a.fallbacks = a.symmetric ? fallback_counter() : nullptr;
+    a.fallback_mask = a.symmetric ? fallback_mask() : nullptr;
     return launch_sweep<false>(a, static_cast<cudaStream_t>(stream));
 }
 

@@ -114,7 +114,7 @@ struct GenericSolver {
     // d0, d1: diagonal entries of rows lane and lane + 32.  P <= 64: threshold-pivoted symmetric elimination
     // first (lu_sym.cuh), partial pivoting (lu_warp.cuh) when a diagonal entry fails the test or P > 64.
     __device__ __forceinline__ double2 solve(const double2 d0, const double2 d1, int& singular, const bool symmetric,
-                                             unsigned long long* fallbacks) {
+                                             unsigned long long* fallbacks, int& fellback) {
         assemble(d0, d1);
         if (symmetric && g.P <= 64) {
             int fail = 0;
@@ -122,6 +122,7 @@ struct GenericSolver {
             __syncwarp();
             if (!fail) return corner;
             if (lane == 0 && fallbacks) atomicAdd(fallbacks, 1ULL);
+            fellback = 1;
             assemble(d0, d1);
         }
         const double2 corner = bordered_schur<MAXNS>(M, g, lane, singular);
@@ -215,7 +216,7 @@ struct WarpSolver {
     // Threshold-pivoted symmetric elimination first (lu_sym.cuh); a system whose diagonal fails the
     // threshold test is re-solved with partial pivoting (lu_fast.cuh).  `fallbacks` counts those.
     __device__ __forceinline__ double2 solve(const double2 d0, const double2 d1, int& singular, const bool symmetric,
-                                             unsigned long long* fallbacks) {
+                                             unsigned long long* fallbacks, int& fellback) {
         const double2 one = make_double2(1.0, 0.0);
         const double2 da = lane < N ? d0 : one, db = lane + 32 < N ? d1 : one;
         if (symmetric) {
@@ -233,6 +234,7 @@ struct WarpSolver {
             __syncwarp();
             if (!fail) return corner;
             if (lane == 0 && fallbacks) atomicAdd(fallbacks, 1ULL);
+            fellback = 1;
         }
         int sing = 0;
         const double2 corner = pivoting_fallback<PT>(wofs, da, db, lane, &sing);
@@ -357,6 +359,14 @@ __global__ void __launch_bounds__(SweepPlan<MODE>::kThreads, 1) elastic_sweep_ke
     }
     __syncthreads();
     if (!active && lane == 0) atomicSub(&warps_active, 1);
+#ifdef JITR_SWEEP_STAGGER
+    // tuning experiment: odd warps start late, so that the panel phases (shared-memory / latency bound) of one half of
+    // the CTA overlap the trailing updates (FP64-pipe bound) of the other half
+    if (warp & 1) {
+        const long long t0 = clock64();
+        while (clock64() - t0 < JITR_SWEEP_STAGGER) __nanosleep(200);
+    }
+#endif
     for (unsigned it = 0;; ++it) {
         const int b = it % LockStep::K;
         if (it >= LockStep::K) lock.wait(b, (it / LockStep::K - 1) & 1);  // every warp has finished iteration it - K
@@ -416,7 +426,9 @@ __global__ void __launch_bounds__(SweepPlan<MODE>::kThreads, 1) elastic_sweep_ke
         const double2 dd0 = make_double2(d0.x + ll1 * cent0 + ls * so0.x, d0.y + ls * so0.y);
         const double2 dd1 = make_double2(d1.x + ll1 * cent1 + ls * so1.x, d1.y + ls * so1.y);
         // corner = -b^T (a^2 A)^-1 b = -R
-        const double2 corner = solver.solve(dd0, dd1, singular, A.symmetric != 0, A.fallbacks);
+        int fellback = 0;
+        const double2 corner = solver.solve(dd0, dd1, singular, A.symmetric != 0, A.fallbacks, fellback);
+        if (fellback && A.fallback_mask && lane == 0) atomicOr(A.fallback_mask + pair, 1ULL << (2 * l + jj));
         const double2* as = A.asym + ((size_t)e * L1 + l) * 4;  // (after the solve: fewer live registers)
         const double2 Hp = as[0], Hm = as[1], Hpp = as[2], Hmp = as[3];
         const double a = A.etab[(size_t)e * JITR_B200_ET_STRIDE + JITR_B200_ET_A];

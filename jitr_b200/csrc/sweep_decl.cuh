@@ -8,6 +8,7 @@ struct SweepArgs {
     int N, lmax, model, n_energies, n_params;
     int symmetric;                  // try the threshold-pivoted symmetric elimination first (fast paths)
     unsigned long long* fallbacks;  // device counter of systems re-solved with partial pivoting
+    unsigned long long* fallback_mask;  // optional [n_pairs] bit mask of the systems that fell back (diagnostic)
     unsigned long long* work_counter;  // device counter handing out (sample, energy) pairs, zero at launch
     long long n_pairs;
     const double* That;

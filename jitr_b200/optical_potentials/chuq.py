@@ -26,6 +26,15 @@ def get_ch89():
     return np.asarray(_CH89, dtype=np.float64)
 
 
+def get_samples(posterior="federal"):
+    """Posterior samples (NUM_POSTERIOR_SAMPLES, 22) of the CHUQ Federal or Democratic posterior (chuq.py:57-89)."""
+    if posterior not in ("federal", "democratic"):
+        raise ValueError("posterior must be either 'federal' or 'democratic'")
+    from ..data import posterior as _load
+
+    return _load(f"chuq_{posterior}")
+
+
 class CHUQ(SingleChannelOpticalModel):
     model_id = _cabi.MODEL_CHUQ
 

@@ -51,6 +51,16 @@ def get_kd03(projectile):
     return np.asarray(_KD03_N if _check(projectile) == (1, 0) else _KD03_P, dtype=np.float64)
 
 
+def get_samples(projectile, posterior="federal"):
+    """Posterior samples (NUM_POSTERIOR_SAMPLES, n_params) of the KDUQ Federal or Democratic posterior
+    (kduq.py:59-97), from the packed copy of the reference's data files (jitr_b200/data)."""
+    if posterior not in ("federal", "democratic"):
+        raise ValueError("posterior must be either 'federal' or 'democratic'")
+    from ..data import posterior as _load
+
+    return _load(f"kduq_{posterior}_{'n' if _check(projectile) == (1, 0) else 'p'}")
+
+
 class KDUQ(SingleChannelOpticalModel):
     """KDUQ optical model (kduq.py:531-559); ``params`` are the global parameters."""
 

@@ -36,6 +36,13 @@ def get_wlh_mean(projectile):
     return np.asarray(_MEAN_N if _check(projectile) == (1, 0) else _MEAN_P, dtype=np.float64)
 
 
+def get_samples(projectile):
+    """The 1000 WLH parameter samples (wlh.py:40-58), shape (NUM_POSTERIOR_SAMPLES, 46)."""
+    from ..data import posterior as _load
+
+    return _load(f"wlh_{'n' if _check(projectile) == (1, 0) else 'p'}")
+
+
 class WLH(SingleChannelOpticalModel):
     """WLH optical model (wlh.py:386-421); ``params`` are the 46 global parameters."""
 

@@ -247,3 +247,40 @@ def test_dom_elastic_workspace(golden, name):
         assert np.max(np.abs(sp - g["Splus"][i, : len(sp)])) < 1e-10
         dsdo = ow.xs(c, so, co)[0]
         assert np.max(np.abs(dsdo / g["dsdo"][i] - 1)) < 1e-9
+
+
+def test_parity_sweep_runner_vs_reference_golden(golden):
+    """oracle/parity_sweep.py (the multi-process evaluator behind the large-sample parity gate) reproduces the
+    reference's config-2 goldens on a two-workspace table."""
+    from oracle import parity_sweep
+
+    names = ("config2_n40Ca_E06", "config2_n208Pb_E15")
+    gs = [golden(n) for n in names]
+    tab = [((int(g["target"][0]), int(g["target"][1])), float(g["kin"][0]), float(g["Rch"]), tuple(float(v) for v in g["kin"])) for g in gs]
+    rows = gs[0]["params"][:4]
+    assert np.array_equal(rows, gs[1]["params"][:4])
+    o = parity_sweep.run(tab, rows, 40, 30, angles=gs[0]["angles"], procs=2)
+    for e, g in enumerate(gs):
+        for i in range(4):
+            L = int(g["nl"][i])
+            assert int(o["nl"][i, e]) == L
+            assert np.max(np.abs(o["splus"][i, e, :L] - g["splus"][i, :L]) / np.abs(g["splus"][i, :L])) < 1e-11
+            assert np.max(np.abs(o["sminus"][i, e, 1:L] - g["sminus"][i, 1:L]) / np.abs(g["sminus"][i, 1:L])) < 1e-11
+            assert np.all(o["splus"][i, e, L:] == 0)
+            assert np.max(np.abs(o["dsdo"][i, e] - g["dsdo"][i]) / g["dsdo"][i]) < 1e-10
+            assert abs(o["tot_rxn"][i, e, 1] - g["rxn"][i]) / g["rxn"][i] < 1e-11
+
+
+def test_refinement_referee_matches_40_digit_solve():
+    """oracle/mp_truth.py: the fast referee (float64 LU + 80-bit iterative refinement) agrees with the mpmath 40-digit
+    solve of the same float64 matrix to 1e-13 -- three orders below the 1e-10 parity gate it arbitrates."""
+    from jitr_b200 import workloads
+    from oracle import mp_truth
+
+    tab = workloads.energy_table()
+    rows = workloads.synthetic_kduq_samples(8)
+    items = [(0, 5, 3, 0), (1, 40, 7, 1), (5, 0, 0, 0), (7, 63, 12, 1)]
+    exact = mp_truth.referee(tab, rows, items, dps=40, procs=2)
+    fast = mp_truth.referee(tab, rows, items, dps=0, procs=2)
+    for a, b in zip(exact, fast):
+        assert abs(a - b) / abs(a) < 1e-13

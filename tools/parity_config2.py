@@ -1,0 +1,232 @@
+#!/usr/bin/env python
+"""Large-sample parity gate on the benchmarked sweep:
+all 416 federal KDUQ rows + >= 1000 of the bench's own multivariate-normal rows, each on all 64 (target, energy)
+workspaces, CUDA path vs the CPU oracle (oracle/parity_sweep.py on the host cores), once with the threshold-pivoted
+symmetric path (the default) and once with partial pivoting everywhere.
+
+    python tools/parity_config2.py [--synthetic 1000] [--out profiles/r02_parity.json]
+
+Reports max and 99.9th-percentile relative errors of S+-, dsigma/dOmega, sigma_rxn, exact agreement of the number of
+partial waves kept, and the same statistics restricted to the systems that took the partial-pivoting fallback.
+`compare()` is also what tests/test_gpu_parity.py and bench.py's ``parity`` key call.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+RTOL_S, RTOL_XS = 1e-10, 1e-8
+
+
+def parity_rows(n_synthetic=1000, pool=100000):
+    """the 416 federal rows + n_synthetic rows drawn (seeded) from the bench's own 10^5-row block 0"""
+    from jitr_b200 import workloads
+
+    rows = workloads.synthetic_kduq_samples(pool)
+    real = rows[:416]
+    pick = np.sort(np.random.default_rng(7).choice(np.arange(416, pool), size=n_synthetic, replace=False))
+    return np.concatenate([real, rows[pick]], axis=0), pick
+
+
+def _stats(err):
+    err = np.asarray(err).ravel()
+    if err.size == 0:
+        return {"n": 0, "max": None, "p999": None}
+    return {"n": int(err.size), "max": float(err.max()), "p999": float(np.quantile(err, 0.999))}
+
+
+def gpu_run(sweep, model, rows, symmetric):
+    """-> dict of numpy arrays + the fallback bit masks"""
+    import torch
+
+    from jitr_b200 import _cabi
+
+    L = _cabi.lib()
+    B = len(rows)
+    p = np.zeros((B, 40))
+    p[:, : rows.shape[1]] = rows
+    pt = torch.tensor(p, device=sweep.device)
+    mask = torch.zeros((B, sweep.nE), dtype=torch.int64, device=sweep.device)
+    try:
+        assert L.jitr_b200_set_option(_cabi.OPT_SYMMETRIC, 1 if symmetric else 0) == 0
+        assert L.jitr_b200_debug_set_fallback_mask(mask.data_ptr()) == 0
+        S, nl, status = sweep.smatrix_params(model, pt)
+        x = sweep.observables(S, nl, want_Ay=False, want_Q=False)
+        torch.cuda.synchronize()
+    finally:
+        L.jitr_b200_debug_set_fallback_mask(None)
+        L.jitr_b200_set_option(_cabi.OPT_SYMMETRIC, 1)
+    return dict(S=S.cpu().numpy(), nl=nl.cpu().numpy(), status=status.cpu().numpy(), dsdo=x.dsdo.cpu().numpy(),
+                rxn=x.rxn.cpu().numpy(), tot=x.t.cpu().numpy(), mask=mask.cpu().numpy().view(np.uint64))
+
+
+def compare_one(g, o):
+    """error statistics of one GPU run g against the oracle arrays o"""
+    L1 = o["splus"].shape[-1]
+    nl_equal = bool(np.array_equal(g["nl"], o["nl"]))
+    ls = np.arange(L1)[None, None, :]
+    kept = ls < o["nl"][..., None]
+    ep = np.abs(g["S"][:, :, 0, :] - o["splus"]) / np.maximum(np.abs(o["splus"]), 1e-300)
+    em = np.abs(g["S"][:, :, 1, :] - o["sminus"]) / np.maximum(np.abs(o["sminus"]), 1e-300)
+    keptm = kept & (ls >= 1)  # S-[0] = 0 by construction
+    zeros_beyond = bool(np.all(g["S"][:, :, 0, :][~kept] == 0) and np.all(g["S"][:, :, 1, :][~keptm] == 0))
+    ed = np.abs(g["dsdo"] - o["dsdo"]) / o["dsdo"]
+    er = np.abs(g["rxn"] - o["tot_rxn"][..., 1]) / np.abs(o["tot_rxn"][..., 1])
+    et = np.abs(g["tot"] - o["tot_rxn"][..., 0]) / np.abs(o["tot_rxn"][..., 0])
+    # systems that took the partial-pivoting fallback: bit 2l + (j = l - 1/2)
+    m = g["mask"]
+    fb_p = ((m[..., None] >> (2 * ls).astype(np.uint64)) & np.uint64(1)).astype(bool) & kept
+    fb_m = ((m[..., None] >> (2 * ls + 1).astype(np.uint64)) & np.uint64(1)).astype(bool) & keptm
+    fb_pairs = m != 0
+    n_sys = int(kept.sum() + keptm.sum())
+    out = {
+        "systems": n_sys, "pairs": int(g["nl"].size), "nl_equal": nl_equal, "zeros_beyond_nl": zeros_beyond,
+        "status_nonzero": int((g["status"] != 0).sum()),
+        "S": _stats(np.concatenate([ep[kept], em[keptm]])), "dsdo": _stats(ed), "sigma_rxn": _stats(er), "sigma_tot": _stats(et),
+        "fallback": {"systems": int(fb_p.sum() + fb_m.sum()), "pairs": int(fb_pairs.sum()),
+                     "S": _stats(np.concatenate([ep[fb_p], em[fb_m]])), "dsdo": _stats(ed[fb_pairs]),
+                     "sigma_rxn": _stats(er[fb_pairs])},
+    }
+    out["fallback"]["fraction"] = out["fallback"]["systems"] / max(n_sys, 1)
+    return out
+
+
+def referee_outliers(g, o, rows, tab, max_systems=4000, max_pairs=400, procs=None):
+    """Where the CUDA path and the float64 oracle differ by more than the gate, a 40-digit solve of the oracle's own
+    float64 matrix (oracle/mp_truth.py: float64 LU + iterative refinement with 80-bit residuals, exact to ~1e-12; the eight
+    worst systems also by mpmath at 40 digits as a cross-check of the referee itself) decides: the reference obtains R through an explicit inverse at cond(A) up to 1e7,
+    so its own S carries ~1e-10 .. 1e-9 of rounding noise on a handful of systems of a large sweep.  An outlier is
+    EXPLAINED when the CUDA value is inside the tolerance of the exact value, or at least as close to it as the oracle's."""
+    from oracle import jitr_oracle as orc
+    from oracle import mp_truth
+
+    L1 = o["splus"].shape[-1]
+    ls = np.arange(L1)[None, None, :]
+    kept = ls < o["nl"][..., None]
+    keptm = kept & (ls >= 1)
+    ep = np.where(kept, np.abs(g["S"][:, :, 0, :] - o["splus"]) / np.maximum(np.abs(o["splus"]), 1e-300), 0.0)
+    em = np.where(keptm, np.abs(g["S"][:, :, 1, :] - o["sminus"]) / np.maximum(np.abs(o["sminus"]), 1e-300), 0.0)
+    items = [(int(i), int(e), int(l), 0) for i, e, l in zip(*np.nonzero(ep >= RTOL_S))]
+    items += [(int(i), int(e), int(l), 1) for i, e, l in zip(*np.nonzero(em >= RTOL_S))]
+    rep = {"S_outlier_systems": len(items), "S_refereed": 0, "S_explained": 0, "S_worst": []}
+    items = sorted(items, key=lambda t: -(ep if t[3] == 0 else em)[t[0], t[1], t[2]])[:max_systems]
+    if items:
+        truth = mp_truth.referee(tab, rows, items, dps=0, procs=procs)
+        truth40 = mp_truth.referee(tab, rows, items[:8], dps=40, procs=procs)
+        rep["referee_vs_mp40_max"] = float(max(abs(a - b) / abs(b) for a, b in zip(truth[:8], truth40)))
+        for (i, e, l, jj), st in zip(items, truth):
+            sg = g["S"][i, e, jj, l]
+            so_ = (o["splus"] if jj == 0 else o["sminus"])[i, e, l]
+            eg, eo = abs(sg - st) / abs(st), abs(so_ - st) / abs(st)
+            ok = eg < RTOL_S or eg <= eo
+            rep["S_refereed"] += 1
+            rep["S_explained"] += int(ok)
+            if len(rep["S_worst"]) < 8:
+                rep["S_worst"].append({"row": i, "energy": e, "l": l, "jj": jj, "abs_S": abs(st), "gpu_vs_oracle": float((ep if jj == 0 else em)[i, e, l]),
+                                       "gpu_vs_mp40": float(eg), "oracle_vs_mp40": float(eo)})
+    # cross sections: pairs with an angle beyond the gate -> every kept partial wave of the pair solved in 40 digits
+    ed = np.abs(g["dsdo"] - o["dsdo"]) / o["dsdo"]
+    bad_pairs = np.argwhere(ed.max(axis=-1) >= RTOL_XS)
+    bad_pairs = sorted((tuple(int(v) for v in p) for p in bad_pairs), key=lambda p: -ed[p].max())
+    rep.update({"dsdo_outlier_pairs": len(bad_pairs), "dsdo_refereed": 0, "dsdo_explained": 0, "dsdo_worst": []})
+    bad_pairs = bad_pairs[:max_pairs]
+    if bad_pairs:
+        items = []
+        for (i, e) in bad_pairs:
+            items += [(i, e, l, 0) for l in range(int(o["nl"][i, e]))] + [(i, e, l, 1) for l in range(1, int(o["nl"][i, e]))]
+        truth = dict(zip(items, mp_truth.referee(tab, rows, items, dps=0, procs=procs)))
+        for (i, e) in bad_pairs:
+            nl = int(o["nl"][i, e])
+            sp = np.array([truth[(i, e, l, 0)] for l in range(nl)])
+            sm = np.array([0.0] + [truth[(i, e, l, 1)] for l in range(1, nl)], dtype=np.complex128)
+            tgt, Elab, Rch, kin = tab[e]
+            ws = orc.ElasticWorkspace(40, L1 - 1, Rch, kin, np.linspace(0.1, np.pi, g["dsdo"].shape[-1]), 0,
+                                      asym_table=np.zeros((L1, 4), dtype=np.complex128))  # angular tables only
+            dt = orc.differential_elastic_xs(ws.k, ws.angles, sp, sm, ws.P, ws.P1, ws.f_c, ws.sigma_l)[0]
+            eg, eo = np.abs(g["dsdo"][i, e] - dt) / dt, np.abs(o["dsdo"][i, e] - dt) / dt
+            ok = bool(np.all((eg < RTOL_XS) | (eg <= eo)))
+            rep["dsdo_refereed"] += 1
+            rep["dsdo_explained"] += int(ok)
+            if len(rep["dsdo_worst"]) < 8:
+                k = int(np.argmax(ed[i, e]))
+                rep["dsdo_worst"].append({"row": i, "energy": e, "angle_index": k, "dsdo": float(dt[k]), "dsdo_max_over_angles": float(dt.max()),
+                                          "gpu_vs_oracle": float(ed[i, e, k]), "gpu_vs_mp40": float(eg[k]), "oracle_vs_mp40": float(eo[k])})
+    rep["all_refereed_explained"] = (rep["S_explained"] == rep["S_refereed"] and rep["dsdo_explained"] == rep["dsdo_refereed"]
+                                     and rep["S_refereed"] == rep["S_outlier_systems"] and rep["dsdo_refereed"] == rep["dsdo_outlier_pairs"])
+    return rep
+
+
+def compare(n_synthetic=1000, sweep=None, model=None, procs=None, pool=100000):
+    """Run the gate; returns the JSON-able report (``passed`` = every bound of BASELINE.md section 3 holds)."""
+    import jitr_b200
+    from jitr_b200 import workloads
+    from jitr_b200.optical_potentials import kduq
+    from oracle import parity_sweep
+
+    rows, pick = parity_rows(n_synthetic, pool)
+    if sweep is None:
+        sweep = jitr_b200.ElasticSweep(workloads.config2_workspaces())
+    model = model or kduq.KDUQ((1, 0))
+    t0 = time.time()
+    o = parity_sweep.run(workloads.energy_table(), rows, workloads.N_BASIS, workloads.LMAX, procs=procs)
+    t_oracle = time.time() - t0
+    rep = {"workload": f"config 2: 416 federal KDUQ rows + {n_synthetic} of the bench's multivariate-normal rows (block 0, seeded pick) "
+                       f"x 64 (target, energy) workspaces, N = 40, lmax = 30, 180 angles",
+           "rows": int(len(rows)), "oracle_seconds": t_oracle, "oracle_procs": procs or os.cpu_count(),
+           "tolerances": {"S_rel": RTOL_S, "xs_rel": RTOL_XS}}
+    ok = True
+    tab = workloads.energy_table()
+    runs = {}
+    for name, sym in (("symmetric_path", True), ("partial_pivoting_only", False)):
+        g = runs[name] = gpu_run(sweep, model, rows, sym)
+        parts = {}
+        for sub, sl in (("federal_416", slice(0, 416)), ("synthetic", slice(416, None)), ("all", slice(None))):
+            gs = {k: v[sl] for k, v in g.items()}
+            os_ = {k: v[sl] for k, v in o.items()}
+            parts[sub] = compare_one(gs, os_)
+        rep[name] = parts
+        a = parts["all"]
+        ok &= a["nl_equal"] and a["zeros_beyond_nl"] and a["status_nonzero"] == 0
+        ok &= a["sigma_rxn"]["max"] < RTOL_XS and a["sigma_tot"]["max"] < RTOL_XS
+        # S and dsigma/dOmega: inside the gate, or -- for the few systems where the float64 reference itself is further
+        # than the gate from the exact solution of its own matrix -- explained by the 40-digit referee
+        t0 = time.time()
+        parts["referee"] = referee_outliers(g, o, rows, tab, procs=procs)
+        parts["referee"]["seconds"] = time.time() - t0
+        ok &= parts["referee"]["all_refereed_explained"]
+        ok &= a["S"]["p999"] < RTOL_S and a["dsdo"]["p999"] < RTOL_XS
+    # the two pivoting schemes against each other (no reference involved)
+    gs, gp = runs["symmetric_path"], runs["partial_pivoting_only"]
+    nz = np.abs(gp["S"]) > 0
+    rep["symmetric_vs_partial_pivoting"] = {
+        "S": _stats(np.abs(gs["S"][nz] - gp["S"][nz]) / np.abs(gp["S"][nz])), "dsdo": _stats(np.abs(gs["dsdo"] - gp["dsdo"]) / gp["dsdo"]),
+        "nl_equal": bool(np.array_equal(gs["nl"], gp["nl"]))}
+    rep["passed"] = bool(ok)
+    return rep
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--synthetic", type=int, default=1000)
+    ap.add_argument("--out", default=None)
+    args = ap.parse_args()
+    rep = compare(args.synthetic)
+    txt = json.dumps(rep, indent=1)
+    if args.out:
+        os.makedirs(os.path.dirname(os.path.abspath(args.out)), exist_ok=True)
+        open(args.out, "w").write(txt + "\n")
+    print(txt)
+    return 0 if rep["passed"] else 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())
