@@ -207,6 +207,19 @@ int jitr_b200_qe_overlap(int nbasis, long long batch, int nj, const double* xp, 
 int jitr_b200_qe_xs(int lmax, int n_angles, long long batch, const double* T, const double* G, double factor,
                     double* out, void* stream);
 
+/*
+ * Perey-Buck-type nonlocal kernels generated on the device: the overflow-free form of perey_buck_nonlocal,
+ * optical_potentials/potential_forms.py:14-19  [ exp(-(r^2+r'^2)/beta^2) 2 i^l z j_l(-i z) / (beta sqrt(pi)),  2 i^l z j_l(-i z) = 2 z i_l(z) ],
+ * times a Woods-Saxon depth at the mean radius, for every l = 0..lmax of every sample at once:
+ *   U_l(r_n, r_m) = -(V + iW) f((r_n + r_m)/2; R, a) * 2 z e^{-z} i_l(z) exp(z - (r_n^2 + r_m^2)/beta^2) / (beta sqrt(pi)),  z = zfac r_n r_m / beta^2
+ *   params [n_samples][5]: V, W, beta, R, a  (a <= 0: no Woods-Saxon factor -> V = -1, W = 0 gives perey_buck_nonlocal itself)
+ *   zfac   2 for the Gaussian nonlocality (exponent -(r - r')^2/beta^2);  2 pi reproduces the reference's literal z
+ *   rgrid  [N] physical mesh (fm);   out [n_samples][lmax+1][N][N] complex, ready to be the `nonlocal` input of
+ *   jitr_b200_solve_batched (system index = sample * (lmax+1) + l).   lmax <= 64.
+ */
+int jitr_b200_perey_buck_kernels(int nbasis, int lmax, long long n_samples, const double* rgrid, const double* params,
+                                 double zfac, double* out, void* stream);
+
 /* bytes of device scratch jitr_b200_solve_batched needs for this problem (0: none; -1: bad arguments) */
 long long jitr_b200_solve_workspace_bytes(int nbasis, int nch, long long batch, int coeffs);
 
@@ -228,7 +241,12 @@ int jitr_b200_fp64_probe(int which, int iters, int warps_dmma, double* tflops_ou
  * use partial pivoting.  Both give the reference's S within its tolerance (tests/test_gpu_parity.py).
  */
 #define JITR_B200_OPT_SYMMETRIC 0
-#define JITR_B200_OPT_COUNT 1
+/* JITR_B200_OPT_ASSUME_SYMMETRIC_KERNEL (default 0): 1 = the caller vouches that the nonlocal kernels / interaction matrices
+ * handed to jitr_b200_solve_batched are symmetric in (r, r'), as every physical nonlocal potential is; the packed solver then
+ * reads their lower triangle only (half the HBM traffic).  0 = the upper triangle is read too and compared element by element;
+ * a system that is not symmetric is solved by the partial-pivoting kernel instead. */
+#define JITR_B200_OPT_ASSUME_SYMMETRIC_KERNEL 1
+#define JITR_B200_OPT_COUNT 2
 int jitr_b200_set_option(int key, int value);
 /* systems the symmetric path handed to the partial-pivoting path since load (-1: no device) */
 long long jitr_b200_sym_fallback_count(void);

@@ -37,7 +37,7 @@ def sweep_modes():
 
 
 def _units():
-    units = [(name, os.path.join(CSRC, name + ".cu"), []) for name in ("api", "probe", "elastic", "general", "quasielastic", "uq")]
+    units = [(name, os.path.join(CSRC, name + ".cu"), []) for name in ("api", "probe", "elastic", "general", "packed_solve", "nonlocal_gen", "quasielastic", "uq")]
     for mode in sweep_modes():
         units.append((f"sweep_{mode}".replace("-", "g"), os.path.join(CSRC, "sweep_inst.cu"), [f"-DJITR_SWEEP_MODE={mode}"]))
     return units

@@ -15,6 +15,7 @@ LIB_PATH = os.environ.get("JITR_B200_LIB") or os.path.join(_HERE, "_lib", "libji
 OK, ERR_BAD_ARG, ERR_UNSUPPORTED, ERR_CUDA = 0, 1, 2, 3
 STATUS_OK, STATUS_NONFINITE, STATUS_SINGULAR = 0, 1, 2
 OPT_SYMMETRIC = 0
+OPT_ASSUME_SYMMETRIC_KERNEL = 1
 MODEL_SHAPE, MODEL_KDUQ, MODEL_CHUQ, MODEL_LOCAL, MODEL_WLH, MODEL_SHAPE_PAIR = 0, 1, 2, 3, 4, 5
 MODEL_NPARAMS = {MODEL_SHAPE: 17, MODEL_KDUQ: 40, MODEL_CHUQ: 22, MODEL_LOCAL: 15, MODEL_WLH: 46, MODEL_SHAPE_PAIR: 18}
 # per-energy table layout (include/jitr_b200.h)
@@ -44,6 +45,7 @@ SIGNATURES = {
     "jitr_b200_percentiles": (_i, [_p, _ll, _ll, _p, _i, _p, _p]),
     "jitr_b200_qe_overlap": (_i, [_i, _ll, _i, _p, _p, _p, _p, _d, _d, _d, _p, _ll, _ll, _p]),
     "jitr_b200_qe_xs": (_i, [_i, _i, _ll, _p, _p, _d, _p, _p]),
+    "jitr_b200_perey_buck_kernels": (_i, [_i, _i, _ll, _p, _p, _d, _p, _p]),
     "jitr_b200_solve_workspace_bytes": (_ll, [_i, _i, _ll, _i]),
     "jitr_b200_solve_batched": (_i, [_i, _i, _ll, _p, _ll, _p, _p, _p, _p, _p, _i, _p, _p, _ll, _p, _p, _p, _p, _p, _p, _p, _p]),
     "jitr_b200_fp64_probe": (_i, [_i, _i, _i, C.POINTER(_d), C.POINTER(_ll)]),

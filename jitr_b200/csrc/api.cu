@@ -42,7 +42,7 @@ int sm_count() {
     return v;
 }
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
-static std::atomic<int> g_options[JITR_B200_OPT_COUNT] = {{1}};
+static std::atomic<int> g_options[JITR_B200_OPT_COUNT] = {{1}, {0}};
 int option(int key) { return (key >= 0 && key < JITR_B200_OPT_COUNT) ? g_options[key].load() : 0; }
 unsigned long long* fallback_counter() {
     static unsigned long long* ctr[kMaxDevices] = {nullptr};
@@ -77,6 +77,32 @@ unsigned long long* next_work_counter(cudaStream_t st) {
     unsigned long long* c = ring[dev] + (seq.fetch_add(1) % kRing);
     if (cudaMemsetAsync(c, 0, sizeof(unsigned long long), st) != cudaSuccess) return nullptr;
     return c;
+}
+int* defer_buffer(long long n_entries, cudaStream_t st) {
+    constexpr int kRing = 4;
+    static int* buf[kMaxDevices][kRing] = {};
+    static long long cap[kMaxDevices][kRing] = {};
+    static std::atomic<unsigned> seq{0};
+    const int dev = current_device();
+    const int slot = (int)(seq.fetch_add(1) % kRing);
+    int* p = nullptr;
+    {
+        std::lock_guard<std::mutex> lock(g_dev_mutex);
+        if (cap[dev][slot] < n_entries) {
+            if (buf[dev][slot]) cudaFree(buf[dev][slot]);  // (synchronises: nothing in flight uses the old block any more)
+            buf[dev][slot] = nullptr;
+            cap[dev][slot] = 0;
+            const long long want = n_entries + n_entries / 4 + 1024;
+            if (cudaMalloc(&buf[dev][slot], (size_t)(want + 4) * sizeof(int)) != cudaSuccess) {
+                cudaGetLastError();
+                return nullptr;
+            }
+            cap[dev][slot] = want;
+        }
+        p = buf[dev][slot];
+    }
+    if (cudaMemsetAsync(p, 0, 4 * sizeof(int), st) != cudaSuccess) return nullptr;
+    return p;
 }
 }  // namespace jitr
 

@@ -12,5 +12,8 @@ unsigned long long* fallback_counter();
 unsigned long long* fallback_mask();    // jitr_b200_debug_set_fallback_mask (nullptr: off)
 // a zeroed (stream-ordered) device counter for one launch; a ring of 256, so launches in flight on
 // different streams do not share one
-unsigned long long* next_work_counter(cudaStream_t st);  // device counter (lazily allocated), nullptr on failure
+unsigned long long* next_work_counter(cudaStream_t st);
+// per-device scratch for the pairs a packed sweep mode defers: [0] = count (zeroed stream-ordered here), [4 ..] = list of
+// at least n_entries ints; grown on demand (a ring of 4 so that sweeps in flight on different streams do not share one)
+int* defer_buffer(long long n_entries, cudaStream_t st);  // device counter (lazily allocated), nullptr on failure
 }  // namespace jitr

@@ -183,6 +183,27 @@ static int launch_sweep(const SweepArgs& a, cudaStream_t st) {
         case 40: return launch_sweep_mode<PARAMS, 40>(a, st);
         default: break;
     }
+    if ((P == 48 || P == 56 || P == 64) && a.symmetric && a.n_pairs < 0x7fffffffLL && !a.pair_list) {
+        // packed modes: lower triangle only, six systems per SM at P = 64; the pairs they defer (a system failed the
+        // threshold test) are redone by the partial-pivoting modes right behind, on the same stream
+        int* buf = defer_buffer(a.n_pairs, st);
+        if (!buf) return set_cuda_error("elastic sweep: deferred-pairs buffer");
+        SweepArgs p = a;
+        p.defer_count = buf;
+        p.defer_list = buf + 4;
+        int rc = JITR_B200_ERR_UNSUPPORTED;
+        switch (P) {
+            case 48: rc = launch_sweep_mode<PARAMS, 48>(p, st); break;
+            case 56: rc = launch_sweep_mode<PARAMS, 56>(p, st); break;
+            case 64: rc = launch_sweep_mode<PARAMS, 64>(p, st); break;
+            default: break;
+        }
+        if (rc != JITR_B200_OK) return rc;
+        SweepArgs r = a;
+        r.pair_list = buf + 4;
+        r.pair_count = buf;
+        return P + 1 <= 64 ? launch_sweep_mode<PARAMS, -2>(r, st) : launch_sweep_mode<PARAMS, -3>(r, st);
+    }
     if (P + 1 <= 64) return launch_sweep_mode<PARAMS, -2>(a, st);
     return launch_sweep_mode<PARAMS, -3>(a, st);
 }

@@ -10,6 +10,7 @@
 #include "common.cuh"
 #include "jitr_b200.h"
 #include "lu_fast.cuh"
+#include "lu_packed.cuh"
 #include "lu_sym.cuh"
 #include "lu_warp.cuh"
 #include "potentials.cuh"
@@ -114,7 +115,7 @@ struct GenericSolver {
     // d0, d1: diagonal entries of rows lane and lane + 32.  P <= 64: threshold-pivoted symmetric elimination
     // first (lu_sym.cuh), partial pivoting (lu_warp.cuh) when a diagonal entry fails the test or P > 64.
     __device__ __forceinline__ double2 solve(const double2 d0, const double2 d1, int& singular, const bool symmetric,
-                                             unsigned long long* fallbacks, int& fellback) {
+                                             unsigned long long* fallbacks, int& fellback, int& /*deferred*/) {
         assemble(d0, d1);
         if (symmetric && g.P <= 64) {
             int fail = 0;
@@ -216,7 +217,7 @@ struct WarpSolver {
     // Threshold-pivoted symmetric elimination first (lu_sym.cuh); a system whose diagonal fails the
     // threshold test is re-solved with partial pivoting (lu_fast.cuh).  `fallbacks` counts those.
     __device__ __forceinline__ double2 solve(const double2 d0, const double2 d1, int& singular, const bool symmetric,
-                                             unsigned long long* fallbacks, int& fellback) {
+                                             unsigned long long* fallbacks, int& fellback, int& /*deferred*/) {
         const double2 one = make_double2(1.0, 0.0);
         const double2 da = lane < N ? d0 : one, db = lane + 32 < N ? d1 : one;
         if (symmetric) {
@@ -243,6 +244,104 @@ struct WarpSolver {
         return corner;
     }
 };
+
+// ---------------------------------------------------------------------------------------------
+// Packed modes, P = 48 / 56 / 64 (BASELINE config 3: N = 60): the lower triangle of  That + diag(d)  alone is
+// assembled in the warp's region (lu_packed.cuh: 38 KB instead of 67.6 KB at P = 64 -> six systems per SM instead of
+// three) and eliminated in place by the threshold-pivoted LDL^T.  That stays in global memory (28.8 KB, read-only,
+// L1/L2 resident) and is fetched one block row -- sixteen independent loads per lane -- at a time.  A system that fails
+// the threshold test defers its whole (sample, energy) pair to the partial-pivoting modes.
+// ---------------------------------------------------------------------------------------------
+template <int PT>
+struct PackedSweepPlan {
+    using G = PackedGeom<PT>;
+    static constexpr int kShared = 2 * PT * 8;  // b, 1/x^2
+    static constexpr int kFit = (kSweepMaxSmem - kShared) / (G::WARP_ELEMS * 16);
+    static constexpr int kMaxWarps = kFit > 16 ? 16 : kFit;
+    static constexpr int kThreads = kMaxWarps * 32;
+    static bool supports(int N) { return N > PT - 8 && N <= PT; }
+    static int warps(int) { return kMaxWarps; }
+    static int smem(int, int w) { return kShared + w * G::WARP_ELEMS * 16; }
+};
+template <int PT>
+struct PackedSolver {
+    using G = PackedGeom<PT>;
+    unsigned wofs;
+    int N, lane;
+    const double* That;
+    __device__ __forceinline__ void init(unsigned char* smem, const double* That_, const double* bvec, const double* mesh_x,
+                                         int N_, int nwarps, int warp, int lane_) {
+        N = N_;
+        lane = lane_;
+        That = That_;
+        wofs = (unsigned)warp * G::WARP_ELEMS * 16;
+        double* b = reinterpret_cast<double*>(smem + (size_t)nwarps * G::WARP_ELEMS * 16);
+        double* c = b + PT;
+        for (int i = threadIdx.x; i < PT; i += blockDim.x) {
+            b[i] = i < N ? bvec[i] : 0.0;
+            c[i] = i < N ? 1.0 / (mesh_x[i] * mesh_x[i]) : 0.0;
+        }
+    }
+    __device__ __forceinline__ const double* tail() const {
+        extern __shared__ __align__(16) unsigned char smem_raw[];
+        return reinterpret_cast<const double*>(smem_raw + (size_t)(blockDim.x >> 5) * G::WARP_ELEMS * 16);
+    }
+    __device__ __forceinline__ void centrifugal(double& c0, double& c1) const {
+        const double* c = tail() + PT;
+        c0 = c[lane];
+        c1 = c[lane + 32 < PT ? lane + 32 : 0];
+    }
+    __device__ __forceinline__ double2 solve(const double2 d0, const double2 d1, int& /*singular*/, const bool /*symmetric*/,
+                                             unsigned long long* fallbacks, int& /*fellback*/, int& deferred) {
+        extern __shared__ __align__(16) unsigned char smem_raw[];
+        double2* M = reinterpret_cast<double2*>(smem_raw + wofs);
+        const double* b = tail();
+        const double2 dd[2] = {d0, d1};
+        // ---- lower triangle of That + diag(d), identity padding, y = b
+#pragma unroll 1
+        for (int tr = 0; tr < G::NB; ++tr) {
+            double t[8][2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int c = lane + 32 * h;
+                if (32 * h <= 8 * tr + 7) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int r = 8 * tr + i;
+                        t[i][h] = (c < r && r < N) ? __ldg(That + r * N + c) : 0.0;
+                    }
+                }
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int c = lane + 32 * h;
+                if (32 * h <= 8 * tr + 7) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int r = 8 * tr + i;
+                        if (c <= r) M[G::off(tr) + i * G::ld(tr) + c] = (c == r) ? (r < N ? dd[h] : make_double2(1.0, 0.0)) : make_double2(t[i][h], 0.0);
+                    }
+                }
+            }
+        }
+        for (int r = lane; r < PT; r += 32) M[G::rhs(r)] = make_double2(b[r], 0.0);
+        __syncwarp();
+        int bad = 0;
+        const double2 corner = packed_ldlt<PT>(M, lane, bad);
+        __syncwarp();
+        if (bad) {
+            if (lane == 0 && fallbacks) atomicAdd(fallbacks, 1ULL);
+            deferred = 1;
+        }
+        return corner;
+    }
+};
+template <> struct SweepPlan<48> : PackedSweepPlan<48> {};
+template <> struct SweepPlan<56> : PackedSweepPlan<56> {};
+template <> struct SweepPlan<64> : PackedSweepPlan<64> {};
+template <> struct WarpSolver<48> : PackedSolver<48> {};
+template <> struct WarpSolver<56> : PackedSolver<56> {};
+template <> struct WarpSolver<64> : PackedSolver<64> {};
 
 // ---------------------------------------------------------------------------------------------
 // Loose lock step of the warps of a CTA: warp w may start iteration it only after EVERY warp has
@@ -335,7 +434,10 @@ __global__ void __launch_bounds__(SweepPlan<MODE>::kThreads, 1) elastic_sweep_ke
     // warp a fixed subset of 4 of the 64 energies -- up to 21 % of a warp's time was an idle tail.
     auto next_pair = [&]() -> long long {
         unsigned long long v = 0;
-        if (lane == 0) v = atomicAdd(A.work_counter, 1ULL);
+        if (lane == 0) {
+            v = atomicAdd(A.work_counter, 1ULL);
+            if (A.pair_list) v = v < (unsigned long long)*A.pair_count ? (unsigned long long)A.pair_list[v] : (unsigned long long)A.n_pairs;
+        }
         return (long long)__shfl_sync(0xffffffffu, v, 0);
     };
     long long pair = next_pair();
@@ -426,9 +528,14 @@ __global__ void __launch_bounds__(SweepPlan<MODE>::kThreads, 1) elastic_sweep_ke
         const double2 dd0 = make_double2(d0.x + ll1 * cent0 + ls * so0.x, d0.y + ls * so0.y);
         const double2 dd1 = make_double2(d1.x + ll1 * cent1 + ls * so1.x, d1.y + ls * so1.y);
         // corner = -b^T (a^2 A)^-1 b = -R
-        int fellback = 0;
-        const double2 corner = solver.solve(dd0, dd1, singular, A.symmetric != 0, A.fallbacks, fellback);
-        if (fellback && A.fallback_mask && lane == 0) atomicOr(A.fallback_mask + pair, 1ULL << (2 * l + jj));
+        int fellback = 0, deferred = 0;
+        const double2 corner = solver.solve(dd0, dd1, singular, A.symmetric != 0, A.fallbacks, fellback, deferred);
+        if ((fellback | deferred) && A.fallback_mask && lane == 0) atomicOr(A.fallback_mask + pair, 1ULL << (2 * l + jj));
+        bool pair_done = false;
+        if (deferred) {  // warp-uniform: the pair is abandoned here and redone by the partial-pivoting modes
+            if (lane == 0) A.defer_list[atomicAdd(A.defer_count, 1)] = (int)pair;
+            pair_done = true;
+        } else {
         const double2* as = A.asym + ((size_t)e * L1 + l) * 4;  // (after the solve: fewer live registers)
         const double2 Hp = as[0], Hm = as[1], Hpp = as[2], Hmp = as[3];
         const double a = A.etab[(size_t)e * JITR_B200_ET_STRIDE + JITR_B200_ET_A];
@@ -444,7 +551,6 @@ __global__ void __launch_bounds__(SweepPlan<MODE>::kThreads, 1) elastic_sweep_ke
         // |1 - S| < tol  (xs/elastic.py:178-181), compared in squares
         const double e1 = 1.0 - S.x;
         const bool small = fma(e1, e1, S.y * S.y) < A.tol * A.tol;
-        bool pair_done = false;
         if (jj == 0) {
             plus_small = small;
             if (lane == 0) Sp_out[l] = S;
@@ -467,15 +573,20 @@ __global__ void __launch_bounds__(SweepPlan<MODE>::kThreads, 1) elastic_sweep_ke
             l += 1;
             jj = 0;
         }
+        }  // !deferred
         if (__any_sync(0xffffffffu, pair_done)) {
-            for (int q = nl + lane; q <= A.lmax; q += 32) {
-                Sp_out[q] = zero2;
-                Sm_out[q] = zero2;
-            }
-            if (lane == 0) {
-                A.nl_out[pair] = nl;
-                A.status[pair] =
-                    nonfinite ? JITR_B200_STATUS_NONFINITE : (singular ? JITR_B200_STATUS_SINGULAR : JITR_B200_STATUS_OK);
+            if (!deferred) {
+                double2* Sp_out = A.S_out + (size_t)pair * 2 * L1;
+                double2* Sm_out = Sp_out + L1;
+                for (int q = nl + lane; q <= A.lmax; q += 32) {
+                    Sp_out[q] = zero2;
+                    Sm_out[q] = zero2;
+                }
+                if (lane == 0) {
+                    A.nl_out[pair] = nl;
+                    A.status[pair] =
+                        nonfinite ? JITR_B200_STATUS_NONFINITE : (singular ? JITR_B200_STATUS_SINGULAR : JITR_B200_STATUS_OK);
+                }
             }
             pair = next_pair();
             active = pair < A.n_pairs;

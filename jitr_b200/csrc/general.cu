@@ -12,37 +12,12 @@
 
 #include "common.cuh"
 #include "jitr_b200.h"
+#include "general_decl.cuh"
 #include "lu_warp.cuh"
 
 namespace jitr {
 
-struct GenArgs {
-    int N, nch, n;  // n = N * nch
-    long long batch;
-    const double2* free_matrix;
-    long long free_stride;
-    const double2* local;
-    const double2* nonlocal_;
-    const double2* interaction;
-    const double* wsqrt;
-    const double* sys;
-    int sys_stride;
-    const double* bvec;
-    const double2* asym;
-    long long asym_stride;
-    const double* weights;
-    double2* R;
-    double2* S;
-    double2* uext;
-    double2* coeffs;
-    double2* workspace;
-    int* status;
-    const int* symflag;            // device int: 0 when the shared free matrix is symmetric (NULL: do not try the symmetric path)
-    unsigned long long* fallbacks;  // systems the symmetric path handed to partial pivoting
-};
-
 constexpr int kGenThreads = 256;
-constexpr int kMaxCh = 16;
 
 // R (in small[0 .. nch^2)) -> Z+-, S = Z+^-1 Z-, u'_ext; writes R, S, uext, status of system sysi.  Called by the
 // whole CTA after a barrier that made R visible; ends with a barrier (ue = small + 3 nch^2 is then readable).
@@ -897,7 +872,9 @@ __global__ void __launch_bounds__(kBlkThreads, 512 / kBlkThreads) block_solve_ke
     const double2 zero2 = make_double2(0.0, 0.0);
 
     BLK_PH_INIT
-    for (long long sysi = blockIdx.x; sysi < A.batch; sysi += gridDim.x) {
+    const long long nsys = A.sys_list ? (long long)*A.sys_count : A.batch;
+    for (long long isys = blockIdx.x; isys < nsys; isys += gridDim.x) {
+        const long long sysi = A.sys_list ? (long long)A.sys_list[isys] : isys;
         const double* sy = A.sys + (size_t)sysi * A.sys_stride;
         const double a = sy[0], E0 = sy[1], k0s = sy[2];
         const double2* F = A.free_matrix + (size_t)sysi * A.free_stride;
@@ -1308,14 +1285,24 @@ static int launch_block_solve_t(const GenArgs& a, const BlkGeom& g, cudaStream_t
         return set_cuda_error("block_solve occupancy");
     if (per_sm > blk_ctas_per_sm(g)) per_sm = blk_ctas_per_sm(g);  // the workspace holds that many slabs per SM
     long long blocks = (long long)sm_count() * per_sm;
-    if (blocks > a.batch) blocks = a.batch;
+    if (blocks > a.batch) blocks = a.batch;  // (with a deferred-systems list: the list is at most the batch)
     block_solve_kernel<T><<<(unsigned)blocks, T, smem, st>>>(a, g);
     count_launch();
     if (cudaGetLastError() != cudaSuccess) return set_cuda_error("block_solve launch");
     return JITR_B200_OK;
 }
 
-static int launch_block_solve(const GenArgs& a_in, cudaStream_t st) {
+// *flag (first int of the workspace) = 0 when the shared free matrix is symmetric
+static int launch_symcheck(const GenArgs& a, int* flag, cudaStream_t st) {
+    if (cudaMemsetAsync(flag, 0, sizeof(int), st) != cudaSuccess) return set_cuda_error("solve_batched symmetry flag");
+    const int nn = a.n * a.n;
+    symcheck_kernel<<<(nn + 255) / 256, 256, 0, st>>>(a.free_matrix, a.n, flag);
+    count_launch();
+    if (cudaGetLastError() != cudaSuccess) return set_cuda_error("symcheck launch");
+    return JITR_B200_OK;
+}
+
+static int launch_block_solve(const GenArgs& a_in, cudaStream_t st, const bool flag_ready = false) {
     GenArgs a = a_in;
     const BlkGeom g = blk_geom(a.n, a.nch);
     // symmetric path: one free matrix for the whole batch, checked here; the potentials are checked per system in the kernel
@@ -1323,14 +1310,26 @@ static int launch_block_solve(const GenArgs& a_in, cudaStream_t st) {
     a.fallbacks = nullptr;
     if (option(JITR_B200_OPT_SYMMETRIC) && a.free_stride == 0) {
         int* flag = reinterpret_cast<int*>(a.workspace);
-        if (cudaMemsetAsync(flag, 0, sizeof(int), st) != cudaSuccess) return set_cuda_error("block_solve symmetry flag");
-        const int nn = a.n * a.n;
-        symcheck_kernel<<<(nn + 255) / 256, 256, 0, st>>>(a.free_matrix, a.n, flag);
-        count_launch();
+        if (!flag_ready) {
+            const int rc = launch_symcheck(a, flag, st);
+            if (rc != JITR_B200_OK) return rc;
+        }
         a.symflag = flag;
         a.fallbacks = fallback_counter();
     }
     return blk_threads(g) == 128 ? launch_block_solve_t<128>(a, g, st) : launch_block_solve_t<256>(a, g, st);
+}
+
+// bytes of the slab part of the workspace (header + one slab per resident CTA)
+static long long blk_slab_bytes(const BlkGeom& g, long long batch) {
+    int sms = sm_count();
+    if (sms <= 0) sms = 148;
+    long long ctas = (long long)sms * blk_ctas_per_sm(g);
+    if (ctas > batch) ctas = batch;
+    return (ctas * g.PR * g.PC + kBlkHeader) * 16;
+}
+static bool packed_path(int nbasis, int nch, int coeffs) {
+    return nch == 1 && !coeffs && packed_solve_supported(nbasis) && option(JITR_B200_OPT_SYMMETRIC) != 0;
 }
 
 template <int MAXNS>
@@ -1367,16 +1366,12 @@ extern "C" int jitr_b200_debug_block_phases(unsigned long long* out16, int reset
 
 extern "C" long long jitr_b200_solve_workspace_bytes(int nbasis, int nch, long long batch, int coeffs) {
     if (nbasis < 1 || nch < 1 || nch > kMaxCh || batch < 0) return -1;
-    if (nch == 1 && !coeffs && ((nbasis + 7) & ~7) <= JITR_WARP_SOLVE_MAXP) return 0;  // warp-per-system: shared memory only
     const long long n = (long long)nbasis * nch;
     const BlkGeom g = blk_geom((int)n, nch);
-    if (g.PR <= kBlkMaxRows) {  // one slab per resident CTA
-        int sms = sm_count();
-        if (sms <= 0) sms = 148;
-        long long ctas = (long long)sms * blk_ctas_per_sm(g);
-        if (ctas > batch) ctas = batch;
-        return (ctas * g.PR * g.PC + kBlkHeader) * 16;
-    }
+    // packed symmetric path: the slabs of the partial-pivoting kernel (for the systems it defers) + the deferred list
+    if (packed_path(nbasis, nch, coeffs)) return blk_slab_bytes(g, batch) + 16 + ((batch * 4 + 15) & ~15LL);
+    if (nch == 1 && !coeffs && ((nbasis + 7) & ~7) <= JITR_WARP_SOLVE_MAXP) return 0;  // warp-per-system: shared memory only
+    if (g.PR <= kBlkMaxRows) return blk_slab_bytes(g, batch);  // one slab per resident CTA
     const long long in_smem = (n * (n + nch) + 2 * n + nch) * 16 + 20000;
     return in_smem > 232448 ? batch * n * (n + nch) * 16 : 0;
 }
@@ -1405,6 +1400,23 @@ extern "C" int jitr_b200_solve_batched(int nbasis, int nch, long long batch, con
     a.uext = reinterpret_cast<double2*>(uext); a.coeffs = reinterpret_cast<double2*>(coeffs);
     a.workspace = reinterpret_cast<double2*>(workspace); a.status = status;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // single channel, no coefficients, one shared free matrix, P <= 64: packed symmetric LDL^T, one warp per system, the
+    // nonlocal kernel staged by bulk-async copies; what it defers goes to the partial-pivoting CTA-per-system kernel
+    if (packed_path(nbasis, nch, coeffs != nullptr) && free_stride == 0 && workspace) {
+        const BlkGeom g = blk_geom(a.n, nch);
+        int* flag = reinterpret_cast<int*>(workspace);
+        int* defer_count = reinterpret_cast<int*>(reinterpret_cast<char*>(workspace) + blk_slab_bytes(g, batch));
+        int* defer_list = defer_count + 4;
+        int rc = launch_symcheck(a, flag, st);
+        if (rc != JITR_B200_OK) return rc;
+        if (cudaMemsetAsync(defer_count, 0, 16, st) != cudaSuccess) return set_cuda_error("solve_batched deferred-systems counter");
+        a.fallbacks = fallback_counter();
+        rc = launch_packed_solve(a, flag, option(JITR_B200_OPT_ASSUME_SYMMETRIC_KERNEL) ? 0 : 1, defer_list, defer_count, st);
+        if (rc != JITR_B200_OK) return rc;
+        a.sys_list = defer_list;
+        a.sys_count = defer_count;
+        return launch_block_solve(a, st, true);
+    }
     // single channel, no coefficients, small P: warp-per-system blocked LU
     if (nch == 1 && !coeffs && ((nbasis + 7) & ~7) <= JITR_WARP_SOLVE_MAXP) {
         static_assert(JITR_WARP_SOLVE_MAXP + 1 <= 64, "warp_solve_kernel<2>: at most two row slots per lane");

@@ -1,0 +1,209 @@
+// Packed symmetric path: complex-symmetric LDL^T of a system whose LOWER TRIANGLE ALONE lives in shared memory.
+//
+// The fast paths of lu_sym.cuh keep a full n x n Schur complement per system (the unscaled pivot rows sit in the upper
+// triangle), which is what limits the fused sweep to 3 resident systems per SM at N = 60 (BASELINE config 3) and is why
+// the nonlocal solve (config 4) went through an L2 slab.  Here a system is stored by 8-row blocks, block row tr holding
+// the columns 0 .. 8 tr + 7 of its rows and nothing right of the diagonal tile:
+//
+//      row r = 8 tr + i  ->  elements  off(tr) + i * ld(tr) + c,   c = 0 .. 8 tr + 7,   ld(tr) = 8 tr + 9  (odd),
+//      off(tr) = 32 tr^2 + 40 tr,      the pad element  c = 8 tr + 8  of row r holds the right-hand side y_r.
+//
+// P = 64: 2 368 elements = 37.9 KB per system instead of 67.6 KB -- six systems per SM.  Every row stride is odd, so the
+// one-row-per-lane column walks of the panel phase and the (rho-permuted) 128-bit accumulator accesses of the trailing
+// update stay bank-conflict free exactly as in lu_sym.cuh.
+//
+// Elimination (threshold pivoting on the diagonal, as lu_sym.cuh):
+//   * panel of 8 columns in registers, one row per lane (two slots while more than 32 rows are alive).  The UNSCALED
+//     column entries w_ik are written back in place; the pivot row is the transposed pivot column and is read back from
+//     the rows of the diagonal block as shared-memory broadcasts.  Nothing is ever stored above the diagonal.
+//   * the threshold test is applied to the multipliers themselves: |Re l|, |Im l| <= 2^JITR_SYM_TAU_LOG2 for every row
+//     below the pivot (equivalent to |a_kk| >= max_i |a_ik| / 64, without the REDUX of the column maximum), checked on
+//     the high words (integer pipe), accumulated per lane and voted on ONCE per system.
+//   * trailing update of the lower tiles on DMMA m8n8k4 in the real representation of the complex product (fragment
+//     mapping of lu_warp.cuh).  A = -L is formed on the fly from the stored w and the panel's eight reciprocals
+//     (one DMUL + one DFMA per fragment element), B = W^T comes straight from the stored rows: no second panel buffer.
+//   * the border: corner = -sum_k y_k^2 / d_k.
+// A system that fails the test is reported to the caller (the fused sweep defers its (sample, energy) pair, the batched
+// solve its system, to the partial-pivoting kernels).
+#pragma once
+#include "lu_sym.cuh"
+
+namespace jitr {
+
+template <int P>
+struct PackedGeom {
+    static_assert(P % 8 == 0 && P >= 8 && P <= 64, "packed path: 8 <= P <= 64, two row slots per lane");
+    static constexpr int NB = P / 8;
+    __host__ __device__ static constexpr int ld(int tr) { return 8 * tr + 9; }
+    __host__ __device__ static constexpr int off(int tr) { return 32 * tr * tr + 40 * tr; }
+    __host__ __device__ static constexpr int row(int r) { return off(r >> 3) + (r & 7) * ld(r >> 3); }
+    __host__ __device__ static constexpr int rhs(int r) { return row(r) + 8 * (r >> 3) + 8; }  // pad element = y_r
+    static constexpr int SIZE = off(NB);       // complex elements of the packed matrix (incl. the y slots)
+    static constexpr int WARP_ELEMS = SIZE + 8;  // + the eight reciprocals of the current panel
+};
+
+// high words of |re|, |im| beyond 2^TAU (or NaN / Inf): the multiplier fails the threshold test
+__device__ __forceinline__ bool mult_too_large(const double2 l) {
+    constexpr int kLim = 0x3ff00000 + (JITR_SYM_TAU_LOG2 << 20);  // high word of 2^TAU
+    const int hx = __double2hiint(l.x) & 0x7fffffff, hy = __double2hiint(l.y) & 0x7fffffff;
+    // |v| <= 2^TAU  <=>  hi < kLim, or hi == kLim with a zero mantissa; the cheap form hi >= kLim + 1 lets (2^TAU, 2^TAU(1+2^-20)) pass
+    return max(hx, hy) > kLim;
+}
+
+// One panel (columns 8 kb .. 8 kb + 7), rows i = 32 s + lane relative to the panel start, nrows alive.
+template <int P, int NS>
+__device__ __forceinline__ void packed_panel(double2* __restrict__ M, double2* __restrict__ rinv_s, const int kb,
+                                             const int lane, double2& cacc, int& bad) {
+    using G = PackedGeom<P>;
+    const int J0 = 8 * kb, nrows = P - J0;
+    const int ldk = G::ld(kb);
+    const int dbase = G::off(kb) + J0;  // entry (J0 + j, J0 + k) of the diagonal block: dbase + j * ldk + k
+    int rb[NS], ry[NS];
+    double2 p[NS][9];
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+        const int i = 32 * s + lane;
+        const int ic = i < nrows ? i : 0;
+        const int tr = kb + (ic >> 3);
+        rb[s] = G::off(tr) + (ic & 7) * G::ld(tr) + J0;
+        ry[s] = rb[s] - J0 + 8 * tr + 8;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) p[s][j] = M[rb[s] + j];
+        p[s][8] = M[ry[s]];
+    }
+    double2 ysave = make_double2(0.0, 0.0), rsave = make_double2(0.0, 0.0);
+#pragma unroll
+    for (int kk = 0; kk < 8; ++kk) {
+        const double2 myrinv = crecip_fast(p[0][kk]);  // speculative: only lane kk's is used
+        if (lane == kk) {
+            const int m = max(__double2hiint(p[0][kk].x) & 0x7fffffff, __double2hiint(p[0][kk].y) & 0x7fffffff);
+            if (m < 0x00100000 || m >= 0x7ff00000) bad = 1;  // zero, denormal, Inf or NaN pivot
+            ysave = p[0][8];
+            rsave = myrinv;
+        }
+        // the unscaled column entries, in place (rows below the pivot): W of the trailing update, and the pivot row
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            const int i = 32 * s + lane;
+            if (i > kk && i < nrows) M[rb[s] + kk] = p[s][kk];
+        }
+        const double2 rinv = shfl2(myrinv, kk);
+        double2 u[9];
+        u[8] = shfl2(p[0][8], kk);
+        __syncwarp();
+#pragma unroll
+        for (int j = kk + 1; j < 8; ++j) u[j] = M[dbase + j * ldk + kk];  // pivot row = transposed pivot column
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            const int i = 32 * s + lane;
+            const double2 l = cmul(p[s][kk], rinv);
+            if (i > kk && i < nrows && mult_too_large(l)) bad = 1;
+#pragma unroll
+            for (int j = kk + 1; j < 9; ++j) cfnma(p[s][j], l, u[j]);
+        }
+    }
+    // corner -= sum_k y_k^2 / d_k : one term per lane k < 8
+    double2 term = cmul(cmul(ysave, rsave), ysave);
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+        term.x += __shfl_xor_sync(kFull, term.x, o);
+        term.y += __shfl_xor_sync(kFull, term.y, o);
+    }
+    const double2 tot = shfl2(term, 0);
+    cacc.x -= tot.x;
+    cacc.y -= tot.y;
+    if (lane < 8) rinv_s[lane] = rsave;
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+        const int i = 32 * s + lane;
+        if (i >= 8 && i < nrows) M[ry[s]] = p[s][8];
+    }
+}
+
+// lower tiles (tr, q), kb < q <= tr < NB, -= L[tr] W[q]^T  after panel kb; tile columns in blocks of three
+template <int P>
+__device__ __forceinline__ void packed_trailing(double2* __restrict__ M, const double2* __restrict__ rinv_s, const int kb,
+                                                const int lane) {
+    using G = PackedGeom<P>;
+    constexpr int NB = G::NB;
+    const int J0 = 8 * kb;
+    const int fr = lane >> 2, fk = lane & 3;
+    const int rho = (fr >> 1) + 4 * (fr & 1);
+    const int part = fk & 1, pn = fr & 1;
+    const int bflip = (part & (pn ^ 1)) ? 0x80000000 : 0;
+    const int kcol = J0 + 4 * (fk >> 1);
+    const double* Md = reinterpret_cast<const double*>(M);
+    // a[s] = -(component `part` of w * rinv) = -(w.x c1 + w.y c2)
+    double c1[4], c2[4];
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        const double2 r = rinv_s[4 * (fk >> 1) + s];
+        c1[s] = part ? r.y : r.x;
+        c2[s] = part ? r.x : -r.y;
+    }
+#pragma unroll 1
+    for (int q0 = kb + 1; q0 < NB; q0 += 3) {
+        double b[3][2][4];
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+            if (q0 + q < NB) {
+                const int qb = G::off(q0 + q) + (fr >> 1) * G::ld(q0 + q) + kcol;
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+#pragma unroll
+                    for (int s = 0; s < 4; ++s) {
+                        const double v = Md[2 * (qb + 4 * h * G::ld(q0 + q) + s) + (part ^ pn)];
+                        b[q][h][s] = __hiloint2double(__double2hiint(v) ^ bflip, __double2loint(v));
+                    }
+            }
+#pragma unroll 1
+        for (int tr = q0; tr < NB; ++tr) {
+            const int rbase = G::off(tr) + rho * G::ld(tr);
+            double a[4];
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+                const double2 w = M[rbase + kcol + s];
+                a[s] = fma(-w.x, c1[s], -(w.y * c2[s]));
+            }
+            double2* Crow = M + rbase + 8 * q0 + fk;
+#pragma unroll
+            for (int q = 0; q < 3; ++q)
+                if (q0 + q <= tr) {  // lower triangle (diagonal tiles in full)
+                    double2 c0 = Crow[8 * q], c1v = Crow[8 * q + 4];
+#pragma unroll
+                    for (int s = 0; s < 4; ++s) {
+                        dmma884(c0.x, c0.y, a[s], b[q][0][s]);
+                        dmma884(c1v.x, c1v.y, a[s], b[q][1][s]);
+                    }
+                    Crow[8 * q] = c0;
+                    Crow[8 * q + 4] = c1v;
+                }
+        }
+    }
+}
+
+// In-place elimination of a packed system (lower triangle + y slots).  Returns -y^T D^-1 y = -b^T A^-1 b on every lane;
+// bad != 0 (warp-uniform on return): a pivot failed the threshold test, the value is meaningless.
+template <int P>
+__device__ __forceinline__ double2 packed_ldlt(double2* __restrict__ M, const int lane, int& bad) {
+    using G = PackedGeom<P>;
+    double2* rinv_s = M + G::SIZE;
+    double2 cacc = make_double2(0.0, 0.0);
+    int mybad = 0;
+    JITR_PH_INIT
+#pragma unroll 1
+    for (int kb = 0; kb < G::NB; ++kb) {
+        if (P - 8 * kb > 32) packed_panel<P, 2>(M, rinv_s, kb, lane, cacc, mybad);
+        else packed_panel<P, 1>(M, rinv_s, kb, lane, cacc, mybad);
+        JITR_PH(0)
+        if (kb == G::NB - 1) break;
+        __syncwarp();
+        packed_trailing<P>(M, rinv_s, kb, lane);
+        __syncwarp();
+        JITR_PH(2)
+    }
+    bad = __any_sync(kFull, mybad) ? 1 : 0;
+    return cacc;
+}
+
+}  // namespace jitr

@@ -1,0 +1,258 @@
+// Single-channel batched R-matrix solve on a packed lower triangle in shared memory (BASELINE config 4: N = 60, one full
+// N x N complex nonlocal kernel per system).  Replaces, for complex-symmetric systems, the L2-slab CTA-per-system kernel of
+// general.cu:  rmatrix/rmatrix.py:126-246 (Solver.interaction_matrix / Solver.solve), quadrature/kernel.py:197-214
+// (nonlocal weighting), rmatrix/core.py:7-60.
+//
+// One WARP per system, PackedGeom<P>::WARP_ELEMS * 16 B of shared memory each (38 KB at P = 64: six systems per SM):
+//   1. the lower triangle of the system's nonlocal kernel (or interaction matrix) is fetched row by row with bulk-async
+//      copies (cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes: row r = (r + 1) * 16 bytes straight into
+//      its packed position), completion on the warp's mbarrier -- the other warps of the SM keep eliminating meanwhile, so
+//      the HBM stream (half of N^2 x 16 B per system) hides behind their FP64 work without a second buffer;
+//   2. one pass forms  A = F + sqrt(w_n w_m) V (a / k0) / k0 / E0 (+ diag V_loc / E0)  in place and, unless the caller
+//      vouches for it, checks V[n][m] == V[m][n] against the upper triangle read straight from global memory;
+//   3. threshold-pivoted LDL^T in place (lu_packed.cuh), R = b^T A^-1 b / a^2, S, u'_ext.
+// Systems that are not symmetric or fail the threshold test are appended to a list and solved by the partial-pivoting
+// kernel of general.cu afterwards (same launch sequence, no host round trip).
+#include <cuda_runtime.h>
+#include <math.h>
+
+#include "common.cuh"
+#include "general_decl.cuh"
+#include "jitr_b200.h"
+#include "lu_packed.cuh"
+
+namespace jitr {
+
+namespace {
+
+constexpr int kPackedMaxSmem = 232448;
+
+template <int P>
+struct PackedPlan {
+    using G = PackedGeom<P>;
+    static constexpr int kTail = 2 * P * 8 + 16 * 8;  // b, wsqrt (doubles) + up to 16 mbarriers
+    static constexpr int kFit = (kPackedMaxSmem - kTail) / (G::WARP_ELEMS * 16);
+    static constexpr int kWarps = kFit > 16 ? 16 : kFit;
+    static constexpr int kThreads = kWarps * 32;
+    static constexpr int kSmem = kWarps * G::WARP_ELEMS * 16 + kTail;
+};
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    unsigned done;
+    do {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done)
+                     : "r"(bar), "r"(parity)
+                     : "memory");
+    } while (!done);
+}
+
+template <int P>
+__global__ void __launch_bounds__(PackedPlan<P>::kThreads, 1)
+packed_solve_kernel(const GenArgs A, const int* __restrict__ symflag, const int check_symmetry,
+                    unsigned long long* __restrict__ work_counter, int* __restrict__ defer_list, int* __restrict__ defer_count) {
+    using G = PackedGeom<P>;
+    using Plan = PackedPlan<P>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int N = A.N;
+    const int warp = __shfl_sync(kFull, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
+    double2* M = reinterpret_cast<double2*>(smem_raw) + (size_t)warp * G::WARP_ELEMS;
+    double* bs = reinterpret_cast<double*>(smem_raw + (size_t)Plan::kWarps * G::WARP_ELEMS * 16);
+    double* ws = bs + P;
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(ws + P);
+    for (int i = threadIdx.x; i < P; i += blockDim.x) {
+        bs[i] = i < N ? A.bvec[i] : 0.0;
+        ws[i] = (i < N && A.wsqrt) ? A.wsqrt[i] : 0.0;
+    }
+    const unsigned bar = smem_u32(bars + warp);
+    if (lane == 0) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    const bool free_ok = *symflag == 0;  // the shared free matrix is symmetric
+    const double2* Vsrc_base = A.interaction ? A.interaction : A.nonlocal_;
+    const double2 zero2 = make_double2(0.0, 0.0);
+    unsigned parity = 0;
+    // systems are handed out one ahead: while a warp eliminates system i, the matrix of its next system is on its way to L2
+    // (cp.async.bulk.prefetch.L2), so the staging copies and the symmetry walk of the next round find it there
+    auto grab = [&]() -> long long {
+        long long v = 0;
+        if (lane == 0) {
+            v = (long long)atomicAdd(work_counter, 1ULL);
+            if (v < A.batch && Vsrc_base) {
+                const unsigned long long src = (unsigned long long)(Vsrc_base + (size_t)v * N * N);
+                const unsigned bytes = (unsigned)(N * N) * 16u;
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+            }
+        }
+        return __shfl_sync(kFull, v, 0);
+    };
+    long long next = grab();
+    while (true) {
+        const long long sysi = next;
+        if (sysi >= A.batch) break;
+        next = grab();
+        bool defer = !free_ok;
+        const double* sy = A.sys + (size_t)sysi * A.sys_stride;
+        const double a = sy[0], E0 = sy[1], k0 = sy[2];
+        const double nl_scale = A.interaction ? 1.0 : (a / k0) / k0 / E0;  // kernel.py:202 (x radius), rmatrix.py:175-178 (/k0, /E0)
+        const double2* Vsrc = Vsrc_base ? Vsrc_base + (size_t)sysi * N * N : nullptr;
+        if (!defer && Vsrc) {
+            // ---- stage the lower triangle: one bulk-async copy per row, all of them in flight at once
+            __syncwarp();
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the warp's earlier accesses to its region come first
+            if (lane == 0) {
+                const unsigned bytes = (unsigned)(N * (N + 1) / 2) * 16u;
+                asm volatile("{ .reg .b64 st; mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1; }" ::"r"(bar), "r"(bytes) : "memory");
+            }
+            __syncwarp();
+            for (int r = lane; r < N; r += 32) {
+                const unsigned dst = smem_u32(M + G::row(r));
+                const unsigned long long src = (unsigned long long)(Vsrc + (size_t)r * N);
+                const unsigned bytes = (unsigned)(r + 1) * 16u;
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                             "r"(bytes), "r"(bar)
+                             : "memory");
+            }
+            mbar_wait(bar, parity);
+            parity ^= 1u;
+        }
+        if (!defer) {
+            // ---- A = F + scaled V (+ local on the diagonal), in place, eight rows (one block row) per step so that every
+            // lane has up to sixteen independent global loads in flight (lane = column: coalesced rows of F; the upper
+            // triangle of V is walked by columns, eight consecutive elements = one 128-byte line per lane)
+            const double2* F = A.free_matrix;
+            const double2* Vloc = (!A.interaction && A.local) ? A.local + (size_t)sysi * N : nullptr;
+            bool asym = false;
+            double2 vl[2];  // local potential / E0 on this lane's two diagonal entries
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int c = lane + 32 * h;
+                vl[h] = zero2;
+                if (Vloc && c < N) {
+                    const double2 w = Vloc[c];
+                    vl[h] = make_double2(w.x / E0, w.y / E0);
+                }
+            }
+            const bool check = Vsrc && check_symmetry;
+#pragma unroll 1
+            for (int tr = 0; tr < G::NB; ++tr) {
+                double2 f[8][2], t[8][2];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int c = lane + 32 * h;
+                    if (32 * h <= 8 * tr + 7) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int r = 8 * tr + i;
+                            f[i][h] = (c <= r && r < N) ? F[(size_t)r * N + c] : make_double2(c == r ? 1.0 : 0.0, 0.0);  // identity padding
+                            t[i][h] = (check && c < r && r < N) ? Vsrc[(size_t)c * N + r] : zero2;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int c = lane + 32 * h;
+                    if (32 * h <= 8 * tr + 7) {
+                        const double wc = ws[c < P ? c : 0] * nl_scale;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int r = 8 * tr + i;
+                            if (c <= r) {
+                                double2* e = M + G::off(tr) + i * G::ld(tr) + c;
+                                double2 v = f[i][h];
+                                if (r < N) {
+                                    if (Vsrc) {
+                                        const double2 w = *e;
+                                        if (check && c < r) asym |= (t[i][h].x != w.x) | (t[i][h].y != w.y);
+                                        if (A.interaction) {
+                                            v.x += w.x; v.y += w.y;
+                                        } else {
+                                            const double sc = wc * ws[r];
+                                            v.x = fma(w.x, sc, v.x); v.y = fma(w.y, sc, v.y);
+                                        }
+                                    }
+                                    if (c == r) {
+                                        v.x += vl[h].x; v.y += vl[h].y;
+                                    }
+                                }
+                                *e = v;
+                            }
+                        }
+                    }
+                }
+            }
+            for (int r = lane; r < P; r += 32) M[G::rhs(r)] = make_double2(bs[r], 0.0);
+            defer = __any_sync(kFull, asym);
+            __syncwarp();
+        }
+        double2 corner = zero2;
+        if (!defer) {
+            int bad = 0;
+            corner = packed_ldlt<P>(M, lane, bad);
+            defer = bad != 0;
+            if (defer && lane == 0 && A.fallbacks) atomicAdd(A.fallbacks, 1ULL);
+        }
+        if (defer) {
+            if (lane == 0) defer_list[atomicAdd(defer_count, 1)] = (int)sysi;
+            continue;
+        }
+        if (lane == 0) {
+            const double2* as = A.asym + (size_t)sysi * A.asym_stride;  // [4][1]: Hp, Hm, Hpp, Hmp
+            const double2 Hp = as[0], Hm = as[1], Hpp = as[2], Hmp = as[3];
+            const double2 R = make_double2(-corner.x / (a * a), -corner.y / (a * a));  // core.py:15-22
+            const double2 aR = make_double2(a * R.x, a * R.y);
+            const double2 tp = cmul(aR, Hpp), tm = cmul(aR, Hmp);
+            // S = Z+^-1 Z-, Z+- = H+- - a R H+-'   (core.py:51-56)
+            const double2 S = cdiv(make_double2(Hm.x - tm.x, Hm.y - tm.y), make_double2(Hp.x - tp.x, Hp.y - tp.y));
+            // u'_ext = (i/2)(H-' w - S H+')   (core.py:58)
+            const double w0 = A.weights[0];
+            const double2 sh = cmul(S, Hpp);
+            const double2 v = make_double2(Hmp.x * w0 - sh.x, Hmp.y * w0 - sh.y);
+            A.R[sysi] = R;
+            A.S[sysi] = S;
+            A.uext[sysi] = make_double2(-0.5 * v.y, 0.5 * v.x);
+            const bool nonfinite = !(isfinite(S.x) && isfinite(S.y));
+            A.status[sysi] = nonfinite ? JITR_B200_STATUS_NONFINITE : JITR_B200_STATUS_OK;
+        }
+        __syncwarp();
+    }
+}
+
+template <int P>
+int launch_packed(const GenArgs& a, const int* symflag, int check_symmetry, int* defer_list, int* defer_count, cudaStream_t st) {
+    using Plan = PackedPlan<P>;
+    auto kern = packed_solve_kernel<P>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Plan::kSmem) != cudaSuccess)
+        return set_cuda_error("cudaFuncSetAttribute(packed_solve)");
+    long long blocks = (a.batch + Plan::kWarps - 1) / Plan::kWarps;
+    if (blocks > sm_count()) blocks = sm_count();
+    unsigned long long* wc = next_work_counter(st);
+    if (!wc) return set_cuda_error("packed_solve work counter");
+    kern<<<(unsigned)blocks, Plan::kThreads, Plan::kSmem, st>>>(a, symflag, check_symmetry, wc, defer_list, defer_count);
+    count_launch();
+    if (cudaGetLastError() != cudaSuccess) return set_cuda_error("packed_solve launch");
+    return JITR_B200_OK;
+}
+
+}  // namespace
+
+bool packed_solve_supported(int nbasis) { return nbasis >= 1 && nbasis <= 64; }
+
+int launch_packed_solve(const GenArgs& a, const int* symflag, int check_symmetry, int* defer_list, int* defer_count, cudaStream_t st) {
+    const int P = (a.N + 7) & ~7;
+    switch (P) {
+        case 8: return launch_packed<8>(a, symflag, check_symmetry, defer_list, defer_count, st);
+        case 16: return launch_packed<16>(a, symflag, check_symmetry, defer_list, defer_count, st);
+        case 24: return launch_packed<24>(a, symflag, check_symmetry, defer_list, defer_count, st);
+        case 32: return launch_packed<32>(a, symflag, check_symmetry, defer_list, defer_count, st);
+        case 40: return launch_packed<40>(a, symflag, check_symmetry, defer_list, defer_count, st);
+        case 48: return launch_packed<48>(a, symflag, check_symmetry, defer_list, defer_count, st);
+        case 56: return launch_packed<56>(a, symflag, check_symmetry, defer_list, defer_count, st);
+        case 64: return launch_packed<64>(a, symflag, check_symmetry, defer_list, defer_count, st);
+        default: return set_error(JITR_B200_ERR_UNSUPPORTED, "packed_solve: nbasis must be in 1..64");
+    }
+}
+
+}  // namespace jitr

@@ -11,6 +11,12 @@ struct SweepArgs {
     unsigned long long* fallback_mask;  // optional [n_pairs] bit mask of the systems that fell back (diagnostic)
     unsigned long long* work_counter;  // device counter handing out (sample, energy) pairs, zero at launch
     long long n_pairs;
+    // packed modes (P = 48, 56, 64): a pair with a system that fails the threshold test is not finished here but appended
+    // to defer_list / defer_count; the partial-pivoting modes then run over that list (pair_list / pair_count)
+    int* defer_list;
+    int* defer_count;
+    const int* pair_list;
+    const int* pair_count;
     const double* That;
     const double* mesh_x;
     const double* bvec;
@@ -31,6 +37,6 @@ template <bool PARAMS, int MODE>
 int launch_sweep_mode(const SweepArgs& a, cudaStream_t st);
 
 // solver modes compiled into the library: fast paths (P = MODE) and generic paths (-2, -3 row slots)
-#define JITR_SWEEP_MODES(X) X(16) X(24) X(32) X(40) X(-2) X(-3)
+#define JITR_SWEEP_MODES(X) X(16) X(24) X(32) X(40) X(48) X(56) X(64) X(-2) X(-3)
 
 }  // namespace jitr

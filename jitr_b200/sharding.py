@@ -18,11 +18,13 @@ def shard_bounds(n_samples: int, world: int, rank: int):
     return rank * n_samples // world, (rank + 1) * n_samples // world
 
 
-def gather_to_root(shard, n_samples: int, dst: int = 0, group=None):
+def gather_to_root(shard, n_samples: int, dst: int = 0, group=None, out=None):
     """Gather the per-rank blocks ``shard`` (leading axis = this rank's samples, as cut by
     ``shard_bounds(n_samples, world, rank)``) into one tensor of leading size ``n_samples`` on rank
     ``dst``; returns None on the other ranks.  One collective; uneven blocks are padded to the
-    largest block for the transfer and trimmed on the root."""
+    largest block for the transfer and trimmed on the root.  ``out`` (root only): a preallocated tensor of leading size
+    ``n_samples`` to receive into -- with equal blocks every rank's message lands directly in its slice (no staging copy:
+    what a 10^5-sample sweep needs, whose angular distributions are 9 GB per rank)."""
     import torch
     import torch.distributed as dist
 
@@ -35,6 +37,10 @@ def gather_to_root(shard, n_samples: int, dst: int = 0, group=None):
     if shard.shape[0] != hi - lo:
         raise ValueError(f"rank {rank}: shard has {shard.shape[0]} samples, expected {hi - lo}")
     send = shard.contiguous()
+    if out is not None and all(h - l == mx for l, h in sizes):
+        bufs = [out[l:h] for l, h in sizes] if rank == dst else None
+        dist.gather(send, bufs, dst=dst, group=group)
+        return out if rank == dst else None
     if hi - lo < mx:
         pad = torch.zeros((mx - (hi - lo),) + tuple(shard.shape[1:]), dtype=shard.dtype, device=shard.device)
         send = torch.cat([send, pad], dim=0)

@@ -335,8 +335,11 @@ def test_large_sample_parity_gate_on_the_benchmarked_sweep():
         # inverts matrices with cond(A) up to 1e7 explicitly and carries that noise itself)
         assert a["S"]["p999"] < RTOL_S and a["dsdo"]["p999"] < RTOL_XS, (mode, a)
         r = rep[mode]["referee"]
-        assert r["all_refereed_explained"], (mode, r)
-        assert r["S_outlier_systems"] <= 1e-4 * a["systems"] and r["dsdo_outlier_pairs"] <= 5e-3 * a["pairs"], (mode, r)
+        assert r["S_all_explained"], (mode, r)
+        assert r["S_outlier_systems"] <= 1e-4 * a["systems"], (mode, r)
+        # cross sections: 1e-8 relative, or -- at diffraction minima, where dsigma/dOmega is 1e-9 of its forward value and the
+        # partial-wave sum cancels by kappa ~ 1e5 -- the S-matrix tolerance propagated to first order, 1e-10 kappa
+        assert a["dsdo_over_allowed_max"] <= 1.0 and a["dsdo_beyond_1e-8"] <= 1e-4 * a["dsdo"]["n"], (mode, a)
         assert r.get("referee_vs_mp40_max", 0.0) < 1e-12
     assert rep["symmetric_vs_partial_pivoting"]["nl_equal"]
     assert rep["partial_pivoting_only"]["all"]["fallback"]["systems"] == 0
@@ -1058,3 +1061,119 @@ def test_device_percentile_bands_of_a_sweep(golden):
     bands = uq.percentiles(ratio, [16, 84]).cpu().numpy()
     assert np.array_equal(bands, np.percentile(ratio.cpu().numpy(), [16, 84], axis=0))
     assert np.all(bands[0] <= bands[1])
+
+
+# ------------------------------------------------------------------ packed symmetric single-channel solve (config 4 path)
+def _single_channel_reference(N, a, l, E0, k0, asym, loc=None, nl=None, inter=None):
+    F = orc.free_matrix(N, a, [l])
+    V = inter if inter is not None else orc.interaction_matrix(N, k0, E0, a, 1, local_potential=loc, nonlocal_potential=nl)
+    R, S, _, up = orc.solve_smatrix(F + V, orc.boundary_vector(N), *[np.ascontiguousarray(asym[i]) for i in range(4)], np.ones(1), a, 1, N)
+    return R, S, up
+
+
+@pytest.mark.parametrize("N", [5, 16, 23, 40, 47, 56, 60, 64])
+def test_packed_single_channel_solve_vs_oracle(N):
+    """jitr_b200_solve_batched, nch = 1, no coefficients: the packed LDL^T kernel with bulk-async staging of the nonlocal
+    kernels (rmatrix.py:160-178, kernel.py:197-214).  Symmetric kernels stay on it, a kernel that is not symmetric in
+    (r, r') is detected on the device and solved by the partial-pivoting kernel, a system whose first diagonal entry is tiny
+    fails the threshold test and is deferred too; all against the oracle's explicit-inverse solve."""
+    rng = np.random.default_rng(1000 + N)
+    B = 37
+    solver = jitr_b200.Solver(N)
+    a, E0, k0, l = 11.0, 21.0, 0.95, 2
+    asym = np.array([orc.coulomb_hankel(l, 0.0, a)]).T  # (4, 1)
+    r = solver.radial_grid(a, k0)
+    rg, rpg = np.meshgrid(r, r, indexing="ij")
+    base = -38.0 * np.exp(-((rg - rpg) / 0.9) ** 2) / (1 + np.exp((0.5 * (rg + rpg) - 5.0) / 0.65)) * (1 + 0.25j)
+    nl = base[None] * (1.0 + 0.05 * rng.standard_normal((B, 1, 1)))
+    loc = (-4.0 - 1.0j) / (1 + np.exp((r[None] - 5.0) / 0.6)) * (1.0 + 0.1 * rng.standard_normal((B, 1)))
+    asym_rows = [3, 17]      # not symmetric: must take the partial-pivoting kernel
+    for b in asym_rows:
+        nl[b, N // 2, 0] *= 1.0 + 1e-9
+    tiny = [5]               # a^2 A[0][0] ~ 0: fails the threshold test
+    Fm = orc.free_matrix(N, a, [l])
+    w = solver.kernel.quadrature.weights
+    for b in tiny:
+        loc[b, 0] = -(Fm[0, 0] + nl[b, 0, 0] * w[0] * (a / k0) / k0 / E0) * E0 + 1e-9
+    L = _cabi.lib()
+    free = torch.tensor(Fm, device="cuda")
+    f0 = L.jitr_b200_sym_fallback_count()
+    out = solver.solve_batch(a, E0, k0, 1, free, torch.tensor(asym, device="cuda"), local_potential=torch.tensor(loc, device="cuda"),
+                             nonlocal_potential=torch.tensor(nl, device="cuda"))
+    assert int(out["status"].abs().sum()) == 0
+    assert L.jitr_b200_sym_fallback_count() - f0 >= len(tiny)
+    for b in range(B):
+        R, S, up = _single_channel_reference(N, a, l, E0, k0, asym, loc=loc[b], nl=nl[b])
+        assert relerr(out["S"][b].cpu().numpy(), S) < (RTOL_S if b not in tiny else 1e-7), (N, b)
+        assert relerr(out["R"][b].cpu().numpy(), R) < (1e-9 if b not in tiny else 1e-6), (N, b)
+        assert relerr(out["uext"][b].cpu().numpy(), up) < (1e-9 if b not in tiny else 1e-6), (N, b)
+    # the caller vouches for symmetry: only the lower triangles are read, so the two doctored kernels now give the answer of
+    # their lower triangle mirrored
+    try:
+        assert L.jitr_b200_set_option(_cabi.OPT_ASSUME_SYMMETRIC_KERNEL, 1) == 0
+        out2 = solver.solve_batch(a, E0, k0, 1, free, torch.tensor(asym, device="cuda"), local_potential=torch.tensor(loc, device="cuda"),
+                                  nonlocal_potential=torch.tensor(nl, device="cuda"))
+    finally:
+        L.jitr_b200_set_option(_cabi.OPT_ASSUME_SYMMETRIC_KERNEL, 0)
+    for b in range(B):
+        if b in asym_rows:
+            low = np.tril(nl[b]) + np.tril(nl[b], -1).T
+            R, S, up = _single_channel_reference(N, a, l, E0, k0, asym, loc=loc[b], nl=low)
+            assert relerr(out2["S"][b].cpu().numpy(), S) < RTOL_S
+        elif b not in tiny:
+            assert torch.equal(out2["S"][b], out["S"][b])
+    # a ready interaction matrix, and local-only input, take the same kernel
+    inter = np.stack([orc.interaction_matrix(N, k0, E0, a, 1, local_potential=loc[b], nonlocal_potential=nl[b]) for b in range(4)])
+    out3 = solver.solve_batch(a, E0, k0, 1, free, torch.tensor(asym, device="cuda"), interaction_matrix=torch.tensor(inter, device="cuda"))
+    out4 = solver.solve_batch(a, E0, k0, 1, free, torch.tensor(asym, device="cuda"), local_potential=torch.tensor(loc[:4], device="cuda"))
+    for b in range(4):
+        if b in asym_rows:
+            continue
+        assert relerr(out3["S"][b].cpu().numpy(), out["S"][b].cpu().numpy()) < 1e-11
+        R, S, up = _single_channel_reference(N, a, l, E0, k0, asym, loc=loc[b])
+        assert relerr(out4["S"][b].cpu().numpy(), S) < RTOL_S
+
+
+def test_device_perey_buck_generator_vs_scipy(golden):
+    """csrc/nonlocal_gen.cu against scipy's exponentially scaled Bessel function (workloads.perey_buck_kernel, the
+    definition the config-4 goldens were made with), against the golden kernels of the real reference run, and against the
+    reference's own perey_buck_nonlocal where that does not overflow."""
+    from scipy import special as sc
+
+    from jitr_b200 import workloads
+    from jitr_b200.optical_potentials import nonlocal_forms
+
+    g = golden("config4_nonlocal")
+    solver = jitr_b200.Solver(60)
+    k = float(g["kin"][3])
+    rg, rpg = solver.nonlocal_radial_grids(float(g["a"]), k)
+    r = solver.radial_grid(float(g["a"]), k)
+    smp = workloads.config4_samples(5)
+    smp[0] = (71.0, 15.0, 0.85)
+    lmax = 30
+    U = nonlocal_forms.perey_buck_kernels(r, lmax, smp[:, 0], smp[:, 1], smp[:, 2], R=workloads.CONFIG4["R"], a=workloads.CONFIG4["a"]).cpu().numpy()
+    for b in range(5):
+        for l in (0, 1, 7, 19, 30):
+            ref = workloads.perey_buck_kernel(rg, rpg, l, *smp[b])
+            scale = np.max(np.abs(ref))
+            big = np.abs(ref) > 1e-200
+            assert np.max(np.abs(U[b, l][big] - ref[big]) / np.abs(ref[big])) < 2e-13, (b, l)
+            assert np.max(np.abs(U[b, l] - ref)) < 1e-13 * scale
+    for l in (0, 3):
+        assert relerr(U[0, l], g[f"s0_l{l}_U"], floor=1e-200) < 2e-13
+    # the reference's literal form (z = 2 pi r r'/beta^2) on a small mesh where spherical_jn(-i z) is still finite
+    rs = np.linspace(0.05, 2.0, 12)
+    a_, b_ = np.meshgrid(rs, rs, indexing="ij")
+    for ell in (0, 2, 5):
+        z = 2 * np.pi * a_ * b_ / 1.1**2
+        ref = np.real(np.exp(-(a_**2 + b_**2) / 1.1**2) * 2 * 1j**ell * z * sc.spherical_jn(ell, -1j * z) / (1.1 * np.sqrt(np.pi)))
+        got = nonlocal_forms.perey_buck_nonlocal(rs, rs, 1.1, ell).cpu().numpy()
+        assert np.max(np.abs(got - ref) / np.abs(ref)) < 1e-12
+    # and the kernels feed the packed solver: S of the golden (sample 0, l = 0, 3)
+    sys4 = ProjectileTargetSystem(float(g["a"]), 6, Ztarget=82, Zproj=0)
+    channels, asym = sys4.get_partial_wave_channels(*g["kin"])
+    for l in (0, 3):
+        free = torch.tensor(solver.free_matrix(float(g["a"]), [l]), device="cuda")
+        at = torch.tensor(np.array([[asym[l].Hp[0]], [asym[l].Hm[0]], [asym[l].Hpp[0]], [asym[l].Hmp[0]]]), device="cuda")
+        out = solver.solve_batch(float(g["a"]), float(g["kin"][1]), k, 1, free, at, nonlocal_potential=torch.tensor(U[:1, l], device="cuda"))
+        assert relerr(out["S"][0].cpu().numpy(), g[f"s0_l{l}_S"]) < RTOL_S
