@@ -214,11 +214,12 @@ int jitr_b200_qe_xs(int lmax, int n_angles, long long batch, const double* T, co
  *   U_l(r_n, r_m) = -(V + iW) f((r_n + r_m)/2; R, a) * 2 z e^{-z} i_l(z) exp(z - (r_n^2 + r_m^2)/beta^2) / (beta sqrt(pi)),  z = zfac r_n r_m / beta^2
  *   params [n_samples][5]: V, W, beta, R, a  (a <= 0: no Woods-Saxon factor -> V = -1, W = 0 gives perey_buck_nonlocal itself)
  *   zfac   2 for the Gaussian nonlocality (exponent -(r - r')^2/beta^2);  2 pi reproduces the reference's literal z
- *   rgrid  [N] physical mesh (fm);   out [n_samples][lmax+1][N][N] complex, ready to be the `nonlocal` input of
- *   jitr_b200_solve_batched (system index = sample * (lmax+1) + l).   lmax <= 64.
+ *   rgrid  [N] physical mesh (fm);   out: element (sample s, l, n, m) at  s * sample_stride + l * l_stride + n * N + m  (complex
+ *   units; 0, 0 = the dense [n_samples][lmax+1][N][N] layout; sample_stride = N*N, l_stride = n_samples*N*N gives [lmax+1][n_samples][N][N],
+ *   one contiguous `nonlocal` batch of jitr_b200_solve_batched per partial wave).   lmax <= 64.
  */
 int jitr_b200_perey_buck_kernels(int nbasis, int lmax, long long n_samples, const double* rgrid, const double* params,
-                                 double zfac, double* out, void* stream);
+                                 double zfac, double* out, long long sample_stride, long long l_stride, void* stream);
 
 /* bytes of device scratch jitr_b200_solve_batched needs for this problem (0: none; -1: bad arguments) */
 long long jitr_b200_solve_workspace_bytes(int nbasis, int nch, long long batch, int coeffs);

@@ -297,30 +297,36 @@ struct PackedSolver {
         double2* M = reinterpret_cast<double2*>(smem_raw + wofs);
         const double* b = tail();
         const double2 dd[2] = {d0, d1};
-        // ---- lower triangle of That + diag(d), identity padding, y = b
+        // ---- lower triangle of That + diag(d), identity padding, y = b.  One block row per step: left of the diagonal tile a
+        // lane owns column c = lane (+32) and has up to sixteen independent loads in flight; the diagonal tile uses all lanes
 #pragma unroll 1
         for (int tr = 0; tr < G::NB; ++tr) {
-            double t[8][2];
+            const int r0 = 8 * tr;
+            const int nrow = min(8, N - r0);  // warp-uniform
+            double2* Mb = M + G::off(tr);
+            const int ldt = G::ld(tr);
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const int c = lane + 32 * h;
-                if (32 * h <= 8 * tr + 7) {
+                if (c < r0) {
+                    const double* Tp = That + r0 * N + c;
+                    double t[8];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int r = 8 * tr + i;
-                        t[i][h] = (c < r && r < N) ? __ldg(That + r * N + c) : 0.0;
-                    }
+                    for (int i = 0; i < 8; ++i) t[i] = i < nrow ? __ldg(Tp + i * N) : 0.0;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) Mb[i * ldt + c] = make_double2(t[i], 0.0);
                 }
             }
+            const int hrow = r0 >> 5;
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int c = lane + 32 * h;
-                if (32 * h <= 8 * tr + 7) {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int r = 8 * tr + i;
-                        if (c <= r) M[G::off(tr) + i * G::ld(tr) + c] = (c == r) ? (r < N ? dd[h] : make_double2(1.0, 0.0)) : make_double2(t[i][h], 0.0);
-                    }
+            for (int k = 0; k < 2; ++k) {
+                const int i = (lane >> 3) + 4 * k, jj = lane & 7;
+                const int r = r0 + i, c = r0 + jj;
+                const double2 dv = shfl2(hrow ? dd[1] : dd[0], r & 31);  // the diagonal entry of row r lives in lane r & 31
+                if (jj <= i) {
+                    double2 v = make_double2(jj == i ? 1.0 : 0.0, 0.0);  // identity padding
+                    if (r < N) v = (jj == i) ? dv : make_double2(__ldg(That + r * N + c), 0.0);
+                    Mb[i * ldt + c] = v;
                 }
             }
         }

@@ -74,12 +74,17 @@ __device__ __forceinline__ void packed_panel(double2* __restrict__ M, double2* _
     double2 ysave = make_double2(0.0, 0.0), rsave = make_double2(0.0, 0.0);
 #pragma unroll
     for (int kk = 0; kk < 8; ++kk) {
-        const double2 myrinv = crecip_fast(p[0][kk]);  // speculative: only lane kk's is used
+        // The pivot chain is the critical path of a warp-per-system elimination (64 columns in sequence, every link a
+        // dependent FP64 instruction of ~23 cycles), so the multiplier is formed as  l = (w conj(d)) / |d|^2 : the product
+        // w conj(d) needs only the pivot itself (broadcast at once) and runs beside the reciprocal of |d|^2, which every lane
+        // computes speculatively on its own entry (only lane kk's is used) -- two links shorter than  l = w (1/d).
+        const double2 dmine = p[0][kk];
+        const double mys = rcp_halley(fma(dmine.x, dmine.x, dmine.y * dmine.y));
         if (lane == kk) {
-            const int m = max(__double2hiint(p[0][kk].x) & 0x7fffffff, __double2hiint(p[0][kk].y) & 0x7fffffff);
+            const int m = max(__double2hiint(dmine.x) & 0x7fffffff, __double2hiint(dmine.y) & 0x7fffffff);
             if (m < 0x00100000 || m >= 0x7ff00000) bad = 1;  // zero, denormal, Inf or NaN pivot
             ysave = p[0][8];
-            rsave = myrinv;
+            rsave = make_double2(dmine.x * mys, -dmine.y * mys);
         }
         // the unscaled column entries, in place (rows below the pivot): W of the trailing update, and the pivot row
 #pragma unroll
@@ -87,16 +92,19 @@ __device__ __forceinline__ void packed_panel(double2* __restrict__ M, double2* _
             const int i = 32 * s + lane;
             if (i > kk && i < nrows) M[rb[s] + kk] = p[s][kk];
         }
-        const double2 rinv = shfl2(myrinv, kk);
+        const double2 piv = shfl2(dmine, kk);
         double2 u[9];
         u[8] = shfl2(p[0][8], kk);
         __syncwarp();
 #pragma unroll
         for (int j = kk + 1; j < 8; ++j) u[j] = M[dbase + j * ldk + kk];  // pivot row = transposed pivot column
+        const double sc = __shfl_sync(kFull, mys, kk);
 #pragma unroll
         for (int s = 0; s < NS; ++s) {
             const int i = 32 * s + lane;
-            const double2 l = cmul(p[s][kk], rinv);
+            const double2 w = p[s][kk];
+            const double tx = fma(w.x, piv.x, w.y * piv.y), ty = fma(w.y, piv.x, -(w.x * piv.y));  // w conj(d)
+            const double2 l = make_double2(tx * sc, ty * sc);
             if (i > kk && i < nrows && mult_too_large(l)) bad = 1;
 #pragma unroll
             for (int j = kk + 1; j < 9; ++j) cfnma(p[s][j], l, u[j]);

@@ -62,6 +62,14 @@ __device__ __forceinline__ double rcp_newton(double x) {
     r = fma(fma(-x, r, 1.0), r, r);
     return r;
 }
+// the same with ONE cubic (Halley) step, r (1 + e + e^2), e = 1 - x r: three dependent FMAs instead of four (2^-69 after the
+// 2^-23 seed) -- for the pivot chain of the packed path, where the reciprocal is the longest link
+__device__ __forceinline__ double rcp_halley(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    const double e = fma(-x, r, 1.0);
+    return fma(r, fma(e, e, e), r);
+}
 __device__ __forceinline__ double2 crecip_fast(double2 a) {
     const double d = rcp_newton(fma(a.x, a.x, a.y * a.y));
     return make_double2(a.x * d, -a.y * d);

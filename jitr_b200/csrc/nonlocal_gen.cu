@@ -59,7 +59,8 @@ __device__ __forceinline__ void scaled_bessel_i(const double z, const int lmax, 
 }
 
 __global__ void perey_buck_kernel(const int N, const int lmax, const long long n_samples, const double* __restrict__ rgrid,
-                                  const double* __restrict__ params, const double zfac, double2* __restrict__ out) {
+                                  const double* __restrict__ params, const double zfac, double2* __restrict__ out,
+                                  const long long sample_stride, const long long l_stride) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long per = (long long)N * N;
     if (idx >= n_samples * per) return;
@@ -81,10 +82,10 @@ __global__ void perey_buck_kernel(const int N, const int lmax, const long long n
     const double amp = ws * 2.0 * z * exp(ex) / (beta * 1.7724538509055159);
     double f[kGenMaxL + 1];
     if (amp != 0.0) scaled_bessel_i(z, lmax, f);
-    double2* o = out + s * (lmax + 1) * per + nm;
+    double2* o = out + s * sample_stride + nm;
     for (int l = 0; l <= lmax; ++l) {
         const double h = amp != 0.0 ? amp * f[l] : 0.0;
-        o[(long long)l * per] = make_double2(-V * h, -W * h);
+        o[(long long)l * l_stride] = make_double2(-V * h, -W * h);
     }
 }
 
@@ -94,13 +95,14 @@ __global__ void perey_buck_kernel(const int N, const int lmax, const long long n
 using namespace jitr;
 
 extern "C" int jitr_b200_perey_buck_kernels(int nbasis, int lmax, long long n_samples, const double* rgrid, const double* params,
-                                            double zfac, double* out, void* stream) {
+                                            double zfac, double* out, long long sample_stride, long long l_stride, void* stream) {
     if (n_samples == 0) return JITR_B200_OK;
     if (nbasis < 1 || lmax < 0 || lmax > kGenMaxL || n_samples < 0 || !rgrid || !params || !out || !(zfac > 0.0))
         return set_error(JITR_B200_ERR_BAD_ARG, "perey_buck_kernels: null pointer or bad size (lmax <= 64)");
     const long long total = n_samples * nbasis * nbasis;
     perey_buck_kernel<<<(unsigned)((total + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
-        nbasis, lmax, n_samples, rgrid, params, zfac, reinterpret_cast<double2*>(out));
+        nbasis, lmax, n_samples, rgrid, params, zfac, reinterpret_cast<double2*>(out),
+        sample_stride > 0 ? sample_stride : (long long)(lmax + 1) * nbasis * nbasis, l_stride > 0 ? l_stride : (long long)nbasis * nbasis);
     count_launch();
     if (cudaGetLastError() != cudaSuccess) return set_cuda_error("perey_buck_kernels launch");
     return JITR_B200_OK;

@@ -49,6 +49,106 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
     } while (!done);
 }
 
+// A = F + (scaled V | interaction) (+ V_loc / E0 on the diagonal), in place on the packed lower triangle whose V part the bulk
+// copies have delivered; identity padding beyond N; optionally the bit-wise comparison of V with its transpose read from
+// global memory.  One block row (8 rows) per step: left of the diagonal tile a lane owns column c = lane (+32) and has up to
+// sixteen independent global loads in flight (rows of F coalesced; the upper triangle of V is walked by columns, eight
+// consecutive elements = one 128-byte line per lane); the diagonal tile is spread over all 32 lanes.  Returns the OR of the
+// XORs of the compared words (0: symmetric).
+template <int P, bool HAS_V, bool INTER, bool CHECK>
+__device__ __forceinline__ unsigned long long stage_system(double2* __restrict__ M, const double2* __restrict__ F,
+                                                           const double2* __restrict__ Vsrc, const double2* __restrict__ Vloc,
+                                                           const double* __restrict__ ws, const double nl_scale, const double E0,
+                                                           const int N, const int lane) {
+    using G = PackedGeom<P>;
+    const double2 zero2 = make_double2(0.0, 0.0);
+    unsigned long long diff = 0ULL;
+    double2 vl[2];  // local potential / E0 of the rows this lane "owns" (row = lane + 32 h)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int c = lane + 32 * h;
+        vl[h] = zero2;
+        if (Vloc && c < N) {
+            const double2 w = Vloc[c];
+            vl[h] = make_double2(w.x / E0, w.y / E0);
+        }
+    }
+#pragma unroll 1
+    for (int tr = 0; tr < G::NB; ++tr) {
+        const int r0 = 8 * tr;
+        const int nrow = min(8, N - r0);  // rows of this block row inside the system (<= 0: all padding); warp-uniform
+        double2* Mb = M + G::off(tr);
+        const int ldt = G::ld(tr);
+        // ---- tiles left of the diagonal tile
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int c = lane + 32 * h;
+            if (c < r0) {
+                const double2* Fp = F + (size_t)r0 * N + c;
+                const double2* Vp = HAS_V ? Vsrc + (size_t)c * N + r0 : nullptr;
+                double2 f[8], t[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    f[i] = i < nrow ? Fp[(size_t)i * N] : zero2;
+                    if (HAS_V && CHECK) t[i] = i < nrow ? Vp[i] : zero2;
+                }
+                const double wc = HAS_V && !INTER ? ws[c] * nl_scale : 0.0;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    double2* e = Mb + i * ldt + c;
+                    double2 v = f[i];
+                    if (HAS_V && i < nrow) {
+                        const double2 w = *e;
+                        if (CHECK) diff |= (unsigned long long)(__double_as_longlong(w.x) ^ __double_as_longlong(t[i].x)) |
+                                           (unsigned long long)(__double_as_longlong(w.y) ^ __double_as_longlong(t[i].y));
+                        if (INTER) {
+                            v.x += w.x; v.y += w.y;
+                        } else {
+                            const double sc = wc * ws[r0 + i];
+                            v.x = fma(w.x, sc, v.x); v.y = fma(w.y, sc, v.y);
+                        }
+                    }
+                    *e = v;
+                }
+            }
+        }
+        // ---- the diagonal tile: element (r0 + i, r0 + j), j <= i, i = (lane >> 3) + 4 k, j = lane & 7
+        const int hrow = r0 >> 5;  // the rows r0 .. r0 + 7 are owned by slot hrow of the lanes (r & 31)
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int i = (lane >> 3) + 4 * k, j = lane & 7;
+            const int r = r0 + i, c = r0 + j;
+            const double2 vd = shfl2(hrow ? vl[1] : vl[0], r & 31);
+            if (j <= i) {
+                double2* e = Mb + i * ldt + c;
+                double2 v = make_double2(j == i ? 1.0 : 0.0, 0.0);  // identity padding
+                if (r < N) {
+                    v = F[(size_t)r * N + c];
+                    if (HAS_V) {
+                        const double2 w = *e;
+                        if (CHECK && j < i) {
+                            const double2 t = Vsrc[(size_t)c * N + r];
+                            diff |= (unsigned long long)(__double_as_longlong(w.x) ^ __double_as_longlong(t.x)) |
+                                    (unsigned long long)(__double_as_longlong(w.y) ^ __double_as_longlong(t.y));
+                        }
+                        if (INTER) {
+                            v.x += w.x; v.y += w.y;
+                        } else {
+                            const double sc = ws[c] * nl_scale * ws[r];
+                            v.x = fma(w.x, sc, v.x); v.y = fma(w.y, sc, v.y);
+                        }
+                    }
+                    if (j == i) {
+                        v.x += vd.x; v.y += vd.y;
+                    }
+                }
+                *e = v;
+            }
+        }
+    }
+    return diff;
+}
+
 template <int P>
 __global__ void __launch_bounds__(PackedPlan<P>::kThreads, 1)
 packed_solve_kernel(const GenArgs A, const int* __restrict__ symflag, const int check_symmetry,
@@ -119,70 +219,17 @@ packed_solve_kernel(const GenArgs A, const int* __restrict__ symflag, const int 
             parity ^= 1u;
         }
         if (!defer) {
-            // ---- A = F + scaled V (+ local on the diagonal), in place, eight rows (one block row) per step so that every
-            // lane has up to sixteen independent global loads in flight (lane = column: coalesced rows of F; the upper
-            // triangle of V is walked by columns, eight consecutive elements = one 128-byte line per lane)
             const double2* F = A.free_matrix;
             const double2* Vloc = (!A.interaction && A.local) ? A.local + (size_t)sysi * N : nullptr;
-            bool asym = false;
-            double2 vl[2];  // local potential / E0 on this lane's two diagonal entries
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int c = lane + 32 * h;
-                vl[h] = zero2;
-                if (Vloc && c < N) {
-                    const double2 w = Vloc[c];
-                    vl[h] = make_double2(w.x / E0, w.y / E0);
-                }
-            }
-            const bool check = Vsrc && check_symmetry;
-#pragma unroll 1
-            for (int tr = 0; tr < G::NB; ++tr) {
-                double2 f[8][2], t[8][2];
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int c = lane + 32 * h;
-                    if (32 * h <= 8 * tr + 7) {
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const int r = 8 * tr + i;
-                            f[i][h] = (c <= r && r < N) ? F[(size_t)r * N + c] : make_double2(c == r ? 1.0 : 0.0, 0.0);  // identity padding
-                            t[i][h] = (check && c < r && r < N) ? Vsrc[(size_t)c * N + r] : zero2;
-                        }
-                    }
-                }
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int c = lane + 32 * h;
-                    if (32 * h <= 8 * tr + 7) {
-                        const double wc = ws[c < P ? c : 0] * nl_scale;
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const int r = 8 * tr + i;
-                            if (c <= r) {
-                                double2* e = M + G::off(tr) + i * G::ld(tr) + c;
-                                double2 v = f[i][h];
-                                if (r < N) {
-                                    if (Vsrc) {
-                                        const double2 w = *e;
-                                        if (check && c < r) asym |= (t[i][h].x != w.x) | (t[i][h].y != w.y);
-                                        if (A.interaction) {
-                                            v.x += w.x; v.y += w.y;
-                                        } else {
-                                            const double sc = wc * ws[r];
-                                            v.x = fma(w.x, sc, v.x); v.y = fma(w.y, sc, v.y);
-                                        }
-                                    }
-                                    if (c == r) {
-                                        v.x += vl[h].x; v.y += vl[h].y;
-                                    }
-                                }
-                                *e = v;
-                            }
-                        }
-                    }
-                }
-            }
+            unsigned long long diff = 0ULL;
+            if (!Vsrc) diff = stage_system<P, false, false, false>(M, F, nullptr, Vloc, ws, nl_scale, E0, N, lane);
+            else if (A.interaction)
+                diff = check_symmetry ? stage_system<P, true, true, true>(M, F, Vsrc, Vloc, ws, nl_scale, E0, N, lane)
+                                      : stage_system<P, true, true, false>(M, F, Vsrc, Vloc, ws, nl_scale, E0, N, lane);
+            else
+                diff = check_symmetry ? stage_system<P, true, false, true>(M, F, Vsrc, Vloc, ws, nl_scale, E0, N, lane)
+                                      : stage_system<P, true, false, false>(M, F, Vsrc, Vloc, ws, nl_scale, E0, N, lane);
+            const bool asym = diff != 0ULL;
             for (int r = lane; r < P; r += 32) M[G::rhs(r)] = make_double2(bs[r], 0.0);
             defer = __any_sync(kFull, asym);
             __syncwarp();

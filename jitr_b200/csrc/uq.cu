@@ -43,10 +43,12 @@ __global__ void __launch_bounds__(kPctCols* kPctRows) percentile_kernel(const do
     ull_rows above = reinterpret_cast<ull_rows>(rank + nq);                                 // smallest key above the selection
     ull_rows n_le = above + nq;                                                             // elements <= the selection
     unsigned(*hist)[kPctCols][256] = reinterpret_cast<unsigned(*)[kPctCols][256]>(n_le + nq);  // [nq][16][256]
+    __shared__ unsigned nan_col[kPctCols];  // the column holds a NaN: numpy.percentile returns NaN for it
     const double* q = Q.q;
     const int tc = threadIdx.x % kPctCols, tr = threadIdx.x / kPctCols;
     const long long col = (long long)blockIdx.x * kPctCols + tc;
     const bool live = col < M;
+    if (threadIdx.x < kPctCols) nan_col[threadIdx.x] = 0u;
     for (int i = threadIdx.x; i < nq * kPctCols; i += blockDim.x) {
         const int t = i / kPctCols, c = i % kPctCols;
         prefix[t][c] = 0ULL;
@@ -76,6 +78,7 @@ __global__ void __launch_bounds__(kPctCols* kPctRows) percentile_kernel(const do
                 for (int u = 0; u < 4; ++u) {
                     if (r0 + (long long)u * kPctRows >= S) break;
                     const unsigned long long k = pct_key(v[u]);
+                    if (pass == 0 && v[u] != v[u]) nan_col[tc] = 1u;  // (benign race: every writer stores 1)
                     const unsigned long long lead = pass == 0 ? 0ULL : k >> (shift + 8);
                     for (int t = 0; t < nq; ++t)
                         if (lead == want[t]) atomicAdd(&hist[t][tc][(unsigned)(k >> shift) & 255u], 1u);
@@ -151,6 +154,7 @@ __global__ void __launch_bounds__(kPctCols* kPctRows) percentile_kernel(const do
         const double diff = __dadd_rn(b, -a);
         double v = __dadd_rn(a, __dmul_rn(diff, g));
         if (g >= 0.5) v = __dadd_rn(b, -__dmul_rn(diff, __dadd_rn(1.0, -g)));
+        if (nan_col[c]) v = __longlong_as_double(0x7ff8000000000000LL);
         out[(size_t)t * M + cc] = v;
     }
 }

@@ -150,10 +150,17 @@ class DOM(SingleChannelOpticalModel):
 
         if isinstance(params, torch.Tensor):
             params = params.detach().cpu().numpy()
-        rx = reaction_kinematics[0][0]
-        Ecm = np.array([k.Ecm for _, k in reaction_kinematics])
-        rows = shape_rows((rx.projectile.A, rx.projectile.Z), (rx.target.A, rx.target.Z), Ecm, self._fermi(rx), params)
-        return torch.tensor(rows, dtype=torch.float64, device=device or "cuda")
+        # a sweep may mix targets (and projectiles) over its energy rows: A, Z, the Fermi energy, the Coulomb correction and
+        # the radii are those of EACH row's own reaction -- rows are grouped by (projectile, target, Ef) and mapped per group
+        groups = {}
+        for e, (rx, kin) in enumerate(reaction_kinematics):
+            key = ((rx.projectile.A, rx.projectile.Z), (rx.target.A, rx.target.Z), self._fermi(rx))
+            groups.setdefault(key, []).append(e)
+        rows = np.empty((np.asarray(params).shape[0], len(reaction_kinematics), 18), dtype=np.float64)
+        for (proj, tgt, Ef), idx in groups.items():
+            Ecm = np.array([reaction_kinematics[e][1].Ecm for e in idx])
+            rows[:, idx, :] = shape_rows(proj, tgt, Ecm, Ef, params)
+        return torch.tensor(np.ascontiguousarray(rows), dtype=torch.float64, device=device or "cuda")
 
     def pack(self, params, device=None):
         raise TypeError("DOM rows depend on the energy: use pair_rows (the workspaces do)")

@@ -14,12 +14,13 @@ from .. import _cabi
 TWO_PI = 2.0 * np.pi
 
 
-def perey_buck_kernels(rgrid, lmax, V, W, beta, R=None, a=None, zfac=2.0, device=None):
+def perey_buck_kernels(rgrid, lmax, V, W, beta, R=None, a=None, zfac=2.0, device=None, l_major=False, out=None):
     """(B, lmax + 1, N, N) complex128 CUDA tensor
     ``U_l(r, r') = -(V + iW) f_WS((r + r')/2; R, a) H_l(r, r'; beta)``, ``H_l = 2 z i_l(z) exp(-(r^2 + r'^2)/beta^2) / (beta sqrt(pi))``,
     ``z = zfac r r'/beta^2``.  ``V``, ``W``, ``beta`` (and ``R``, ``a``): scalars or (B,) arrays; without ``R``/``a`` there is no
     Woods-Saxon factor.  ``zfac = 2`` is the Gaussian nonlocality; ``zfac = 2 pi`` is the literal ``z`` of the reference's
-    ``perey_buck_nonlocal`` (with ``V = -1, W = 0`` its values)."""
+    ``perey_buck_nonlocal`` (with ``V = -1, W = 0`` its values).  ``l_major``: return (lmax + 1, B, N, N) instead, one
+    contiguous batch per partial wave."""
     import torch
 
     _cabi.require_device()
@@ -30,9 +31,14 @@ def perey_buck_kernels(rgrid, lmax, V, W, beta, R=None, a=None, zfac=2.0, device
     rg = torch.as_tensor(np.ascontiguousarray(rgrid, dtype=np.float64), device=dev)
     N = rg.shape[0]
     pt = torch.as_tensor(np.ascontiguousarray(p), device=dev)
-    out = torch.empty((B, lmax + 1, N, N), dtype=torch.complex128, device=dev)
+    shape = (lmax + 1, B, N, N) if l_major else (B, lmax + 1, N, N)
+    if out is None:
+        out = torch.empty(shape, dtype=torch.complex128, device=dev)
+    assert tuple(out.shape) == shape and out.is_contiguous()
+    ss, ls = (N * N, B * N * N) if l_major else (0, 0)
     with torch.cuda.device(dev):
-        rc = _cabi.lib().jitr_b200_perey_buck_kernels(N, int(lmax), B, _cabi.ptr(rg), _cabi.ptr(pt), float(zfac), _cabi.ptr(out), _cabi.stream_ptr())
+        rc = _cabi.lib().jitr_b200_perey_buck_kernels(N, int(lmax), B, _cabi.ptr(rg), _cabi.ptr(pt), float(zfac), _cabi.ptr(out), ss, ls,
+                                                      _cabi.stream_ptr())
     _cabi.check(rc, "jitr_b200_perey_buck_kernels")
     return out
 

@@ -32,7 +32,12 @@ def _particle(p, mass):
         elif (A, Z) == (1, 1):
             mass = MASS_P
         else:
-            mass = A * AMU  # crude default; pass mass_target= for a tabulated value
+            # the reference looks the rest mass up in its mass table (reactions/reaction.py:167): same table, same default
+            from ..data import rest_mass
+
+            mass = rest_mass(A, Z)
+            if mass is None:
+                raise ValueError(f"no tabulated rest mass for (A, Z) = ({A}, {Z}): pass the mass explicitly (mass_target=...)")
     return Particle(int(A), int(Z), float(mass))
 
 

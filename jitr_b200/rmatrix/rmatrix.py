@@ -241,7 +241,19 @@ class Solver:
         L = _cabi.lib()
         nb = self.kernel.quadrature.nbasis
         n = nb * nch
-        dev = torch.device("cuda", torch.cuda.current_device())
+        # the batch lives where its inputs live: the free matrix decides the device (the current device for host inputs)
+        dev = free_matrix.device if isinstance(free_matrix, torch.Tensor) and free_matrix.is_cuda else torch.device("cuda", torch.cuda.current_device())
+        with torch.cuda.device(dev):
+            return self._solve_batch_on(dev, a, E0, k0, nch, free_matrix, asym, local_potential, nonlocal_potential, interaction_matrix,
+                                        basis_boundary, weights, wavefunction, batch)
+
+    def _solve_batch_on(self, dev, a, E0, k0, nch, free_matrix, asym, local_potential, nonlocal_potential, interaction_matrix,
+                        basis_boundary, weights, wavefunction, batch):
+        import torch
+
+        L = _cabi.lib()
+        nb = self.kernel.quadrature.nbasis
+        n = nb * nch
         tabs = self.device_tables(dev)
         loc = nl = None
         if interaction_matrix is None:

@@ -262,6 +262,21 @@ class DifferentialWorkspace:
         return ElasticXS(x.dsdo[:, 0], x.Ay[:, 0], x.Q[:, 0], x.t[:, 0], x.rxn[:, 0])
 
 
+def _on_device(fn):
+    """Run a method of ElasticSweep with the sweep's device current: its tables live there, and the C ABI launches on the
+    current device / torch's current stream of that device."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(self, *args, **kwargs):
+        import torch
+
+        with torch.cuda.device(self.device):
+            return fn(self, *args, **kwargs)
+
+    return wrapper
+
+
 class ElasticSweep:
     """All (sample, energy) pairs of a UQ sweep in one fused launch.
 
@@ -318,6 +333,7 @@ class ElasticSweep:
     # ------------------------------------------------------------------ nbasis > 64
     MAX_FUSED_NBASIS = 64
 
+    @_on_device
     def _eval_potentials(self, model, params):
         """Built-in forms on the mesh of every energy: (B, E, N) central, spin_orbit (complex) and coulomb (real)
         CUDA tensors (jitr_b200_eval_potentials: the same device code the fused sweep inlines)."""
@@ -334,6 +350,7 @@ class ElasticSweep:
         _cabi.check(rc, "jitr_b200_eval_potentials")
         return c, so, co.to(torch.complex128)
 
+    @_on_device
     def _smatrix_large(self, central, spin_orbit, coulomb, out=None):
         """nbasis beyond the fused kernel (N > 64, e.g. the reference's Frescox regression cases with N = 100):
         per (energy, l) the systems  A = F_l + diag((V_c + V_C + (l.s) V_so) / E0)  of all samples and both j go
@@ -391,6 +408,7 @@ class ElasticSweep:
         status = torch.empty((B, self.nE), dtype=torch.int32, device=self.device)
         return S, nl, status
 
+    @_on_device
     def smatrix_params(self, model, params, out=None):
         """Built-in potentials: params (B, n_params) CUDA float64 -> S (B, E, 2, lmax+1), nl (B, E), status (B, E)."""
         import torch
@@ -416,6 +434,7 @@ class ElasticSweep:
         _cabi.check(rc, "jitr_b200_elastic_sweep_params")
         return S, nl, status
 
+    @_on_device
     def smatrix_tensors(self, central, spin_orbit=None, coulomb=None, out=None):
         """User potentials: (B, E, N) complex128 CUDA tensors of mesh values (MeV)."""
         import torch
@@ -444,6 +463,7 @@ class ElasticSweep:
         return S, nl, status
 
     # ------------------------------------------------------------------ observables
+    @_on_device
     def observables(self, S, nl, want_Ay=True, want_Q=True, out=None):
         """S (B, E, 2, lmax+1), nl (B, E) -> ElasticXS of CUDA tensors (B, E, n_angles) / (B, E)."""
         import torch
@@ -466,6 +486,7 @@ class ElasticSweep:
         _cabi.check(rc, "jitr_b200_elastic_observables")
         return ElasticXS(dsdo, Ay, Q, tr[..., 0], tr[..., 1])
 
+    @_on_device
     def misfit(self, S, nl, y, weights, scale=None, want_dsdo=False):
         """Weighted misfit against data, reduced on the device: sum_theta w (scale * dsdo - y)^2 per (sample, energy).
 
@@ -504,11 +525,14 @@ class ElasticSweep:
         S, nl, status = self.smatrix_params(model, params)
         return self.misfit(S, nl, y, weights, scale) + (status,)
 
-    def xs_params_to_host(self, model, params_host, dsdo_host, tr_host, chunk=8192):
+    @_on_device
+    def xs_params_to_host(self, model, params_host, dsdo_host, tr_host, chunk=8192, status_host=None):
         """End-to-end sweep with HOST buffers: ``params_host`` (B, n_params) pinned float64 ->
-        ``dsdo_host`` (B, E, n_angles) and ``tr_host`` (B, E, 2) pinned float64.  The sample axis is
-        processed in chunks on two device buffer sets so that the device->host copy of chunk i
-        overlaps the solve of chunk i+1 (copy stream + events).  Returns the number of systems solved."""
+        ``dsdo_host`` (B, E, n_angles) and ``tr_host`` (B, E, 2) pinned float64, and -- when given --
+        ``status_host`` (B, E) pinned int32 (JITR_B200_STATUS_* per (sample, energy): a non-finite or singular
+        system is reported, not silent).  The sample axis is processed in chunks on two device buffer sets so that
+        the device->host copy of chunk i overlaps the solve of chunk i+1 (copy stream + events).  Returns the
+        number of systems solved."""
         import torch
 
         B = params_host.shape[0]
@@ -547,6 +571,8 @@ class ElasticSweep:
             with torch.cuda.stream(self._copy_stream):
                 dsdo_host[s0 : s0 + n].copy_(dsdo[:n], non_blocking=True)
                 tr_host[s0 : s0 + n].copy_(tr[:n], non_blocking=True)
+                if status_host is not None:
+                    status_host[s0 : s0 + n].copy_(status, non_blocking=True)
                 b["done"] = torch.cuda.Event()
                 b["done"].record(self._copy_stream)
         cur.wait_stream(self._copy_stream)

@@ -31,10 +31,17 @@ MAX_ARG = np.log(1 / 1e-16)
 # ----------------------------------------------------------------------------
 # mesh / kinetic operator
 # ----------------------------------------------------------------------------
+_MESH_CACHE = {}
+
+
 def legendre_mesh(nbasis):
-    """Gauss-Legendre nodes/weights mapped to (0,1).  quadrature/quadrature.py:66-74."""
-    t, w = np.polynomial.legendre.leggauss(nbasis)
-    return 0.5 * (t + 1.0), 0.5 * w
+    """Gauss-Legendre nodes/weights mapped to (0,1).  quadrature/quadrature.py:66-74.  Computed once per nbasis, as the
+    reference does in Kernel.__init__ (quadrature/kernel.py:30-55); callers get copies."""
+    if nbasis not in _MESH_CACHE:
+        t, w = np.polynomial.legendre.leggauss(nbasis)
+        _MESH_CACHE[nbasis] = (0.5 * (t + 1.0), 0.5 * w)
+    x, w = _MESH_CACHE[nbasis]
+    return x.copy(), w.copy()
 
 
 def kinetic_bloch_matrix(nbasis, a, l):

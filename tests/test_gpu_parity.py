@@ -800,6 +800,30 @@ def test_dom_multi_energy_sweep_vs_oracle():
             assert abs(float(x.rxn[b, e]) - rxn) <= RTOL_XS * abs(rxn)
 
 
+def test_dom_mixed_target_sweep_equals_per_workspace_results():
+    """A DOM sweep whose energy rows belong to DIFFERENT targets (and Fermi energies): every row must use its own A, Z, Ef,
+    Coulomb correction and radii -- the sweep equals the single-workspace results row by row, and the oracle."""
+    from jitr_b200.optical_potentials import dom
+
+    g = np.load("tests/golden/dom_n40Ca_14MeV.npz")
+    ang = np.linspace(0.2, 3.0, 31)
+    solver = jitr_b200.Solver(32)
+    rx_ca = ElasticReaction((40, 20), (1, 0), mass_target=float(g["masses"][0]), mass_projectile=float(g["masses"][1]), Ef=float(g["Ef"]))
+    rx_pb = ElasticReaction((208, 82), (1, 0), mass_target=193687.12278341982, mass_projectile=float(g["masses"][1]), Ef=-5.65)
+    wss = [jitr_b200.DifferentialWorkspace.build_from_system(rx, rx.kinematics(E), R, solver, 16, ang)
+           for rx, E, R in ((rx_ca, 9.0, 10.5), (rx_pb, 9.0, 13.0), (rx_ca, 21.0, 10.5), (rx_pb, 21.0, 13.0))]
+    model = dom.DOM()
+    p = g["params"][:3]
+    x = jitr_b200.ElasticSweep(wss).xs_params(model, p)
+    for e, w in enumerate(wss):
+        one = jitr_b200.ElasticSweep([w]).xs_params(model, p)
+        assert torch.equal(one.dsdo[:, 0], x.dsdo[:, e]) and torch.equal(one.rxn[:, 0], x.rxn[:, e])
+        tgt = (w.reaction.target.A, w.reaction.target.Z)
+        ow = orc.ElasticWorkspace(32, 16, 10.5 if tgt[0] == 40 else 13.0, tuple(w.kinematics), ang, 0)
+        c, so, co = orc.dom_potentials(w.radial_grid(), (1, 0), tgt, w.kinematics.Ecm, float(w.reaction.Ef), p[1])
+        assert relerr(x.dsdo[1, e].cpu().numpy(), ow.xs(c, so, co)[0]) < RTOL_XS
+
+
 def test_blocked_solver_many_channels_two_border_tiles():
     """nch = 9 > 8: two tiles of border rows / right-hand sides, on the symmetric path, on partial pivoting, and with
     coefficients, against the reference algorithm."""
@@ -1043,6 +1067,25 @@ def test_device_percentiles_match_numpy_bit_for_bit():
             assert np.array_equal(got, want), (v.shape, q, np.abs(got - want).max())
     with pytest.raises(ValueError):
         uq.percentiles(torch.zeros((4, 4), device="cuda", dtype=torch.float64), [101.0])
+
+
+def test_device_percentiles_nan_column_like_numpy():
+    """A column that holds a NaN (a sample whose system was flagged non-finite) gives NaN, as numpy.percentile does; its
+    neighbours in the same 16-column tile are untouched."""
+    from jitr_b200 import uq
+
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((257, 40))
+    x[17, 5] = np.nan
+    x[200, 33] = np.nan
+    x[3, 34] = -0.0
+    q = [2.5, 50.0, 97.5]
+    with np.errstate(invalid="ignore"):
+        ref = np.percentile(x, q, axis=0)
+    got = uq.percentiles(torch.tensor(x, device="cuda"), q).cpu().numpy()
+    assert np.array_equal(np.isnan(got), np.isnan(ref)) and np.isnan(got[:, 5]).all() and np.isnan(got[:, 33]).all()
+    ok = ~np.isnan(ref)
+    assert np.array_equal(got[ok], ref[ok])
 
 
 def test_device_percentile_bands_of_a_sweep(golden):

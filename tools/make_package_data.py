@@ -26,3 +26,22 @@ out["wlh_p"] = wlh.get_samples((1, 1))
 for k, v in out.items():
     print(k, v.shape, v.dtype)
 np.savez_compressed(os.path.join(ROOT, "jitr_b200", "data", "posteriors.npz"), **out)
+
+# ---- default rest masses (utils/mass.py: mass.mass(A, Z)[0] with the default model, as reactions/reaction.py:167 uses it)
+from jitr.utils import mass as _mass  # noqa: E402
+
+_mass.init_mass_db()
+db = _mass.__MASS_DB__
+AZ, m0 = [], []
+for A, Z in sorted(set(zip(db["A"].astype(int), db["Z"].astype(int)))):
+    if A < 2:
+        continue
+    try:
+        v = _mass.mass(int(A), int(Z))[0]
+    except Exception:
+        continue
+    if v is not None and np.isfinite(v):
+        AZ.append((A, Z))
+        m0.append(float(v))
+np.savez_compressed(os.path.join(ROOT, "jitr_b200", "data", "masses.npz"), AZ=np.array(AZ, dtype=np.int32), m0=np.array(m0))
+print("masses", len(m0))
