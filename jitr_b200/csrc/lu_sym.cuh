@@ -57,6 +57,45 @@ struct SymGeom {
 template <int NS, class StoreW, class LoadU>
 __device__ __forceinline__ void sym_panel_eliminate(double2 (&p)[NS][9], const int nrows, const int lane,
                                                     double2& cacc, int& fail, StoreW store_w, LoadU load_u) {
+#ifdef JITR_SYM_FASTCHAIN
+    // Variant of the pivot chain (lu_packed.cuh): no column-maximum REDUX -- the threshold test is applied to the multipliers
+    // themselves, |Re l|, |Im l| <= 2^TAU for the rows below the pivot -- and  l = (w conj(d)) / |d|^2  so that the complex
+    // product runs beside the reciprocal.
+    double2 ysave = make_double2(0.0, 0.0), rsave = make_double2(0.0, 0.0);
+    int myfail = 0;
+    constexpr int kLim = 0x3ff00000 + (JITR_SYM_TAU_LOG2 << 20);
+#pragma unroll
+    for (int kk = 0; kk < 8; ++kk) {
+        const double2 dmine = p[0][kk];
+        const double mys = rcp_halley(fma(dmine.x, dmine.x, dmine.y * dmine.y));
+        if (lane == kk) {
+            const int m = max(__double2hiint(dmine.x) & 0x7fffffff, __double2hiint(dmine.y) & 0x7fffffff);
+            if (m < 0x00100000 || m >= 0x7ff00000) myfail = 1;
+            ysave = p[0][8];
+            rsave = make_double2(dmine.x * mys, -dmine.y * mys);
+        }
+#pragma unroll
+        for (int s = 0; s < NS; ++s) store_w(s, kk, p[s][kk]);
+        const double2 piv = shfl2(dmine, kk);
+        double2 u[9];
+        u[8] = shfl2(p[0][8], kk);
+        __syncwarp();
+#pragma unroll
+        for (int j = kk + 1; j < 8; ++j) u[j] = load_u(kk, j);
+        const double sc = __shfl_sync(kFull, mys, kk);
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            const int i = 32 * s + lane;
+            const double2 w = p[s][kk];
+            const double tx = fma(w.x, piv.x, w.y * piv.y), ty = fma(w.y, piv.x, -(w.x * piv.y));
+            const double2 l = make_double2(tx * sc, ty * sc);
+            if (i > kk && i < nrows && max(__double2hiint(l.x) & 0x7fffffff, __double2hiint(l.y) & 0x7fffffff) > kLim) myfail = 1;
+            p[s][kk] = l;
+#pragma unroll
+            for (int j = kk + 1; j < 9; ++j) cfnma(p[s][j], l, u[j]);
+        }
+    }
+#else
     // lane k (k < 8) keeps y_k and 1/d_k of "its" pivot for the corner term, formed once per panel
     double2 ysave = make_double2(0.0, 0.0), rsave = make_double2(0.0, 0.0);
     int myfail = 0;
@@ -97,6 +136,7 @@ __device__ __forceinline__ void sym_panel_eliminate(double2 (&p)[NS][9], const i
             for (int j = kk + 1; j < 9; ++j) cfnma(p[s][j], l, u[j]);
         }
     }
+#endif
     // corner -= sum_k y_k^2 / d_k : one term per lane k < 8, summed over the eight lanes
     double2 term = cmul(cmul(ysave, rsave), ysave);
 #pragma unroll
