@@ -19,6 +19,7 @@ namespace jitr {
 // ---------------------------------------------------------------------------------------------
 struct ObsArgs {
     int lmax, n_angles, n_energies, chunk;
+    int tables_in_smem;  // 0: the Legendre tables exceed shared memory (lmax >= 80 at 180 angles) and are read from global / L2
     long long n_samples;
     const double2* S;
     const int* nl;
@@ -48,16 +49,23 @@ template <bool MISFIT>
 __global__ void __launch_bounds__(kObsWarps * 32) elastic_observables_kernel(const ObsArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int L1 = A.lmax + 1, NA = A.n_angles;
-    double* Ps = reinterpret_cast<double*>(smem_raw);  // [L1][NA]
-    double* P1s = Ps + (size_t)L1 * NA;                 // [L1][NA]
-    double2* coef = reinterpret_cast<double2*>(P1s + (size_t)L1 * NA);  // [warps][2][L1]
     const int e = blockIdx.y;
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
     const double* Pg = A.P + (size_t)e * L1 * NA;
     const double* P1g = A.P1 + (size_t)e * L1 * NA;
-    for (int i = threadIdx.x; i < L1 * NA; i += blockDim.x) {
-        Ps[i] = Pg[i];
-        P1s[i] = P1g[i];
+    const double* Ps = Pg;    // [L1][NA]
+    const double* P1s = P1g;  // [L1][NA]
+    double2* coef = reinterpret_cast<double2*>(smem_raw);  // [warps][2][L1]
+    if (A.tables_in_smem) {
+        double* Pw = reinterpret_cast<double*>(smem_raw);
+        double* P1w = Pw + (size_t)L1 * NA;
+        coef = reinterpret_cast<double2*>(P1w + (size_t)L1 * NA);
+        for (int i = threadIdx.x; i < L1 * NA; i += blockDim.x) {
+            Pw[i] = Pg[i];
+            P1w[i] = P1g[i];
+        }
+        Ps = Pw;
+        P1s = P1w;
     }
     __syncthreads();
     double2* ca = coef + (size_t)warp * 2 * L1;  // coefficient of P_l
@@ -266,8 +274,12 @@ extern "C" int jitr_b200_elastic_sweep_tensors(int nbasis, int lmax, long long n
 
 static int launch_observables(ObsArgs a, const char* what, cudaStream_t st) {
     const int L1 = a.lmax + 1;
-    const size_t smem = (size_t)2 * L1 * a.n_angles * 8 + (size_t)kObsWarps * 2 * L1 * 16;
-    if (smem > 232448) return set_error(JITR_B200_ERR_UNSUPPORTED, "elastic_observables: (lmax+1)*n_angles tables exceed shared memory");
+    size_t smem = (size_t)2 * L1 * a.n_angles * 8 + (size_t)kObsWarps * 2 * L1 * 16;
+    a.tables_in_smem = 1;
+    if (smem > 232448) {  // large lmax (the Frescox regression cases reach 100): tables from global memory / L2
+        a.tables_in_smem = 0;
+        smem = (size_t)kObsWarps * 2 * L1 * 16;
+    }
     auto kern = a.misfit ? elastic_observables_kernel<true> : elastic_observables_kernel<false>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
         return set_cuda_error("cudaFuncSetAttribute(observables)");

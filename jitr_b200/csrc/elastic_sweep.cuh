@@ -446,8 +446,11 @@ __global__ void __launch_bounds__(SweepPlan<MODE>::kThreads, 1) elastic_sweep_ke
         }
         return (long long)__shfl_sync(0xffffffffu, v, 0);
     };
-    long long pair = next_pair();
-    bool active = pair < A.n_pairs;  // warp-uniform
+    // l-split mode: a work item is one partial wave l of one pair (both j), item = pair * (lmax + 1) + l
+    const long long n_items = A.lsplit ? A.n_pairs * L1 : A.n_pairs;
+    long long item = next_pair();
+    long long pair = A.lsplit ? item / L1 : item;
+    bool active = item < n_items;  // warp-uniform
     bool fresh = true;               // the pair's potentials have not been evaluated yet
     int e = 0, l = 0, jj = 0, nl = 0, singular = 0, nonfinite = 0;
     bool plus_small = false;  // |1 - S+| < tol at the current l
@@ -523,7 +526,8 @@ __global__ void __launch_bounds__(SweepPlan<MODE>::kThreads, 1) elastic_sweep_ke
             d1 = make_double2(t1 + a2 * (vc1.x / E0 - 1.0), a2 * (vc1.y / E0));
             so0 = make_double2(a2 * (vs0.x / E0), a2 * (vs0.y / E0));
             so1 = make_double2(a2 * (vs1.x / E0), a2 * (vs1.y / E0));
-            l = 0; jj = 0; nl = 0; singular = 0; nonfinite = 0;
+            l = A.lsplit ? (int)(item - pair * L1) : 0;
+            jj = 0; nl = 0; singular = 0; nonfinite = 0;
             fresh = false;
         }
         // ---- one system: partial wave l, j = l + 1/2 (jj = 0) or l - 1/2 (jj = 1)
@@ -563,7 +567,7 @@ __global__ void __launch_bounds__(SweepPlan<MODE>::kThreads, 1) elastic_sweep_ke
             if (l == 0) {  // l = 0 has the single j = 1/2 system; S- [0] = 0 (xs/elastic.py:112,152)
                 if (lane == 0) Sm_out[0] = zero2;
                 nl = 1;
-                pair_done = A.lmax == 0;
+                pair_done = A.lmax == 0 || A.lsplit;
                 l = 1;
             } else {
                 jj = 1;
@@ -571,8 +575,8 @@ __global__ void __launch_bounds__(SweepPlan<MODE>::kThreads, 1) elastic_sweep_ke
         } else {
             if (lane == 0) Sm_out[l] = S;
             nl = l + 1;
-            pair_done = l == A.lmax;
-            if (A.tol > 0.0) {
+            pair_done = l == A.lmax || A.lsplit;
+            if (A.tol > 0.0 && !A.lsplit) {
                 // (the vote keeps every branch of this loop provably warp-uniform for the compiler)
                 if (__all_sync(0xffffffffu, small && plus_small)) pair_done = true;
             }
@@ -581,7 +585,9 @@ __global__ void __launch_bounds__(SweepPlan<MODE>::kThreads, 1) elastic_sweep_ke
         }
         }  // !deferred
         if (__any_sync(0xffffffffu, pair_done)) {
-            if (!deferred) {
+            if (A.lsplit) {
+                if (lane == 0) A.lsplit_flags[item] = nonfinite ? JITR_B200_STATUS_NONFINITE : (singular ? JITR_B200_STATUS_SINGULAR : JITR_B200_STATUS_OK);
+            } else if (!deferred) {
                 double2* Sp_out = A.S_out + (size_t)pair * 2 * L1;
                 double2* Sm_out = Sp_out + L1;
                 for (int q = nl + lane; q <= A.lmax; q += 32) {
@@ -594,8 +600,9 @@ __global__ void __launch_bounds__(SweepPlan<MODE>::kThreads, 1) elastic_sweep_ke
                         nonfinite ? JITR_B200_STATUS_NONFINITE : (singular ? JITR_B200_STATUS_SINGULAR : JITR_B200_STATUS_OK);
                 }
             }
-            pair = next_pair();
-            active = pair < A.n_pairs;
+            item = next_pair();
+            pair = A.lsplit ? item / L1 : item;
+            active = item < n_items;
             fresh = true;
             if (!active && lane == 0) {
                 atomicMax(&last_iter, (int)it);
@@ -605,6 +612,34 @@ __global__ void __launch_bounds__(SweepPlan<MODE>::kThreads, 1) elastic_sweep_ke
         }
         lock.arrive(b, lane);
     }
+}
+
+// l-split mode, second step: the reference's data-dependent break (xs/elastic.py:178-181) applied to the finished S-matrices
+// of a pair -- same comparison, same order -- then zeros beyond the kept partial waves, nl and the status of the kept ones.
+static __global__ void sweep_finalize_kernel(const SweepArgs A) {
+    const long long pair = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pair >= A.n_pairs) return;
+    const int L1 = A.lmax + 1;
+    double2* Sp = A.S_out + (size_t)pair * 2 * L1;
+    double2* Sm = Sp + L1;
+    int nl = 1;
+    for (int l = 1; l <= A.lmax; ++l) {
+        nl = l + 1;
+        if (A.tol > 0.0) {
+            const double ep = 1.0 - Sp[l].x, em = 1.0 - Sm[l].x;
+            if (fma(ep, ep, Sp[l].y * Sp[l].y) < A.tol * A.tol && fma(em, em, Sm[l].y * Sm[l].y) < A.tol * A.tol) break;
+        }
+    }
+    int nonfinite = 0, singular = 0;
+    for (int l = 0; l < nl; ++l) {
+        const int f = A.lsplit_flags[pair * L1 + l];
+        nonfinite |= f == JITR_B200_STATUS_NONFINITE;
+        singular |= f == JITR_B200_STATUS_SINGULAR;
+    }
+    const double2 zero2 = make_double2(0.0, 0.0);
+    for (int l = nl; l <= A.lmax; ++l) Sp[l] = Sm[l] = zero2;
+    A.nl_out[pair] = nl;
+    A.status[pair] = nonfinite ? JITR_B200_STATUS_NONFINITE : (singular ? JITR_B200_STATUS_SINGULAR : JITR_B200_STATUS_OK);
 }
 
 template <bool PARAMS, int MODE>
@@ -617,15 +652,30 @@ int launch_sweep_mode(const SweepArgs& a, cudaStream_t st) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
         return set_cuda_error("cudaFuncSetAttribute(elastic_sweep)");
     const int sms = sm_count();
-    long long blocks = (a.n_pairs + warps - 1) / warps;
+    SweepArgs args = a;
+    // small batches: fewer pairs than half the resident warps -> one work item per partial wave (fast modes only: they
+    // handle a failed threshold test inside the kernel)
+    args.lsplit = 0;
+    if (MODE > 0 && MODE <= 40 && !a.pair_list && a.lmax > 0 && 2 * a.n_pairs < (long long)sms * warps) {
+        args.lsplit_flags = defer_buffer(a.n_pairs * (a.lmax + 1), st);
+        if (!args.lsplit_flags) return set_cuda_error("elastic sweep: l-split scratch");
+        args.lsplit_flags += 4;
+        args.lsplit = 1;
+    }
+    const long long items = args.lsplit ? a.n_pairs * (a.lmax + 1) : a.n_pairs;
+    long long blocks = (items + warps - 1) / warps;
     if (blocks > sms) blocks = sms;
     if (blocks < 1) return JITR_B200_OK;
-    SweepArgs args = a;
     args.work_counter = next_work_counter(st);
     if (!args.work_counter) return set_cuda_error("elastic_sweep work counter");
     kern<<<(unsigned)blocks, warps * 32, smem, st>>>(args);
     count_launch();
     if (cudaGetLastError() != cudaSuccess) return set_cuda_error("elastic_sweep launch");
+    if (args.lsplit) {
+        sweep_finalize_kernel<<<(unsigned)((a.n_pairs + 127) / 128), 128, 0, st>>>(args);
+        count_launch();
+        if (cudaGetLastError() != cudaSuccess) return set_cuda_error("elastic_sweep finalize launch");
+    }
     return JITR_B200_OK;
 }
 

@@ -17,6 +17,10 @@ struct SweepArgs {
     int* defer_count;
     const int* pair_list;
     const int* pair_count;
+    // small batches (fewer pairs than warps): one work item per (pair, l) instead of per pair, no early break inside the
+    // kernel; the partial waves kept (and the status) are decided afterwards from lsplit_flags[pair][l] (sweep_finalize)
+    int lsplit;
+    int* lsplit_flags;
     const double* That;
     const double* mesh_x;
     const double* bvec;

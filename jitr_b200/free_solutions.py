@@ -156,7 +156,100 @@ def coulomb_fg_steed(lmax, eta, rho, acc=1e-16, maxit=100000):
     return F, G, Fp, Gp
 
 
-# Steed's normalisation loses about |G_0 / F_0| ulps below the turning point: beyond this ratio use mpmath
+def _taylor_step(l, eta, rho0, u0, up0, h, nterms=48):
+    """One step of the Coulomb equation  u'' = (l(l+1)/rho^2 + 2 eta/rho - 1) u  from rho0 to rho0 + h by its Taylor series at
+    rho0 (|h| <= rho0/4: the terms fall off like 4^-n).  Returns (u, u') at rho0 + h."""
+    L = l * (l + 1.0)
+    c = np.zeros(nterms + 2)
+    c[0], c[1] = u0, up0
+    k0, k1 = L + 2.0 * eta * rho0 - rho0 * rho0, 2.0 * eta - 2.0 * rho0
+    r2 = rho0 * rho0
+    for m in range(nterms):
+        acc = (k0 - m * (m - 1.0)) * c[m] - 2.0 * rho0 * (m + 1.0) * m * c[m + 1]
+        if m >= 1:
+            acc += k1 * c[m - 1]
+        if m >= 2:
+            acc -= c[m - 2]
+        c[m + 2] = acc / (r2 * (m + 2.0) * (m + 1.0))
+    u = up = 0.0
+    for n in range(nterms + 1, -1, -1):  # Horner
+        u = u * h + c[n]
+    for n in range(nterms + 1, 0, -1):
+        up = up * h + n * c[n]
+    return u, up
+
+
+def coulomb_fg_below_turning_point(lmax, eta, rho):
+    """F_l, G_l, F_l', G_l' for l = 0..lmax at 0 < rho < 2 eta (inside the l = 0 turning point), without multi-precision
+    arithmetic.  Steed's normalisation cancels there (it loses |G_0/F_0| ulps), so:
+      1. Steed's method at rho_1 = 4 eta + 2, comfortably outside, gives G_0, G_0' to ~1e-15;
+      2. G_0 is carried INWARD to rho by Taylor-series steps of the Coulomb equation (steps of min(rho/4, 1), 48 terms): the
+         irregular solution grows inward, so the integration is stable and keeps the relative accuracy;
+      3. F_0'/F_0 at rho from the continued fraction CF1 + downward recurrence (stable for the regular solution), and the
+         Wronskian F'G - FG' = 1 gives  F_0 = 1 / (f_0 G_0 - G_0');
+      4. G_l by upward recurrence (stable for the irregular solution), F_l from the downward-recurrence ratios.
+    Returns (F, G, F', G') or None."""
+    eta, rho, Lm = float(eta), float(rho), int(lmax)
+    rho1 = 4.0 * eta + 2.0
+    st = coulomb_fg_steed(0, eta, rho1)
+    if st is None:
+        return None
+    g, gp = float(st[1][0]), float(st[3][0])
+    r = rho1
+    while r > rho:
+        h = max(rho - r, -min(0.25 * r, 1.0))  # |h| <= 1: no cancellation between the terms where the solution oscillates
+        g, gp = _taylor_step(0, eta, r, g, gp, h)
+        r += h
+    if not (np.isfinite(g) and np.isfinite(gp)):
+        return None
+    # CF1 at lmax, downward recurrence: F up to a common factor
+    xi = 1.0 / rho
+    S = lambda k: k * xi + eta / k  # noqa: E731
+    R2 = lambda k: 1.0 + (eta / k) ** 2  # noqa: E731
+    tiny = 1e-300
+    k = Lm + 1
+    f = S(k) or tiny
+    C, D = f, 0.0
+    for _ in range(200000):
+        a_, b_ = -R2(k), S(k) + S(k + 1)
+        D = (b_ + a_ * D) or tiny
+        C = (b_ + a_ / C) or tiny
+        D = 1.0 / D
+        delta = C * D
+        f *= delta
+        k += 1
+        if abs(delta - 1.0) < 1e-16:
+            break
+    else:
+        return None
+    F, Fp = np.zeros(Lm + 1), np.zeros(Lm + 1)
+    F[Lm] = 1e-60
+    Fp[Lm] = f * F[Lm]
+    for l in range(Lm, 0, -1):
+        Sl, Rl = S(l), np.sqrt(R2(l))
+        F[l - 1] = (Sl * F[l] + Fp[l]) / Rl
+        Fp[l - 1] = Sl * F[l - 1] - Rl * F[l]
+        if abs(F[l - 1]) > 1e250:
+            F[l - 1:] *= 1e-250
+            Fp[l - 1:] *= 1e-250
+    f0 = Fp[0] / F[0]
+    F0 = 1.0 / (f0 * g - gp)
+    scale = F0 / F[0]
+    F *= scale
+    Fp *= scale
+    G, Gp = np.zeros(Lm + 1), np.zeros(Lm + 1)
+    G[0], Gp[0] = g, gp
+    for l in range(Lm):
+        Sl, Rl = S(l + 1), np.sqrt(R2(l + 1))
+        G[l + 1] = (Sl * G[l] - Gp[l]) / Rl
+        Gp[l + 1] = Rl * G[l] - Sl * G[l + 1]
+    if not (np.all(np.isfinite(F)) and np.all(np.isfinite(G))):
+        return None
+    return F, G, Fp, Gp
+
+
+# Steed's normalisation loses about |G_0 / F_0| ulps below the turning point: beyond this ratio the inward integration of
+# G_0 + Wronskian route (coulomb_fg_below_turning_point) takes over; mpmath only if that fails (overflow far inside)
 STEED_MAX_G0_OVER_F0 = 1.0e2
 
 _TABLE_CACHE: dict = {}
@@ -175,6 +268,8 @@ def coulomb_hankel_table(lmax, eta, s):
         fg = coulomb_fg_steed(lmax + 1, eta, s) if eta > 0.0 else None
         if fg is not None and abs(fg[1][0]) <= STEED_MAX_G0_OVER_F0 * abs(fg[0][0]) and np.all(np.isfinite(fg[1])):
             F, G = fg[0], fg[1]
+        elif eta > 0.0 and (fb := coulomb_fg_below_turning_point(lmax + 1, eta, s)) is not None:
+            F, G = fb[0], fb[1]
         else:
             F = np.array([float(np.real(CoulombAsymptotics.F(s, int(l), eta))) for l in ls])
             G = np.array([float(np.real(CoulombAsymptotics.G(s, int(l), eta))) for l in ls])

@@ -352,49 +352,57 @@ class ElasticSweep:
 
     @_on_device
     def _smatrix_large(self, central, spin_orbit, coulomb, out=None):
-        """nbasis beyond the fused kernel (N > 64, e.g. the reference's Frescox regression cases with N = 100):
-        per (energy, l) the systems  A = F_l + diag((V_c + V_C + (l.s) V_so) / E0)  of all samples and both j go
-        through the general batched solve (jitr_b200_solve_batched); the early break of
-        xs/elastic.py:178-181 is applied afterwards (and the l loop stops once every sample has met it)."""
+        """nbasis beyond the fused kernel (N > 64, e.g. the reference's Frescox regression cases with N = 100): ONE batched
+        solve per energy.  All samples, all partial waves and both j of an energy form one batch of
+        jitr_b200_solve_batched: the free matrix of l = 0 is shared, the centrifugal term l(l+1)/(a x_n)^2 rides on the
+        diagonal with the local potential,  A = F_0 + diag((V_c + V_C + (l.s) V_so)/E0 + l(l+1)/(a x_n)^2),  the asymptotics are
+        per system.  The data-dependent break of xs/elastic.py:178-181 is applied afterwards on the device (first l >= 1
+        with |1 - S+| < tol and |1 - S-| < tol is the last one kept): no host synchronisation anywhere."""
         import torch
 
         B, L1 = central.shape[0], self.lmax + 1
         S, nl, status = self._alloc_S(B) if out is None else out
-        S.zero_()
-        status.zero_()
         vc = central if coulomb is None else central + coulomb
         q = self.solver.kernel.quadrature
-        eye = np.eye(self.N)
+        dev = self.device
+        # system s of a sample: s = 0 -> (l = 0, j = 1/2);  s = 2l - 1 -> (l, l + 1/2);  s = 2l -> (l, l - 1/2)
+        ns = 2 * L1 - 1
+        ls_of = np.zeros(ns, dtype=np.int64)
+        lds_of = np.zeros(ns)
+        for l in range(1, L1):
+            ls_of[2 * l - 1], lds_of[2 * l - 1] = l, float(l)
+            ls_of[2 * l], lds_of[2 * l] = l, -float(l + 1)
+        l_idx = torch.tensor(ls_of, device=dev)
+        lds = torch.tensor(lds_of, dtype=torch.float64, device=dev)
+        x = torch.tensor(q.abscissa, dtype=torch.float64, device=dev)
         for e, iw in enumerate(self.integral):
             kin = iw.kinematics
-            done = torch.zeros(B, dtype=torch.bool, device=self.device)
-            nle = torch.full((B,), L1, dtype=torch.int32, device=self.device)
-            for l in range(L1):
-                key = (e, l)
-                if key not in self._free_cache:
-                    self._free_cache[key] = torch.tensor(q.kinetic_matrix(iw.a, l) - eye, dtype=torch.complex128, device=self.device)
-                asym_l = self.asym[e, l].reshape(4, 1)
-                if l == 0 or spin_orbit is None:
-                    loc = vc[:, e]
-                    r = self.solver.solve_batch(iw.a, kin.Ecm, kin.k, 1, self._free_cache[key], asym_l, local_potential=loc)
-                    sp = r["S"][:, 0, 0]
-                    sm = sp if l > 0 else torch.zeros_like(sp)
-                    st = r["status"]
-                else:
-                    loc = torch.cat([vc[:, e] + l * spin_orbit[:, e], vc[:, e] - (l + 1) * spin_orbit[:, e]], dim=0)
-                    r = self.solver.solve_batch(iw.a, kin.Ecm, kin.k, 1, self._free_cache[key], asym_l, local_potential=loc)
-                    sp, sm = r["S"][:B, 0, 0], r["S"][B:, 0, 0]
-                    st = torch.maximum(r["status"][:B], r["status"][B:])
-                live = ~done
-                S[:, e, 0, l] = torch.where(live, sp, torch.zeros_like(sp))
-                S[:, e, 1, l] = torch.where(live, sm, torch.zeros_like(sm))
-                status[:, e] = torch.maximum(status[:, e], torch.where(live, st, torch.zeros_like(st)))
-                if l >= 1 and self.tol > 0:
-                    hit = live & ((1 - sp).abs() < self.tol) & ((1 - sm).abs() < self.tol)
-                    nle = torch.where(hit, torch.full_like(nle, l + 1), nle)
-                    done = done | hit
-                    if bool(done.all()):
-                        break
+            key = (e, 0)
+            if key not in self._free_cache:
+                self._free_cache[key] = torch.tensor(q.kinetic_matrix(iw.a, 0) - np.eye(self.N), dtype=torch.complex128, device=dev)
+            cent = (l_idx * (l_idx + 1)).to(torch.float64)[:, None] / (iw.a * x[None, :]) ** 2  # (ns, N)
+            loc = vc[:, e, None, :] + (kin.Ecm * cent)[None].to(torch.complex128)
+            if spin_orbit is not None:
+                loc = loc + lds[None, :, None] * spin_orbit[:, e, None, :]
+            asym_sys = self.asym[e][l_idx].reshape(1, ns, 4, 1).expand(B, ns, 4, 1).reshape(B * ns, 4, 1).contiguous()
+            r = self.solver.solve_batch(iw.a, kin.Ecm, kin.k, 1, self._free_cache[key], asym_sys, local_potential=loc.reshape(B * ns, self.N))
+            Ss = r["S"].reshape(B, ns)
+            st = r["status"].reshape(B, ns)
+            zero = torch.zeros((B, 1), dtype=Ss.dtype, device=dev)
+            sp = torch.cat([Ss[:, :1], Ss[:, 1::2]], dim=1)   # (B, L1)
+            sm = torch.cat([zero, Ss[:, 2::2]], dim=1)
+            stp = torch.cat([st[:, :1], st[:, 1::2]], dim=1)
+            stm = torch.cat([torch.zeros((B, 1), dtype=st.dtype, device=dev), st[:, 2::2]], dim=1)
+            if self.tol > 0 and L1 > 1:
+                small = ((1 - sp[:, 1:]).abs() < self.tol) & ((1 - sm[:, 1:]).abs() < self.tol)
+                none_before = small.to(torch.int32).cumsum(dim=1) == 0          # no hit up to and including l
+                nle = torch.clamp(none_before.sum(dim=1) + 2, max=L1).to(torch.int32)  # leading misses + the hit itself + l = 0
+            else:
+                nle = torch.full((B,), L1, dtype=torch.int32, device=dev)
+            keep = torch.arange(L1, device=dev)[None, :] < nle[:, None]
+            S[:, e, 0] = torch.where(keep, sp, torch.zeros_like(sp))
+            S[:, e, 1] = torch.where(keep, sm, torch.zeros_like(sm))
+            status[:, e] = torch.where(keep, torch.maximum(stp, stm), torch.zeros_like(stp)).max(dim=1).values
             nl[:, e] = nle
         return S, nl, status
 

@@ -205,3 +205,36 @@ def test_dom_host_parameter_rows(golden):
             k += 1
     with pytest.raises(ValueError):
         dom.shape_rows((1, 0), (40, 20), np.array([10.0]), -8.0, np.zeros((2, 5)))
+
+
+def test_coulomb_functions_below_turning_point_without_mpmath(monkeypatch):
+    """utils/free_solutions.py:39-109 without multi-precision arithmetic in EVERY regime: inside the l = 0 turning point
+    (rho < 2 eta, low-energy protons) G_0 is integrated inward from a point outside and F_0 follows from the Wronskian
+    (free_solutions.coulomb_fg_below_turning_point): <= 1e-13 of mpmath on an (eta, rho, l) grid, and the table builder no
+    longer reaches mpmath there."""
+    import mpmath as mp
+
+    from jitr_b200 import free_solutions as fs
+
+    worst = 0.0
+    for eta in (0.3, 0.59, 1.4, 3.0, 7.5, 15.0, 30.0):
+        for frac in (0.02, 0.3, 0.9, 0.99):
+            rho = 2 * eta * frac
+            F, G, Fp, Gp = fs.coulomb_fg_below_turning_point(9, eta, rho)
+            for l in (0, 1, 4, 9):
+                f, g = mp.coulombf(l, eta, rho), mp.coulombg(l, eta, rho)
+                worst = max(worst, float(abs(F[l] - f) / abs(f)), float(abs(G[l] - g) / abs(g)))
+                assert abs(F[l] * Gp[l] - Fp[l] * G[l] + 1.0) < 1e-10  # Wronskian F G' - F' G = -1
+    assert worst < 1e-13, worst
+
+    def boom(*a, **k):
+        raise AssertionError("mpmath reached")
+
+    want = fs.coulomb_hankel_table(6, 1.413707698547276, 1.1)  # eta of examples/coupled.py, well inside the turning point
+    ref = np.array([[complex(mp.coulombg(l, 1.413707698547276, 1.1)) + 1j * complex(mp.coulombf(l, 1.413707698547276, 1.1)) for l in range(7)]])
+    assert np.max(np.abs(want[:, 0] - ref[0]) / np.abs(ref[0])) < 1e-13
+    fs._TABLE_CACHE.clear()
+    monkeypatch.setattr(fs.CoulombAsymptotics, "F", staticmethod(boom))
+    monkeypatch.setattr(fs.CoulombAsymptotics, "G", staticmethod(boom))
+    again = fs.coulomb_hankel_table(6, 1.413707698547276, 1.1)
+    assert np.array_equal(again, want)
