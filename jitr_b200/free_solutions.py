@@ -191,6 +191,8 @@ def coulomb_fg_below_turning_point(lmax, eta, rho):
     Returns (F, G, F', G') or None."""
     eta, rho, Lm = float(eta), float(rho), int(lmax)
     rho1 = 4.0 * eta + 2.0
+    if not (0.0 < rho < rho1):
+        return None
     st = coulomb_fg_steed(0, eta, rho1)
     if st is None:
         return None
@@ -248,9 +250,8 @@ def coulomb_fg_below_turning_point(lmax, eta, rho):
     return F, G, Fp, Gp
 
 
-# Steed's normalisation loses about |G_0 / F_0| ulps below the turning point: beyond this ratio the inward integration of
-# G_0 + Wronskian route (coulomb_fg_below_turning_point) takes over; mpmath only if that fails (overflow far inside)
-STEED_MAX_G0_OVER_F0 = 1.0e2
+# Steed's normalisation loses about |G_0 / F_0| ulps INSIDE the turning point: there the inward integration of G_0 + Wronskian
+# route (coulomb_fg_below_turning_point) is used; mpmath only if a routine fails (overflow far inside the barrier)
 
 _TABLE_CACHE: dict = {}
 
@@ -265,10 +266,12 @@ def coulomb_hankel_table(lmax, eta, s):
         F = s * sc.spherical_jn(ls, s)
         G = -s * sc.spherical_yn(ls, s)
     else:
-        fg = coulomb_fg_steed(lmax + 1, eta, s) if eta > 0.0 else None
-        if fg is not None and abs(fg[1][0]) <= STEED_MAX_G0_OVER_F0 * abs(fg[0][0]) and np.all(np.isfinite(fg[1])):
+        # at or above the l = 0 turning point rho = 2 eta Steed's method holds ~1e-14 of |H| everywhere (also at the nodes of
+        # F_0, where |G_0/F_0| is large for a harmless reason); inside it the inward integration of G_0 + Wronskian takes over
+        fg = coulomb_fg_steed(lmax + 1, eta, s) if (eta > 0.0 and s >= 2.0 * eta) else None
+        if fg is not None and np.all(np.isfinite(fg[0])) and np.all(np.isfinite(fg[1])):
             F, G = fg[0], fg[1]
-        elif eta > 0.0 and (fb := coulomb_fg_below_turning_point(lmax + 1, eta, s)) is not None:
+        elif eta > 0.0 and s < 2.0 * eta and (fb := coulomb_fg_below_turning_point(lmax + 1, eta, s)) is not None:
             F, G = fb[0], fb[1]
         else:
             F = np.array([float(np.real(CoulombAsymptotics.F(s, int(l), eta))) for l in ls])
