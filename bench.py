@@ -302,7 +302,6 @@ class Config45:
         import torch
 
         import jitr_b200
-        from jitr_b200.free_solutions import coulomb_hankel_table  # noqa: F401
         from jitr_b200.reactions import ProjectileTargetSystem
 
         self.torch, self.dev, self.rank, self.world = torch, dev, rank, world
@@ -372,7 +371,8 @@ class Config45:
             ev[1].record()
             ev[2].record()
         if self.world > 1:
-            dist.gather(self.Sout, list(self.gather_out.unbind(0)) if self.rank == 0 else None, dst=0)
+            # (NCCL has no complex type: the S-matrices travel as interleaved float64 pairs)
+            dist.gather(self.torch.view_as_real(self.Sout), [self.torch.view_as_real(g) for g in self.gather_out.unbind(0)] if self.rank == 0 else None, dst=0)
         if ev:
             ev[3].record()
 
