@@ -1328,8 +1328,8 @@ static long long blk_slab_bytes(const BlkGeom& g, long long batch) {
     if (ctas > batch) ctas = batch;
     return (ctas * g.PR * g.PC + kBlkHeader) * 16;
 }
-static bool packed_path(int nbasis, int nch, int coeffs) {
-    return nch == 1 && !coeffs && packed_solve_supported(nbasis) && option(JITR_B200_OPT_SYMMETRIC) != 0;
+static bool packed_path(int nbasis, int nch, int /*coeffs*/) {
+    return nch == 1 && packed_solve_supported(nbasis) && option(JITR_B200_OPT_SYMMETRIC) != 0;
 }
 
 template <int MAXNS>

@@ -39,7 +39,7 @@ struct PackedGeom {
     __host__ __device__ static constexpr int row(int r) { return off(r >> 3) + (r & 7) * ld(r >> 3); }
     __host__ __device__ static constexpr int rhs(int r) { return row(r) + 8 * (r >> 3) + 8; }  // pad element = y_r
     static constexpr int SIZE = off(NB);       // complex elements of the packed matrix (incl. the y slots)
-    static constexpr int WARP_ELEMS = SIZE + 8;  // + the eight reciprocals of the current panel
+    static constexpr int WARP_ELEMS = SIZE;    // (the reciprocal of pivot k takes the place of the diagonal entry k once it is used)
 };
 
 // high words of |re|, |im| beyond 2^TAU (or NaN / Inf): the multiplier fails the threshold test
@@ -52,8 +52,7 @@ __device__ __forceinline__ bool mult_too_large(const double2 l) {
 
 // One panel (columns 8 kb .. 8 kb + 7), rows i = 32 s + lane relative to the panel start, nrows alive.
 template <int P, int NS>
-__device__ __forceinline__ void packed_panel(double2* __restrict__ M, double2* __restrict__ rinv_s, const int kb,
-                                             const int lane, double2& cacc, int& bad) {
+__device__ __forceinline__ void packed_panel(double2* __restrict__ M, const int kb, const int lane, double2& cacc, int& bad) {
     using G = PackedGeom<P>;
     const int J0 = 8 * kb, nrows = P - J0;
     const int ldk = G::ld(kb);
@@ -120,7 +119,11 @@ __device__ __forceinline__ void packed_panel(double2* __restrict__ M, double2* _
     const double2 tot = shfl2(term, 0);
     cacc.x -= tot.x;
     cacc.y -= tot.y;
-    if (lane < 8) rinv_s[lane] = rsave;
+    // 1/d_k replaces the diagonal entry (trailing update, back substitution); every row keeps its final right-hand side y
+    if (lane < 8) {
+        M[rb[0] + lane] = rsave;
+        M[ry[0]] = ysave;
+    }
 #pragma unroll
     for (int s = 0; s < NS; ++s) {
         const int i = 32 * s + lane;
@@ -130,8 +133,7 @@ __device__ __forceinline__ void packed_panel(double2* __restrict__ M, double2* _
 
 // lower tiles (tr, q), kb < q <= tr < NB, -= L[tr] W[q]^T  after panel kb; tile columns in blocks of three
 template <int P>
-__device__ __forceinline__ void packed_trailing(double2* __restrict__ M, const double2* __restrict__ rinv_s, const int kb,
-                                                const int lane) {
+__device__ __forceinline__ void packed_trailing(double2* __restrict__ M, const int kb, const int lane) {
     using G = PackedGeom<P>;
     constexpr int NB = G::NB;
     const int J0 = 8 * kb;
@@ -145,7 +147,8 @@ __device__ __forceinline__ void packed_trailing(double2* __restrict__ M, const d
     double c1[4], c2[4];
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
-        const double2 r = rinv_s[4 * (fk >> 1) + s];
+        const int jd = 4 * (fk >> 1) + s;
+        const double2 r = M[G::off(kb) + jd * G::ld(kb) + J0 + jd];  // 1/d of column J0 + jd
         c1[s] = part ? r.y : r.x;
         c2[s] = part ? r.x : -r.y;
     }
@@ -195,23 +198,52 @@ __device__ __forceinline__ void packed_trailing(double2* __restrict__ M, const d
 template <int P>
 __device__ __forceinline__ double2 packed_ldlt(double2* __restrict__ M, const int lane, int& bad) {
     using G = PackedGeom<P>;
-    double2* rinv_s = M + G::SIZE;
     double2 cacc = make_double2(0.0, 0.0);
     int mybad = 0;
     JITR_PH_INIT
 #pragma unroll 1
     for (int kb = 0; kb < G::NB; ++kb) {
-        if (P - 8 * kb > 32) packed_panel<P, 2>(M, rinv_s, kb, lane, cacc, mybad);
-        else packed_panel<P, 1>(M, rinv_s, kb, lane, cacc, mybad);
+        if (P - 8 * kb > 32) packed_panel<P, 2>(M, kb, lane, cacc, mybad);
+        else packed_panel<P, 1>(M, kb, lane, cacc, mybad);
         JITR_PH(0)
         if (kb == G::NB - 1) break;
         __syncwarp();
-        packed_trailing<P>(M, rinv_s, kb, lane);
+        packed_trailing<P>(M, kb, lane);
         __syncwarp();
         JITR_PH(2)
     }
     bad = __any_sync(kFull, mybad) ? 1 : 0;
     return cacc;
+}
+
+// z = A^-1 b from the factors packed_ldlt leaves behind (W below the diagonal, 1/d on it, y = L^-1 b in the y slots):
+// z_i = (y_i - sum_{j > i} w_ji z_j) / d_i, column oriented -- row j of the packed storage holds w_ji for all i < j, lane i
+// (+32) accumulates its own entry, z_j is broadcast as it becomes final.  z[h] = entry lane + 32 h.  (core.py:63-82)
+template <int P>
+__device__ __forceinline__ void packed_back_substitute(const double2* __restrict__ M, const int lane, double2 (&z)[2]) {
+    using G = PackedGeom<P>;
+    double2 t[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int i = lane + 32 * h;
+        t[h] = i < P ? M[G::rhs(i)] : make_double2(0.0, 0.0);
+        z[h] = make_double2(0.0, 0.0);
+    }
+#pragma unroll 1
+    for (int j = P - 1; j >= 0; --j) {
+        const int rowj = G::row(j);
+        const double2 tj = shfl2(j >= 32 ? t[1] : t[0], j & 31);
+        const double2 zj = cmul(tj, M[rowj + j]);
+        if (lane == (j & 31)) {
+            if (j >= 32) z[1] = zj;
+            else z[0] = zj;
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int i = lane + 32 * h;
+            if (i < j) cfnma(t[h], M[rowj + i], zj);
+        }
+    }
 }
 
 }  // namespace jitr

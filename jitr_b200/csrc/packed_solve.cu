@@ -245,7 +245,8 @@ packed_solve_kernel(const GenArgs A, const int* __restrict__ symflag, const int 
             if (lane == 0) defer_list[atomicAdd(defer_count, 1)] = (int)sysi;
             continue;
         }
-        if (lane == 0) {
+        double2 ue = zero2;
+        {
             const double2* as = A.asym + (size_t)sysi * A.asym_stride;  // [4][1]: Hp, Hm, Hpp, Hmp
             const double2 Hp = as[0], Hm = as[1], Hpp = as[2], Hmp = as[3];
             const double2 R = make_double2(-corner.x / (a * a), -corner.y / (a * a));  // core.py:15-22
@@ -257,11 +258,24 @@ packed_solve_kernel(const GenArgs A, const int* __restrict__ symflag, const int 
             const double w0 = A.weights[0];
             const double2 sh = cmul(S, Hpp);
             const double2 v = make_double2(Hmp.x * w0 - sh.x, Hmp.y * w0 - sh.y);
-            A.R[sysi] = R;
-            A.S[sysi] = S;
-            A.uext[sysi] = make_double2(-0.5 * v.y, 0.5 * v.x);
-            const bool nonfinite = !(isfinite(S.x) && isfinite(S.y));
-            A.status[sysi] = nonfinite ? JITR_B200_STATUS_NONFINITE : JITR_B200_STATUS_OK;
+            ue = make_double2(-0.5 * v.y, 0.5 * v.x);
+            if (lane == 0) {
+                A.R[sysi] = R;
+                A.S[sysi] = S;
+                A.uext[sysi] = ue;
+                const bool nonfinite = !(isfinite(S.x) && isfinite(S.y));
+                A.status[sysi] = nonfinite ? JITR_B200_STATUS_NONFINITE : JITR_B200_STATUS_OK;
+            }
+        }
+        if (A.coeffs) {
+            // x = A^-1 (b u'_ext) = u'_ext A^-1 b   (core.py:81-82, one channel)
+            double2 z[2];
+            packed_back_substitute<P>(M, lane, z);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int i = lane + 32 * h;
+                if (i < N) A.coeffs[(size_t)sysi * N + i] = cmul(ue, z[h]);
+            }
         }
         __syncwarp();
     }

@@ -1165,6 +1165,18 @@ def test_packed_single_channel_solve_vs_oracle(N):
             assert relerr(out2["S"][b].cpu().numpy(), S) < RTOL_S
         elif b not in tiny:
             assert torch.equal(out2["S"][b], out["S"][b])
+    # wavefunction coefficients from the same factors (back substitution on the packed triangle, core.py:63-82)
+    outw = solver.solve_batch(a, E0, k0, 1, free, torch.tensor(asym, device="cuda"), local_potential=torch.tensor(loc, device="cuda"),
+                              nonlocal_potential=torch.tensor(nl, device="cuda"), wavefunction=True)
+    assert int(outw["status"].abs().sum()) == 0
+    bvec = orc.boundary_vector(N)
+    for b in range(0, B, 3):
+        F_ = orc.free_matrix(N, a, [l])
+        V_ = orc.interaction_matrix(N, k0, E0, a, 1, local_potential=loc[b], nonlocal_potential=nl[b])
+        R, S, Ainv, up = orc.solve_smatrix(F_ + V_, bvec, *[np.ascontiguousarray(asym[i]) for i in range(4)], np.ones(1), a, 1, N)
+        x = orc.solution_coeffs(Ainv, bvec, up, 1, N)
+        assert normerr(outw["coeffs"][b].cpu().numpy(), x) < (1e-9 if b not in tiny else 1e-6), (N, b)
+        assert relerr(outw["S"][b].cpu().numpy(), S) < (RTOL_S if b not in tiny else 1e-7)
     # a ready interaction matrix, and local-only input, take the same kernel
     inter = np.stack([orc.interaction_matrix(N, k0, E0, a, 1, local_potential=loc[b], nonlocal_potential=nl[b]) for b in range(4)])
     out3 = solver.solve_batch(a, E0, k0, 1, free, torch.tensor(asym, device="cuda"), interaction_matrix=torch.tensor(inter, device="cuda"))
