@@ -28,6 +28,13 @@
 #pragma once
 #include "lu_sym.cuh"
 
+#ifndef JITR_PACKED_TR_UNROLL
+#define JITR_PACKED_TR_UNROLL 1
+#endif
+#define JITR_PRAGMA_STR(x) _Pragma(#x)
+#define JITR_PRAGMA_UNROLL(n) JITR_PRAGMA_STR(unroll n)
+#define JITR_PACKED_TR_PRAGMA JITR_PRAGMA_UNROLL(JITR_PACKED_TR_UNROLL)
+
 namespace jitr {
 
 template <int P>
@@ -167,7 +174,7 @@ __device__ __forceinline__ void packed_trailing(double2* __restrict__ M, const i
                         b[q][h][s] = __hiloint2double(__double2hiint(v) ^ bflip, __double2loint(v));
                     }
             }
-#pragma unroll 1
+        JITR_PACKED_TR_PRAGMA
         for (int tr = q0; tr < NB; ++tr) {
             const int rbase = G::off(tr) + rho * G::ld(tr);
             double a[4];

@@ -174,25 +174,16 @@ packed_solve_kernel(const GenArgs A, const int* __restrict__ symflag, const int 
     const double2* Vsrc_base = A.interaction ? A.interaction : A.nonlocal_;
     const double2 zero2 = make_double2(0.0, 0.0);
     unsigned parity = 0;
-    // systems are handed out one ahead: while a warp eliminates system i, the matrix of its next system is on its way to L2
-    // (cp.async.bulk.prefetch.L2), so the staging copies and the symmetry walk of the next round find it there
+    // (A cp.async.bulk.prefetch.L2 of the next system's matrix one system ahead was measured and removed: ncu showed 97 KB of DRAM
+    // reads per system instead of the algorithmic 57.6 KB -- the prefetched lines were fetched again -- and 7 % less throughput.)
     auto grab = [&]() -> long long {
         long long v = 0;
-        if (lane == 0) {
-            v = (long long)atomicAdd(work_counter, 1ULL);
-            if (v < A.batch && Vsrc_base) {
-                const unsigned long long src = (unsigned long long)(Vsrc_base + (size_t)v * N * N);
-                const unsigned bytes = (unsigned)(N * N) * 16u;
-                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
-            }
-        }
+        if (lane == 0) v = (long long)atomicAdd(work_counter, 1ULL);
         return __shfl_sync(kFull, v, 0);
     };
-    long long next = grab();
     while (true) {
-        const long long sysi = next;
+        const long long sysi = grab();
         if (sysi >= A.batch) break;
-        next = grab();
         bool defer = !free_ok;
         const double* sy = A.sys + (size_t)sysi * A.sys_stride;
         const double a = sy[0], E0 = sy[1], k0 = sy[2];

@@ -26,6 +26,22 @@ def timeit(fn, reps=3):
     return a.elapsed_time(b) / reps
 
 
+def main5(B, rng, out, dev):
+    """config 5 only, through the workloads generator (the real potential of examples/coupled.py)"""
+    from jitr_b200 import workloads as W
+
+    c = W.CONFIG5
+    solver = jitr_b200.Solver(c["N"])
+    free = torch.tensor(solver.free_matrix(c["a"], [0, 0, 0], list(c["E"]), [c["mu"]] * 3), device=dev)
+    r = solver.radial_grid(c["a"], c["k"])
+    Vt = torch.tensor(W.config5_potentials(r, B), device=dev)
+    asym3 = torch.tensor(np.tile(np.array([[0.3 + 0.9j], [0.3 - 0.9j], [-0.8 + 0.2j], [-0.8 - 0.2j]]), (1, 3)), device=dev)
+    ms = timeit(lambda: solver.solve_batch(c["a"], c["E"][0], c["k"], 3, free, asym3, local_potential=Vt))
+    n = 150
+    out["config5_real_potential"] = {"batch": B, "ms": ms, "solves_per_s": B / ms * 1e3, "tflops": B * (8 * n**3 / 3 + 8 * n**2 * 3) / ms / 1e9}
+    print(json.dumps(out))
+
+
 def main():
     B = int(sys.argv[1]) if len(sys.argv) > 1 else 10000
     import os
@@ -35,11 +51,14 @@ def main():
     if os.environ.get("JITR_B200_ASSUME_SYM"):
         _c.lib().jitr_b200_set_option(_c.OPT_ASSUME_SYMMETRIC_KERNEL, 1)
     only4 = bool(os.environ.get("ONLY4"))
+    only5 = bool(os.environ.get("ONLY5"))
     rng = np.random.default_rng(0)
     out = {}
     dev = "cuda"
     asym1 = torch.tensor(np.array([[0.3 + 0.9j], [0.3 - 0.9j], [-0.8 + 0.2j], [-0.8 - 0.2j]]), device=dev)
     # ---- config 4
+    if only5:
+        return main5(B, rng, out, dev)
     N = 60
     solver = jitr_b200.Solver(N)
     a, E0, k0 = 14.5, 29.8, 1.2
