@@ -299,34 +299,55 @@ struct PackedSolver {
         const double2 dd[2] = {d0, d1};
         // ---- lower triangle of That + diag(d), identity padding, y = b.  One block row per step: left of the diagonal tile a
         // lane owns column c = lane (+32) and has up to sixteen independent loads in flight; the diagonal tile uses all lanes
+        // (two block rows per step: up to thirty-two independent loads per lane in flight -- That comes from L2)
 #pragma unroll 1
-        for (int tr = 0; tr < G::NB; ++tr) {
-            const int r0 = 8 * tr;
-            const int nrow = min(8, N - r0);  // warp-uniform
-            double2* Mb = M + G::off(tr);
-            const int ldt = G::ld(tr);
+        for (int tr0 = 0; tr0 < G::NB; tr0 += 2) {
+            double t[2][2][8], td[2][2];
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int c = lane + 32 * h;
-                if (c < r0) {
-                    const double* Tp = That + r0 * N + c;
-                    double t[8];
+            for (int u = 0; u < 2; ++u) {
+                const int tr = tr0 + u, r0 = 8 * tr;
+                const int nrow = min(8, N - r0);  // warp-uniform
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) t[i] = i < nrow ? __ldg(Tp + i * N) : 0.0;
+                for (int k = 0; k < 2; ++k) {  // the diagonal tile: element (r0 + i, r0 + jj), i = (lane >> 3) + 4 k, jj = lane & 7
+                    const int i = (lane >> 3) + 4 * k, jj = lane & 7;
+                    td[u][k] = (tr < G::NB && jj < i && r0 + i < N) ? __ldg(That + (r0 + i) * N + r0 + jj) : 0.0;
+                }
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) Mb[i * ldt + c] = make_double2(t[i], 0.0);
+                for (int h = 0; h < 2; ++h) {
+                    const int c = lane + 32 * h;
+                    if (tr < G::NB && c < r0) {
+                        const double* Tp = That + r0 * N + c;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) t[u][h][i] = i < nrow ? __ldg(Tp + i * N) : 0.0;
+                    }
                 }
             }
-            const int hrow = r0 >> 5;
 #pragma unroll
-            for (int k = 0; k < 2; ++k) {
-                const int i = (lane >> 3) + 4 * k, jj = lane & 7;
-                const int r = r0 + i, c = r0 + jj;
-                const double2 dv = shfl2(hrow ? dd[1] : dd[0], r & 31);  // the diagonal entry of row r lives in lane r & 31
-                if (jj <= i) {
-                    double2 v = make_double2(jj == i ? 1.0 : 0.0, 0.0);  // identity padding
-                    if (r < N) v = (jj == i) ? dv : make_double2(__ldg(That + r * N + c), 0.0);
-                    Mb[i * ldt + c] = v;
+            for (int u = 0; u < 2; ++u) {
+                const int tr = tr0 + u, r0 = 8 * tr;
+                if (tr < G::NB) {
+                    double2* Mb = M + G::off(tr);
+                    const int ldt = G::ld(tr);
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int c = lane + 32 * h;
+                        if (c < r0) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) Mb[i * ldt + c] = make_double2(t[u][h][i], 0.0);
+                        }
+                    }
+                    const int hrow = r0 >> 5;
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) {
+                        const int i = (lane >> 3) + 4 * k, jj = lane & 7;
+                        const int r = r0 + i, c = r0 + jj;
+                        const double2 dv = shfl2(hrow ? dd[1] : dd[0], r & 31);  // the diagonal entry of row r lives in lane r & 31
+                        if (jj <= i) {
+                            double2 v = make_double2(jj == i ? 1.0 : 0.0, 0.0);  // identity padding
+                            if (r < N) v = (jj == i) ? dv : make_double2(td[u][k], 0.0);
+                            Mb[i * ldt + c] = v;
+                        }
+                    }
                 }
             }
         }
@@ -478,14 +499,22 @@ __global__ void __launch_bounds__(SweepPlan<MODE>::kThreads, 1) elastic_sweep_ke
         while (clock64() - t0 < JITR_SWEEP_STAGGER) __nanosleep(200);
     }
 #endif
+    // The packed modes run their panels in a runtime loop: their elimination code is a few KB and fits the instruction cache
+    // whatever the warps are doing, so they run free (JITR_PACKED_LOCKSTEP=1 puts them in lock step again).
+#ifndef JITR_PACKED_LOCKSTEP
+#define JITR_PACKED_LOCKSTEP 0
+#endif
+    constexpr bool kLock = MODE < 48 || JITR_PACKED_LOCKSTEP != 0;
     for (unsigned it = 0;; ++it) {
         const int b = it % LockStep::K;
-        if (it >= LockStep::K) lock.wait(b, (it / LockStep::K - 1) & 1);  // every warp has finished iteration it - K
-        {
+        if (kLock) {
+            if (it >= LockStep::K) lock.wait(b, (it / LockStep::K - 1) & 1);  // every warp has finished iteration it - K
             const int na = *(volatile int*)&warps_active;
             __threadfence_block();
             const int li = *(volatile int*)&last_iter;
             if (__all_sync(0xffffffffu, na == 0 && (int)it >= li + LockStep::K)) break;
+        } else if (!active) {
+            break;
         }
         if (!active) {
             lock.arrive(b, lane);
@@ -604,13 +633,13 @@ __global__ void __launch_bounds__(SweepPlan<MODE>::kThreads, 1) elastic_sweep_ke
             pair = A.lsplit ? item / L1 : item;
             active = item < n_items;
             fresh = true;
-            if (!active && lane == 0) {
+            if (kLock && !active && lane == 0) {
                 atomicMax(&last_iter, (int)it);
                 __threadfence_block();
                 atomicSub(&warps_active, 1);
             }
         }
-        lock.arrive(b, lane);
+        if (kLock) lock.arrive(b, lane);
     }
 }
 
