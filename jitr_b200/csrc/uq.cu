@@ -34,8 +34,12 @@ __device__ __forceinline__ double pct_virtual_index(long long n, double percent)
     return __dmul_rn((double)(n - 1), __ddiv_rn(percent, 100.0));
 }
 
+// NQ = number of quantiles, a compile-time value: the per-thread arrays over the quantiles stay in registers (the runtime-nq
+// version of round 1 indexed them dynamically and kept them in local memory: 534 LDL/STL in its SASS)
+template <int NQ>
 __global__ void __launch_bounds__(kPctCols* kPctRows) percentile_kernel(const double* __restrict__ x, long long S, long long M,
-                                                                        const PctQ Q, int nq, double* __restrict__ out) {
+                                                                        const PctQ Q, double* __restrict__ out) {
+    constexpr int nq = NQ;
     extern __shared__ __align__(16) unsigned char pct_smem[];
     typedef unsigned long long (*ull_rows)[kPctCols];
     ull_rows prefix = reinterpret_cast<ull_rows>(pct_smem);                                 // [nq][16] selected key so far
@@ -64,7 +68,8 @@ __global__ void __launch_bounds__(kPctCols* kPctRows) percentile_kernel(const do
         for (int i = threadIdx.x; i < nq * kPctCols * 256; i += blockDim.x) (&hist[0][0][0])[i] = 0u;
         __syncthreads();
         if (live) {
-            unsigned long long want[kPctMaxQ];  // leading digits of the class that holds the wanted rank
+            unsigned long long want[NQ];  // leading digits of the class that holds the wanted rank
+#pragma unroll
             for (int t = 0; t < nq; ++t) want[t] = pass == 0 ? 0ULL : prefix[t][tc] >> (shift + 8);
             // four independent rows in flight per thread
             for (long long r0 = tr; r0 < S; r0 += 4 * kPctRows) {
@@ -80,6 +85,7 @@ __global__ void __launch_bounds__(kPctCols* kPctRows) percentile_kernel(const do
                     const unsigned long long k = pct_key(v[u]);
                     if (pass == 0 && v[u] != v[u]) nan_col[tc] = 1u;  // (benign race: every writer stores 1)
                     const unsigned long long lead = pass == 0 ? 0ULL : k >> (shift + 8);
+#pragma unroll
                     for (int t = 0; t < nq; ++t)
                         if (lead == want[t]) atomicAdd(&hist[t][tc][(unsigned)(k >> shift) & 255u], 1u);
                 }
@@ -108,7 +114,8 @@ __global__ void __launch_bounds__(kPctCols* kPctRows) percentile_kernel(const do
     __syncthreads();
     if (live) {
         // per-thread partial results first: one shared-memory atomic per thread and target at the end
-        unsigned long long sel[kPctMaxQ], cnt[kPctMaxQ], mn[kPctMaxQ];
+        unsigned long long sel[NQ], cnt[NQ], mn[NQ];
+#pragma unroll
         for (int t = 0; t < nq; ++t) {
             sel[t] = prefix[t][tc];
             cnt[t] = 0ULL;
@@ -125,12 +132,14 @@ __global__ void __launch_bounds__(kPctCols* kPctRows) percentile_kernel(const do
             for (int u = 0; u < 4; ++u) {
                 if (r0 + (long long)u * kPctRows >= S) break;
                 const unsigned long long k = pct_key(v[u]);
+#pragma unroll
                 for (int t = 0; t < nq; ++t) {
                     if (k <= sel[t]) ++cnt[t];
                     else if (k < mn[t]) mn[t] = k;
                 }
             }
         }
+#pragma unroll
         for (int t = 0; t < nq; ++t) {
             atomicAdd(&n_le[t][tc], cnt[t]);
             atomicMin(&above[t][tc], mn[t]);
@@ -174,10 +183,26 @@ extern "C" int jitr_b200_percentiles(const double* values, long long n_samples, 
         Q.q[t] = q_host[t];
     }
     const size_t smem = (size_t)nq * kPctCols * (4 * 8 + 256 * 4);
-    if (cudaFuncSetAttribute(percentile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-        return set_cuda_error("cudaFuncSetAttribute(percentiles)");
     const unsigned blocks = (unsigned)((n_columns + kPctCols - 1) / kPctCols);
-    percentile_kernel<<<blocks, kPctCols * kPctRows, smem, static_cast<cudaStream_t>(stream)>>>(values, n_samples, n_columns, Q, nq, out);
+    bool ok = true;
+    auto launch = [&](auto kern) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+            ok = false;
+            return;
+        }
+        kern<<<blocks, kPctCols * kPctRows, smem, static_cast<cudaStream_t>(stream)>>>(values, n_samples, n_columns, Q, out);
+    };
+    switch (nq) {
+        case 1: launch(percentile_kernel<1>); break;
+        case 2: launch(percentile_kernel<2>); break;
+        case 3: launch(percentile_kernel<3>); break;
+        case 4: launch(percentile_kernel<4>); break;
+        case 5: launch(percentile_kernel<5>); break;
+        case 6: launch(percentile_kernel<6>); break;
+        case 7: launch(percentile_kernel<7>); break;
+        default: launch(percentile_kernel<8>); break;
+    }
+    if (!ok) return set_cuda_error("cudaFuncSetAttribute(percentiles)");
     count_launch();
     if (cudaGetLastError() != cudaSuccess) return set_cuda_error("percentiles launch");
     return JITR_B200_OK;
