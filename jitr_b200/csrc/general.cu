@@ -763,6 +763,172 @@ __device__ __forceinline__ void blk_sym_diag(const double2* __restrict__ Pn, dou
     }
 }
 
+// the same with symmetric 2 x 2 pivots (pair_mask from blk_sym_diag22): only called to RETRY a panel that failed the test,
+// out of line so that the 1 x 1 code of the hot loop keeps its registers
+// rows below the diagonal block of the panel at kp (its columns are in Pn, the factorised block in L11 / slot): forward
+// substitution, multipliers -> Lx (scaled) and Wx (unscaled), growth check, U rows for the coefficients
+__device__ __noinline__ void blk_sym_rows22(const double2* __restrict__ Pn, const double2* __restrict__ L11,
+                                             const double2* __restrict__ slot, double2* __restrict__ Lx, double2* __restrict__ Wx,
+                                             double2* __restrict__ M, const int ld, const int kp, const int P, const int PR,
+                                             const bool coeffs, int* __restrict__ fail, const int pair_mask, const int tid) {
+    if (tid < 8 || tid >= PR - kp) return;
+    double2 p[8], w[8];
+    {
+        const double2* rowp = Pn + tid * kBlkLpLd;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) p[c] = rowp[c];
+    }
+    // the growth bound applies to the rows of A; the border rows only have to stay finite
+    const double lim = (kp + tid < P) ? kBlkSymMaxMult : 1.0e300;
+    bool bad = false;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        if (j > 0 && ((pair_mask >> (j - 1)) & 1)) continue;  // second column of a 2 x 2 pivot: done with the first
+        if (j < 7 && ((pair_mask >> j) & 1)) {
+            // 2 x 2 pivot (columns j, j + 1):  [l0 l1] = [w0 w1] E,  E = D^-1 = [[slot[j], slot[8 + j]], [slot[8 + j], slot[j + 1]]]
+            const double2 w0 = p[j], w1 = p[j + 1];
+            w[j] = w0;
+            w[j + 1] = w1;
+            const double2 e00 = slot[j], e01 = slot[8 + j], e11 = slot[j + 1];
+            double2 l0 = cmul(w0, e00), l1 = cmul(w0, e01);
+            const double2 t0 = cmul(w1, e01), t1 = cmul(w1, e11);
+            l0.x += t0.x; l0.y += t0.y;
+            l1.x += t1.x; l1.y += t1.y;
+            p[j] = l0;
+            p[j + 1] = l1;
+            bad |= !(fabs(l0.x) <= lim && fabs(l0.y) <= lim && fabs(l1.x) <= lim && fabs(l1.y) <= lim);
+#pragma unroll
+            for (int c = j + 2; c < 8; ++c) {
+                cfnma(p[c], l0, L11[j * 8 + c]);
+                cfnma(p[c], l1, L11[(j + 1) * 8 + c]);
+            }
+        } else {
+            w[j] = p[j];
+            const double2 l = cmul(p[j], slot[j]);
+            p[j] = l;
+            bad |= !(fabs(l.x) <= lim && fabs(l.y) <= lim);
+#pragma unroll
+            for (int c = j + 1; c < 8; ++c) cfnma(p[c], l, L11[j * 8 + c]);
+        }
+    }
+    double2* lp = Lx + (tid - 8) * kBlkLpLd;
+    double2* wp = Wx + (tid - 8) * kBlkLpLd;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        lp[c] = p[c];
+        wp[c] = w[c];
+    }
+    if (bad) *fail = 1;
+    if (coeffs) {
+        // U = D L^T for the back substitution of the coefficients: row kp + c of U holds the unscaled multipliers w_c
+        // of the rows below (the border rows give Y = L^-1 B in the RHS columns)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) M[(size_t)(kp + c) * ld + kp + tid] = w[c];
+    }
+}
+
+// blk_sym_diag with symmetric 2 x 2 pivots, for the retry of a panel that failed the 1 x 1 test.
+// Symmetric 2 x 2 pivots (round 2).  With a purely real potential (examples/coupled.py) the matrix is real symmetric INDEFINITE and
+// a diagonal entry of a Schur complement passes through zero now and then: 86 % of the l = 0 systems of BASELINE config 5 met one
+// somewhere and left the symmetric path.  When |d_j| < |a_j+1,j| / 16 (and j < 7: the pair must not straddle the panel) the columns
+// j, j + 1 are eliminated together with the 2 x 2 block D = [[d_j, a_j+1,j], [a_j+1,j, d_j+1]] as the pivot (Bunch-Kaufman without
+// interchanges): [l0 l1] = [w0 w1] D^-1, trailing update  -= l0 w0^T + l1 w1^T  -- the same L W^T form, so the tile kernels do not
+// change.  pair_mask bit j = columns j, j + 1 form a pair; D^-1 = [[slot[j], slot[8+j]], [slot[8+j], slot[j+1]]].  The multiplier
+// bound stays the safety net (9 % of the l = 0 systems still fail it and finish with partial pivoting; 0 % from l = 3 on).
+// Not used when coefficients are wanted (the back substitution assumes a triangular U).
+__device__ __noinline__ void blk_sym_diag22(const double2* __restrict__ Pn, double2* __restrict__ L11, double2* __restrict__ slot,
+                                             double2* __restrict__ M, const int ld, const int kp, const bool coeffs,
+                                             int* __restrict__ fail, int* __restrict__ pair_mask_out, const int lane) {
+    double2 p[8];
+    {
+        const double2* rowp = Pn + (lane < 8 ? lane : 0) * kBlkLpLd;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) p[c] = rowp[c];
+    }
+    bool bad = false;
+    int mask = 0;
+    bool skip = false;  // warp-uniform: column j is the second of a pair
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        if (skip) {
+            skip = false;
+            continue;
+        }
+        bool pair = false;
+        if (j < 7 && !coeffs) {
+            // decided by the pivot's own lane on max(|re|, |im|), broadcast
+            const double ma = fmax(fabs(p[j].x), fabs(p[j].y)), mb = fmax(fabs(p[j + 1].x), fabs(p[j + 1].y));
+            pair = __shfl_sync(kFull, (int)(16.0 * ma < mb), j) != 0;
+        }
+        if (pair) {
+            // D = [[a, b], [b, d]] : a, b on lane j (p[j], p[j+1]), d on lane j + 1 (p[j+1])
+            const double2 a = shfl2(p[j], j), b = shfl2(p[j + 1], j), d = shfl2(p[j + 1], j + 1);
+            double2 det = cmul(a, d);
+            const double2 bb = cmul(b, b);
+            det.x -= bb.x; det.y -= bb.y;
+            const double2 dinv = crecip_fast(det);
+            const double2 e00 = cmul(d, dinv), e11 = cmul(a, dinv);
+            double2 e01 = cmul(b, dinv);
+            e01.x = -e01.x; e01.y = -e01.y;
+            double2 r0[8], r1[8];
+#pragma unroll
+            for (int c = j + 2; c < 8; ++c) {
+                r0[c] = shfl2(p[c], j);
+                r1[c] = shfl2(p[c], j + 1);
+            }
+            if (lane == 0) {
+                slot[j] = e00;
+                slot[j + 1] = e11;
+                slot[8 + j] = e01;
+            }
+            if (lane > j + 1 && lane < 8) {
+                const double2 w0 = p[j], w1 = p[j + 1];
+                double2 l0 = cmul(w0, e00), l1 = cmul(w0, e01);
+                const double2 t0 = cmul(w1, e01), t1 = cmul(w1, e11);
+                l0.x += t0.x; l0.y += t0.y;
+                l1.x += t1.x; l1.y += t1.y;
+                p[j] = l0;
+                p[j + 1] = l1;
+                bad |= !(fabs(l0.x) <= kBlkSymMaxMult && fabs(l0.y) <= kBlkSymMaxMult && fabs(l1.x) <= kBlkSymMaxMult &&
+                         fabs(l1.y) <= kBlkSymMaxMult);
+#pragma unroll
+                for (int c = j + 2; c < 8; ++c) {
+                    cfnma(p[c], l0, r0[c]);
+                    cfnma(p[c], l1, r1[c]);
+                }
+            }
+            if (lane == j) bad |= !(isfinite(dinv.x) && isfinite(dinv.y));  // singular 2 x 2 block
+            mask |= 1 << j;
+            skip = true;
+        } else {
+            const double2 rinv = crecip_fast(shfl2(p[j], j));
+            double2 rowj[8];
+#pragma unroll
+            for (int c = j + 1; c < 8; ++c) rowj[c] = shfl2(p[c], j);
+            if (lane == 0) slot[j] = rinv;
+            if (lane > j && lane < 8) {
+                const double2 l = cmul(p[j], rinv);
+                p[j] = l;
+                bad |= !(fabs(l.x) <= kBlkSymMaxMult && fabs(l.y) <= kBlkSymMaxMult);
+#pragma unroll
+                for (int c = j + 1; c < 8; ++c) cfnma(p[c], l, rowj[c]);
+            }
+            if (lane == j) bad |= !(isfinite(rinv.x) && isfinite(rinv.y));  // zero pivot
+        }
+    }
+    if (lane == 0) *pair_mask_out = mask;
+    if (lane < 8) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) L11[lane * 8 + c] = p[c];
+        if (coeffs) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+                if (c >= lane) M[(size_t)(kp + lane) * ld + kp + c] = p[c];
+        }
+        if (bad) *fail = 1;
+    }
+}
+
 // Wavefunction coefficients (core.py:63-82): X = U^-1 Y for the nch right-hand sides (columns P..P+nch-1 of the
 // slab, which holds U and Y = L^-1 P B after the elimination), eight rows at a time from the bottom; then
 // x = sum_i u'_ext,i X[:, i].  Out of line: keeps its registers out of the elimination loop.
@@ -1017,6 +1183,17 @@ __global__ void __launch_bounds__(kBlkThreads, 512 / kBlkThreads) block_solve_ke
                 BLK_PH(10)
                 __syncthreads();
                 BLK_PH(11)
+                if (misc[4] && !coeffs) {
+                    // panel k0 failed the 1 x 1 test (in its diagonal block or in a row below): retry it with symmetric 2 x 2
+                    // pivots -- Pn still holds its columns
+                    __syncthreads();
+                    if (tid == 0) misc[4] = 0;
+                    __syncthreads();
+                    if (warp == 0) blk_sym_diag22(Pn, L11, slot, M, ld, k0, coeffs, &misc[4], &misc[7], lane);
+                    __syncthreads();
+                    blk_sym_rows22(Pn, L11, slot, Lp, Wp, M, ld, k0, P, PR, coeffs, &misc[4], misc[7], tid);
+                    __syncthreads();
+                }
                 if (misc[4]) {  // CTA-uniform: a multiplier beyond the threshold (or not finite) in panel k0
                     if (tid == 0) misc[5] = k0;
                     __syncthreads();
@@ -1055,6 +1232,15 @@ __global__ void __launch_bounds__(kBlkThreads, 512 / kBlkThreads) block_solve_ke
                 __syncthreads();
                 blk_sym_rows(Pn, L11, slot, Lp2, Wp2, M, ld, R0, P, PR, coeffs, &misc[4], tid);
                 __syncthreads();
+                if (misc[4] && !coeffs) {  // retry panel B with symmetric 2 x 2 pivots
+                    __syncthreads();
+                    if (tid == 0) misc[4] = 0;
+                    __syncthreads();
+                    if (warp == 0) blk_sym_diag22(Pn, L11, slot, M, ld, R0, coeffs, &misc[4], &misc[7], lane);
+                    __syncthreads();
+                    blk_sym_rows22(Pn, L11, slot, Lp2, Wp2, M, ld, R0, P, PR, coeffs, &misc[4], misc[7], tid);
+                    __syncthreads();
+                }
                 if (misc[4]) {
                     // panel B failed: complete panel A's update of the slab, then partial pivoting from R0
                     blk_sym_rest(M, ld, R0, ntr, 1, Lpd, Wpd, &misc[6], lane);
