@@ -352,13 +352,24 @@ class Config45:
                                           R=W.CONFIG4["R"], a=W.CONFIG4["a"], l_major=True, out=self.U, device=self.dev)
 
     def _solve_all(self, U=None, V=None):
-        for l in range(self.lmax + 1):
-            if self.cfg == 4:
-                o = self.solver.solve_batch(self.a, self.E0, self.k0, 1, self.free[l], self.asym[l], nonlocal_potential=(self.U if U is None else U)[l])
-            else:
-                o = self.solver.solve_batch(self.a, self.E0, self.k0, 3, self.free[l], self.asym[l], local_potential=self.V if V is None else V)
-            self.Sout[l].copy_(o["S"])
-            self.status[l].copy_(o["status"])
+        """ONE batched call for all (partial wave, sample) systems: the free matrix is picked per system (free_index = l), the
+        asymptotics are per system (jitr_b200_solve_batched_indexed)."""
+        torch = self.torch
+        L1, S = self.lmax + 1, self.B
+        if not hasattr(self, "_free_stack"):
+            self._free_stack = torch.stack(self.free).contiguous()
+            self._free_index = torch.arange(L1, dtype=torch.int32, device=self.dev).repeat_interleave(S).contiguous()
+            self._asym_sys = torch.stack(self.asym)[self._free_index.long()].contiguous()   # (L1 * S, 4, nch)
+        if self.cfg == 4:
+            Uall = (self.U if U is None else U).reshape(L1 * S, self.N, self.N)
+            o = self.solver.solve_batch(self.a, self.E0, self.k0, 1, self._free_stack, self._asym_sys, nonlocal_potential=Uall,
+                                        free_index=self._free_index)
+        else:
+            Vall = (self.V if V is None else V).unsqueeze(0).expand(L1, S, 3, 3, self.N).reshape(L1 * S, 3, 3, self.N)
+            o = self.solver.solve_batch(self.a, self.E0, self.k0, 3, self._free_stack, self._asym_sys, local_potential=Vall,
+                                        free_index=self._free_index)
+        self.Sout.copy_(o["S"].reshape(L1, S, self.nch, self.nch))
+        self.status.copy_(o["status"].reshape(L1, S))
 
     def step(self, timed_events=None):
         import torch.distributed as dist
@@ -414,9 +425,9 @@ class Config45:
     def e2e_bytes(self):
         if self.cfg == 4:
             return (int(self.rows_host.numel() * 8), int(self.S_host.numel() * 16 + self.st_host.numel() * 4),
-                    "nonlocal_forms.perey_buck_kernels (pinned host (V, W, beta, R, a) rows -> kernels generated in HBM) + Solver.solve_batch per l -> pinned host S, status")
+                    "nonlocal_forms.perey_buck_kernels (pinned host (V, W, beta, R, a) rows -> kernels generated in HBM) + ONE Solver.solve_batch(free_index=l) -> pinned host S, status")
         return (int(self.V_host.numel() * 16), int(self.S_host.numel() * 16 + self.st_host.numel() * 4),
-                "Solver.solve_batch per l (pinned host coupling potentials [S,3,3,50] -> pinned host S, status)")
+                "ONE Solver.solve_batch(free_index=l) (pinned host coupling potentials [S,3,3,50] -> pinned host S, status)")
 
     def cpu_run(self, per_worker, warm=False):
         from oracle import cpu_sweep

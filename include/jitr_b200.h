@@ -164,6 +164,18 @@ int jitr_b200_solve_batched(int nbasis, int nch, long long batch, const double* 
                             double* workspace, int* status, void* stream);
 
 /*
+ * The same solve for a batch that mixes partial waves (or energies): `free_matrices` holds n_free free matrices [n_free][n][n] and
+ * system b uses number free_index[b] (device int32 array of `batch` entries) -- e.g. all (sample, l) systems of a nonlocal sweep in ONE
+ * call, free_index = l, with per-system asymptotics (asym_stride = 4 nch).  Everything else as jitr_b200_solve_batched.
+ */
+int jitr_b200_solve_batched_indexed(int nbasis, int nch, long long batch, const double* free_matrices, int n_free,
+                                    const int* free_index, const double* local, const double* nonlocal_,
+                                    const double* interaction, const double* wsqrt, const double* sys, int sys_stride,
+                                    const double* bvec, const double* asym, long long asym_stride, const double* weights,
+                                    double* R, double* S, double* uext, double* coeffs, double* workspace, int* status,
+                                    void* stream);
+
+/*
  * Weighted misfit of the angular distributions against data, reduced on the device (the batched likelihood of a
  * calibration loop, e.g. the log-likelihood of the reference's quickstart notebook): same inputs as
  * jitr_b200_elastic_observables, plus

@@ -48,6 +48,7 @@ SIGNATURES = {
     "jitr_b200_perey_buck_kernels": (_i, [_i, _i, _ll, _p, _p, _d, _p, _ll, _ll, _p]),
     "jitr_b200_solve_workspace_bytes": (_ll, [_i, _i, _ll, _i]),
     "jitr_b200_solve_batched": (_i, [_i, _i, _ll, _p, _ll, _p, _p, _p, _p, _p, _i, _p, _p, _ll, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "jitr_b200_solve_batched_indexed": (_i, [_i, _i, _ll, _p, _i, _p, _p, _p, _p, _p, _p, _i, _p, _p, _ll, _p, _p, _p, _p, _p, _p, _p, _p]),
     "jitr_b200_fp64_probe": (_i, [_i, _i, _i, C.POINTER(_d), C.POINTER(_ll)]),
 }
 

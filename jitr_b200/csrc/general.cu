@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(kGenThreads) general_solve_kernel(const GenArg
         double2* M = IN_SMEM ? Msm : A.workspace + (size_t)sysi * n * ld;
         const double* sy = A.sys + (size_t)sysi * A.sys_stride;
         const double a = sy[0], E0 = sy[1], k0 = sy[2];
-        const double2* F = A.free_matrix + (size_t)sysi * A.free_stride;
+        const double2* F = A.free_matrix + (A.free_index ? (size_t)A.free_index[sysi] * A.n * A.n : (size_t)sysi * A.free_stride);
         // ---------------- assemble [A | B]
         const double nl_scale = (a / k0) / k0 / E0;  // kernel.py:202 (x radius), rmatrix.py:175-178 (/k0, /E0)
         for (int idx = tid; idx < n * ld; idx += nt) {
@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(256, 1) warp_solve_kernel(const GenArgs A) {
     for (long long sysi = (long long)blockIdx.x * nwarps + warp; sysi < A.batch; sysi += (long long)gridDim.x * nwarps) {
         const double* sy = A.sys + (size_t)sysi * A.sys_stride;
         const double a = sy[0], E0 = sy[1], k0 = sy[2];
-        const double2* F = A.free_matrix + (size_t)sysi * A.free_stride;
+        const double2* F = A.free_matrix + (A.free_index ? (size_t)A.free_index[sysi] * A.n * A.n : (size_t)sysi * A.free_stride);
         const double nl_scale = (a / k0) / k0 / E0;  // kernel.py:202 (x radius), rmatrix.py:175-178 (/k0, /E0)
         const double2* Vint = A.interaction ? A.interaction + (size_t)sysi * N * N : nullptr;
         const double2* Vnl = (!A.interaction && A.nonlocal_) ? A.nonlocal_ + (size_t)sysi * N * N : nullptr;
@@ -1043,7 +1043,7 @@ __global__ void __launch_bounds__(kBlkThreads, 512 / kBlkThreads) block_solve_ke
         const long long sysi = A.sys_list ? (long long)A.sys_list[isys] : isys;
         const double* sy = A.sys + (size_t)sysi * A.sys_stride;
         const double a = sy[0], E0 = sy[1], k0s = sy[2];
-        const double2* F = A.free_matrix + (size_t)sysi * A.free_stride;
+        const double2* F = A.free_matrix + (A.free_index ? (size_t)A.free_index[sysi] * A.n * A.n : (size_t)sysi * A.free_stride);
         const double nl_scale = (a / k0s) / k0s / E0;  // kernel.py:202 (x radius), rmatrix.py:175-178 (/k0, /E0)
         // complex symmetric systems (local couplings on the symmetric free matrix) are eliminated with diagonal pivots;
         // from the first panel with a multiplier beyond the threshold on, partial pivoting takes over
@@ -1451,9 +1451,10 @@ __global__ void __launch_bounds__(kBlkThreads, 512 / kBlkThreads) block_solve_ke
 }
 
 // 0 -> *flag stays 0 when the n x n matrix F equals its transpose bit for bit
-__global__ void symcheck_kernel(const double2* __restrict__ F, int n, int* __restrict__ flag) {
+__global__ void symcheck_kernel(const double2* __restrict__ F_all, int n, int* __restrict__ flag) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= n * n) return;
+    const double2* F = F_all + (size_t)blockIdx.y * n * n;  // blockIdx.y: which of the free matrices
     const int i = idx / n, j = idx - i * n;
     if (j >= i) return;
     const double2 x = F[idx], y = F[(size_t)j * n + i];
@@ -1484,7 +1485,7 @@ static int launch_block_solve_t(const GenArgs& a, const BlkGeom& g, cudaStream_t
 static int launch_symcheck(const GenArgs& a, int* flag, cudaStream_t st) {
     if (cudaMemsetAsync(flag, 0, sizeof(int), st) != cudaSuccess) return set_cuda_error("solve_batched symmetry flag");
     const int nn = a.n * a.n;
-    symcheck_kernel<<<(nn + 255) / 256, 256, 0, st>>>(a.free_matrix, a.n, flag);
+    symcheck_kernel<<<dim3((nn + 255) / 256, a.free_index ? a.n_free : 1), 256, 0, st>>>(a.free_matrix, a.n, flag);
     count_launch();
     if (cudaGetLastError() != cudaSuccess) return set_cuda_error("symcheck launch");
     return JITR_B200_OK;
@@ -1564,12 +1565,11 @@ extern "C" long long jitr_b200_solve_workspace_bytes(int nbasis, int nch, long l
     return in_smem > 232448 ? batch * n * (n + nch) * 16 : 0;
 }
 
-extern "C" int jitr_b200_solve_batched(int nbasis, int nch, long long batch, const double* free_matrix,
-                                       long long free_stride, const double* local, const double* nonlocal_,
-                                       const double* interaction, const double* wsqrt, const double* sys,
-                                       int sys_stride, const double* bvec, const double* asym, long long asym_stride,
-                                       const double* weights, double* R, double* S, double* uext, double* coeffs,
-                                       double* workspace, int* status, void* stream) {
+static int solve_batched_impl(int nbasis, int nch, long long batch, const double* free_matrix, long long free_stride,
+                              const int* free_index, int n_free, const double* local, const double* nonlocal_,
+                              const double* interaction, const double* wsqrt, const double* sys, int sys_stride,
+                              const double* bvec, const double* asym, long long asym_stride, const double* weights, double* R,
+                              double* S, double* uext, double* coeffs, double* workspace, int* status, void* stream) {
     if (batch == 0) return JITR_B200_OK;  // empty batch (its tensors have null data pointers)
     if (nbasis < 1 || nch < 1 || nch > kMaxCh || batch < 0 || !free_matrix || !sys || !bvec || !asym || !weights || !R ||
         !S || !uext || !status)
@@ -1579,6 +1579,7 @@ extern "C" int jitr_b200_solve_batched(int nbasis, int nch, long long batch, con
     GenArgs a{};
     a.N = nbasis; a.nch = nch; a.n = nbasis * nch; a.batch = batch;
     a.free_matrix = reinterpret_cast<const double2*>(free_matrix); a.free_stride = free_stride;
+    a.free_index = free_index; a.n_free = n_free;
     a.local = reinterpret_cast<const double2*>(local);
     a.nonlocal_ = reinterpret_cast<const double2*>(nonlocal_);
     a.interaction = reinterpret_cast<const double2*>(interaction);
@@ -1638,4 +1639,26 @@ extern "C" int jitr_b200_solve_batched(int nbasis, int nch, long long batch, con
     count_launch();
     if (cudaGetLastError() != cudaSuccess) return set_cuda_error("general_solve launch");
     return JITR_B200_OK;
+}
+
+extern "C" int jitr_b200_solve_batched(int nbasis, int nch, long long batch, const double* free_matrix,
+                                       long long free_stride, const double* local, const double* nonlocal_,
+                                       const double* interaction, const double* wsqrt, const double* sys,
+                                       int sys_stride, const double* bvec, const double* asym, long long asym_stride,
+                                       const double* weights, double* R, double* S, double* uext, double* coeffs,
+                                       double* workspace, int* status, void* stream) {
+    return solve_batched_impl(nbasis, nch, batch, free_matrix, free_stride, nullptr, 1, local, nonlocal_, interaction, wsqrt, sys,
+                              sys_stride, bvec, asym, asym_stride, weights, R, S, uext, coeffs, workspace, status, stream);
+}
+
+extern "C" int jitr_b200_solve_batched_indexed(int nbasis, int nch, long long batch, const double* free_matrices, int n_free,
+                                               const int* free_index, const double* local, const double* nonlocal_,
+                                               const double* interaction, const double* wsqrt, const double* sys,
+                                               int sys_stride, const double* bvec, const double* asym, long long asym_stride,
+                                               const double* weights, double* R, double* S, double* uext, double* coeffs,
+                                               double* workspace, int* status, void* stream) {
+    if (batch > 0 && (n_free < 1 || !free_index))
+        return set_error(JITR_B200_ERR_BAD_ARG, "solve_batched_indexed: free_index and n_free >= 1 required");
+    return solve_batched_impl(nbasis, nch, batch, free_matrices, 0, free_index, n_free, local, nonlocal_, interaction, wsqrt, sys,
+                              sys_stride, bvec, asym, asym_stride, weights, R, S, uext, coeffs, workspace, status, stream);
 }

@@ -33,6 +33,9 @@ struct GenArgs {
     // the systems sys_list[0 .. *sys_count) instead of 0 .. batch
     const int* sys_list;
     const int* sys_count;
+    // jitr_b200_solve_batched_indexed: n_free free matrices, system b uses number free_index[b] (free_stride is 0 then)
+    const int* free_index;
+    int n_free;
 };
 
 

@@ -210,7 +210,7 @@ packed_solve_kernel(const GenArgs A, const int* __restrict__ symflag, const int 
             parity ^= 1u;
         }
         if (!defer) {
-            const double2* F = A.free_matrix;
+            const double2* F = A.free_matrix + (A.free_index ? (size_t)A.free_index[sysi] * N * N : 0);
             const double2* Vloc = (!A.interaction && A.local) ? A.local + (size_t)sysi * N : nullptr;
             unsigned long long diff = 0ULL;
             if (!Vsrc) diff = stage_system<P, false, false, false>(M, F, nullptr, Vloc, ws, nl_scale, E0, N, lane);

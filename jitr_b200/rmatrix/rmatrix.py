@@ -224,9 +224,12 @@ class Solver:
 
     def solve_batch(
         self, a, E0, k0, nch, free_matrix, asym, local_potential=None, nonlocal_potential=None,
-        interaction_matrix=None, basis_boundary=None, weights=None, wavefunction=False, batch=None,
+        interaction_matrix=None, basis_boundary=None, weights=None, wavefunction=False, batch=None, free_index=None,
     ):
         """Batched ``solve`` on the device.
+
+        ``free_index`` (B,) int32 CUDA tensor: the batch mixes partial waves -- ``free_matrix`` is then (n_free, n, n) and system b
+        uses ``free_matrix[free_index[b]]`` (one call for all (sample, l) systems of a sweep; give ``asym`` per system).
 
         ``free_matrix``: (n, n) shared or (B, n, n) complex128 CUDA tensor; ``asym``: (4, nch) shared or
         (B, 4, nch) rows H+, H-, H+', H-'; potentials with a leading batch axis:
@@ -245,10 +248,10 @@ class Solver:
         dev = free_matrix.device if isinstance(free_matrix, torch.Tensor) and free_matrix.is_cuda else torch.device("cuda", torch.cuda.current_device())
         with torch.cuda.device(dev):
             return self._solve_batch_on(dev, a, E0, k0, nch, free_matrix, asym, local_potential, nonlocal_potential, interaction_matrix,
-                                        basis_boundary, weights, wavefunction, batch)
+                                        basis_boundary, weights, wavefunction, batch, free_index)
 
     def _solve_batch_on(self, dev, a, E0, k0, nch, free_matrix, asym, local_potential, nonlocal_potential, interaction_matrix,
-                        basis_boundary, weights, wavefunction, batch):
+                        basis_boundary, weights, wavefunction, batch, free_index=None):
         import torch
 
         L = _cabi.lib()
@@ -270,8 +273,11 @@ class Solver:
                 batch = interaction_matrix.shape[0]
         B = int(batch)
         free_matrix = free_matrix.to(device=dev, dtype=torch.complex128).contiguous()
-        free_stride = 0 if free_matrix.dim() == 2 else n * n
+        free_stride = 0 if (free_matrix.dim() == 2 or free_index is not None) else n * n
         assert free_matrix.shape[-2:] == (n, n)
+        if free_index is not None:
+            free_index = free_index.to(device=dev, dtype=torch.int32).contiguous()
+            assert free_matrix.dim() == 3 and free_index.shape == (B,)
         asym = asym.to(device=dev, dtype=torch.complex128).contiguous()
         asym_stride = 0 if asym.dim() == 2 else 4 * nch
         assert asym.shape[-2:] == (4, nch)
@@ -304,12 +310,20 @@ class Solver:
         if ws_bytes < 0:
             raise ValueError("jitr_b200_solve_workspace_bytes: bad arguments")
         ws = torch.empty((ws_bytes // 16,), dtype=torch.complex128, device=dev) if ws_bytes else None
-        rc = L.jitr_b200_solve_batched(
-            nb, nch, B, _cabi.ptr(free_matrix), free_stride, _cabi.ptr(loc), _cabi.ptr(nl), _cabi.ptr(interaction_matrix),
-            _cabi.ptr(tabs["wsqrt"]), _cabi.ptr(sys_t), sys_stride, _cabi.ptr(bvec), _cabi.ptr(asym), asym_stride,
-            _cabi.ptr(w_t), _cabi.ptr(R), _cabi.ptr(S), _cabi.ptr(uext), _cabi.ptr(coeffs), _cabi.ptr(ws),
-            _cabi.ptr(status), _cabi.stream_ptr(),
-        )
+        if free_index is not None:
+            rc = L.jitr_b200_solve_batched_indexed(
+                nb, nch, B, _cabi.ptr(free_matrix), int(free_matrix.shape[0]), _cabi.ptr(free_index), _cabi.ptr(loc), _cabi.ptr(nl),
+                _cabi.ptr(interaction_matrix), _cabi.ptr(tabs["wsqrt"]), _cabi.ptr(sys_t), sys_stride, _cabi.ptr(bvec), _cabi.ptr(asym),
+                asym_stride, _cabi.ptr(w_t), _cabi.ptr(R), _cabi.ptr(S), _cabi.ptr(uext), _cabi.ptr(coeffs), _cabi.ptr(ws),
+                _cabi.ptr(status), _cabi.stream_ptr(),
+            )
+        else:
+            rc = L.jitr_b200_solve_batched(
+                nb, nch, B, _cabi.ptr(free_matrix), free_stride, _cabi.ptr(loc), _cabi.ptr(nl), _cabi.ptr(interaction_matrix),
+                _cabi.ptr(tabs["wsqrt"]), _cabi.ptr(sys_t), sys_stride, _cabi.ptr(bvec), _cabi.ptr(asym), asym_stride,
+                _cabi.ptr(w_t), _cabi.ptr(R), _cabi.ptr(S), _cabi.ptr(uext), _cabi.ptr(coeffs), _cabi.ptr(ws),
+                _cabi.ptr(status), _cabi.stream_ptr(),
+            )
         _cabi.check(rc, "jitr_b200_solve_batched")
         out = dict(R=R, S=S, uext=uext, status=status)
         if wavefunction:

@@ -1268,3 +1268,32 @@ def test_frescox_regression_cases(golden, cid):
     ref = g[f"{cid}_dsdo"]
     assert np.max(np.abs(dsdo - ref) / np.maximum(ref, 1e-6 * ref.max())) < 1e-7                     # the reference itself
     assert abs(float(x.rxn[0]) - float(g[f"{cid}_rxn"])) < RTOL_XS * abs(float(g[f"{cid}_rxn"]))
+
+
+def test_indexed_free_matrices_equal_per_partial_wave_calls():
+    """jitr_b200_solve_batched_indexed: one call for a batch that mixes partial waves (free matrix picked per system, asymptotics
+    per system) gives bit for bit what one call per partial wave gives -- single channel (packed kernel) and coupled (CTA kernel)."""
+    rng = np.random.default_rng(77)
+    for N, nch in ((60, 1), (24, 3)):
+        solver = jitr_b200.Solver(N)
+        a, k0 = 9.0, 0.8
+        E = list(12.0 - 0.5 * np.arange(nch))
+        mu = [930.0] * nch
+        ls = [0, 2, 5]
+        B = 9
+        free = torch.tensor(np.stack([solver.free_matrix(a, [l] * nch, E, mu) for l in ls]), device="cuda")
+        asym = torch.tensor(np.stack([np.array([orc.coulomb_hankel(l, 0.0, a) for _ in range(nch)]).T for l in ls]), device="cuda")  # (3, 4, nch)
+        r = solver.radial_grid(a, k0)
+        loc = np.zeros((B, nch, nch, N), dtype=np.complex128)
+        for i in range(nch):
+            for j in range(i, nch):
+                v = (-30.0 - 3j) * (i == j) / (1 + np.exp((r - 4.0) / 0.6)) * (1 + 0.1 * rng.standard_normal((B, 1))) + 2.0 * (i != j) * np.exp(-((r - 4) / 1.5) ** 2)
+                loc[:, i, j] = v
+                loc[:, j, i] = v
+        loc_t = torch.tensor(loc, device="cuda")
+        idx = torch.arange(3, dtype=torch.int32, device="cuda").repeat_interleave(B)
+        one = solver.solve_batch(a, E[0], k0, nch, free, asym[idx.long()].contiguous(), local_potential=loc_t.repeat(3, 1, 1, 1), free_index=idx)
+        assert int(one["status"].abs().sum()) == 0
+        for q, l in enumerate(ls):
+            per = solver.solve_batch(a, E[0], k0, nch, free[q], asym[q], local_potential=loc_t)
+            assert torch.equal(one["S"][q * B:(q + 1) * B], per["S"]) and torch.equal(one["R"][q * B:(q + 1) * B], per["R"])
