@@ -188,10 +188,17 @@ static int launch_sweep(const SweepArgs& a, cudaStream_t st) {
         case 16: return launch_sweep_mode<PARAMS, 16>(a, st);
         case 24: return launch_sweep_mode<PARAMS, 24>(a, st);
         case 32: return launch_sweep_mode<PARAMS, 32>(a, st);
+#ifndef JITR_PACKED40
         case 40: return launch_sweep_mode<PARAMS, 40>(a, st);
+#endif
         default: break;
     }
-    if ((P == 48 || P == 56 || P == 64) && a.symmetric && a.n_pairs < 0x7fffffffLL && !a.pair_list) {
+#ifdef JITR_PACKED40
+    constexpr int kPackedFrom = 40;
+#else
+    constexpr int kPackedFrom = 48;
+#endif
+    if (P >= kPackedFrom && P <= 64 && a.symmetric && a.n_pairs < 0x7fffffffLL && !a.pair_list) {
         // packed modes: lower triangle only, six systems per SM at P = 64; the pairs they defer (a system failed the
         // threshold test) are redone by the partial-pivoting modes right behind, on the same stream
         int* buf = defer_buffer(a.n_pairs, st);
@@ -201,6 +208,9 @@ static int launch_sweep(const SweepArgs& a, cudaStream_t st) {
         p.defer_list = buf + 4;
         int rc = JITR_B200_ERR_UNSUPPORTED;
         switch (P) {
+#ifdef JITR_PACKED40
+            case 40: rc = launch_sweep_mode<PARAMS, 40>(p, st); break;
+#endif
             case 48: rc = launch_sweep_mode<PARAMS, 48>(p, st); break;
             case 56: rc = launch_sweep_mode<PARAMS, 56>(p, st); break;
             case 64: rc = launch_sweep_mode<PARAMS, 64>(p, st); break;

@@ -246,18 +246,22 @@ struct WarpSolver {
 };
 
 // ---------------------------------------------------------------------------------------------
-// Packed modes, P = 48 / 56 / 64 (BASELINE config 3: N = 60): the lower triangle of  That + diag(d)  alone is
-// assembled in the warp's region (lu_packed.cuh: 38 KB instead of 67.6 KB at P = 64 -> six systems per SM instead of
-// three) and eliminated in place by the threshold-pivoted LDL^T.  That stays in global memory (28.8 KB, read-only,
-// L1/L2 resident) and is fetched one block row -- sixteen independent loads per lane -- at a time.  A system that fails
-// the threshold test defers its whole (sample, energy) pair to the partial-pivoting modes.
+// Packed modes, P = 48 / 56 / 64 (BASELINE config 3: N = 60): only the LOWER TRIANGLE of the Schur complement of the first
+// panel is ever stored (lu_packed.cuh: 29.6 KB at P = 64 instead of the 67.6 KB of the assembled bordered matrix -> seven
+// systems per SM instead of three).  The first panel is eliminated in registers straight from That (global memory, 28.8 KB,
+// read-only, L1/L2 resident), the rest in place by the threshold-pivoted packed LDL^T.  A system that fails the threshold
+// test defers its whole (sample, energy) pair to the partial-pivoting modes.
 // ---------------------------------------------------------------------------------------------
 template <int PT>
 struct PackedSweepPlan {
-    using G = PackedGeom<PT>;
+    using G = PackedGeom<PT - 8>;  // the Schur complement of the first panel is all that is stored (packed_first_panel)
     static constexpr int kShared = 2 * PT * 8;  // b, 1/x^2
     static constexpr int kFit = (kSweepMaxSmem - kShared) / (G::WARP_ELEMS * 16);
-    static constexpr int kMaxWarps = kFit > 16 ? 16 : kFit;
+    // at most JITR_PACKED_WARPS warps (12: 168 registers per thread -- the first panel keeps all B fragments in registers)
+#ifndef JITR_PACKED_WARPS
+#define JITR_PACKED_WARPS 12
+#endif
+    static constexpr int kMaxWarps = kFit > JITR_PACKED_WARPS ? JITR_PACKED_WARPS : kFit;
     static constexpr int kThreads = kMaxWarps * 32;
     static bool supports(int N) { return N > PT - 8 && N <= PT; }
     static int warps(int) { return kMaxWarps; }
@@ -265,7 +269,7 @@ struct PackedSweepPlan {
 };
 template <int PT>
 struct PackedSolver {
-    using G = PackedGeom<PT>;
+    using G = PackedGeom<PT - 8>;
     unsigned wofs;
     int N, lane;
     const double* That;
@@ -296,66 +300,17 @@ struct PackedSolver {
         extern __shared__ __align__(16) unsigned char smem_raw[];
         double2* M = reinterpret_cast<double2*>(smem_raw + wofs);
         const double* b = tail();
-        const double2 dd[2] = {d0, d1};
-        // ---- lower triangle of That + diag(d), identity padding, y = b.  One block row per step: left of the diagonal tile a
-        // lane owns column c = lane (+32) and has up to sixteen independent loads in flight; the diagonal tile uses all lanes
-        // (two block rows per step: up to thirty-two independent loads per lane in flight -- That comes from L2)
-#pragma unroll 1
-        for (int tr0 = 0; tr0 < G::NB; tr0 += 2) {
-            double t[2][2][8], td[2][2];
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                const int tr = tr0 + u, r0 = 8 * tr;
-                const int nrow = min(8, N - r0);  // warp-uniform
-#pragma unroll
-                for (int k = 0; k < 2; ++k) {  // the diagonal tile: element (r0 + i, r0 + jj), i = (lane >> 3) + 4 k, jj = lane & 7
-                    const int i = (lane >> 3) + 4 * k, jj = lane & 7;
-                    td[u][k] = (tr < G::NB && jj < i && r0 + i < N) ? __ldg(That + (r0 + i) * N + r0 + jj) : 0.0;
-                }
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int c = lane + 32 * h;
-                    if (tr < G::NB && c < r0) {
-                        const double* Tp = That + r0 * N + c;
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) t[u][h][i] = i < nrow ? __ldg(Tp + i * N) : 0.0;
-                    }
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                const int tr = tr0 + u, r0 = 8 * tr;
-                if (tr < G::NB) {
-                    double2* Mb = M + G::off(tr);
-                    const int ldt = G::ld(tr);
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const int c = lane + 32 * h;
-                        if (c < r0) {
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) Mb[i * ldt + c] = make_double2(t[u][h][i], 0.0);
-                        }
-                    }
-                    const int hrow = r0 >> 5;
-#pragma unroll
-                    for (int k = 0; k < 2; ++k) {
-                        const int i = (lane >> 3) + 4 * k, jj = lane & 7;
-                        const int r = r0 + i, c = r0 + jj;
-                        const double2 dv = shfl2(hrow ? dd[1] : dd[0], r & 31);  // the diagonal entry of row r lives in lane r & 31
-                        if (jj <= i) {
-                            double2 v = make_double2(jj == i ? 1.0 : 0.0, 0.0);  // identity padding
-                            if (r < N) v = (jj == i) ? dv : make_double2(td[u][k], 0.0);
-                            Mb[i * ldt + c] = v;
-                        }
-                    }
-                }
-            }
-        }
-        for (int r = lane; r < PT; r += 32) M[G::rhs(r)] = make_double2(b[r], 0.0);
+        const double2 one = make_double2(1.0, 0.0);
+        const double2 dd[2] = {lane < N ? d0 : one, lane + 32 < N ? d1 : one};  // identity padding beyond N
+        // first panel straight from That (no assembly pass), its Schur complement into the packed region, then in place
+        double2 corner = make_double2(0.0, 0.0);
+        int fail = 0, bad = 0;
+        packed_first_panel<PT>(M, That, b, dd, N, lane, corner, fail);
+        const double2 rest = packed_ldlt<PT - 8>(M, lane, bad);
+        corner.x += rest.x;
+        corner.y += rest.y;
         __syncwarp();
-        int bad = 0;
-        const double2 corner = packed_ldlt<PT>(M, lane, bad);
-        __syncwarp();
+        bad |= fail;
         if (bad) {
             if (lane == 0 && fallbacks) atomicAdd(fallbacks, 1ULL);
             deferred = 1;
@@ -363,6 +318,10 @@ struct PackedSolver {
         return corner;
     }
 };
+#ifdef JITR_PACKED40
+template <> struct SweepPlan<40> : PackedSweepPlan<40> {};
+template <> struct WarpSolver<40> : PackedSolver<40> {};
+#endif
 template <> struct SweepPlan<48> : PackedSweepPlan<48> {};
 template <> struct SweepPlan<56> : PackedSweepPlan<56> {};
 template <> struct SweepPlan<64> : PackedSweepPlan<64> {};
@@ -504,7 +463,11 @@ __global__ void __launch_bounds__(SweepPlan<MODE>::kThreads, 1) elastic_sweep_ke
 #ifndef JITR_PACKED_LOCKSTEP
 #define JITR_PACKED_LOCKSTEP 0
 #endif
+#ifdef JITR_PACKED40
+    constexpr bool kLock = MODE < 40 || JITR_PACKED_LOCKSTEP != 0;
+#else
     constexpr bool kLock = MODE < 48 || JITR_PACKED_LOCKSTEP != 0;
+#endif
     for (unsigned it = 0;; ++it) {
         const int b = it % LockStep::K;
         if (kLock) {

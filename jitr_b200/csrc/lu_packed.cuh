@@ -223,6 +223,111 @@ __device__ __forceinline__ double2 packed_ldlt(double2* __restrict__ M, const in
     return cacc;
 }
 
+// First panel of  That + diag(d)  straight from That (the fused sweep: the system never exists as a whole, lu_sym.cuh), for the
+// packed layout: the eight pivot columns are eliminated in registers from That's columns (global memory, L1/L2 resident), and only
+// the Schur complement of order n = PT - 8 is written -- into a PackedGeom<PT - 8> region (P = 64: 29.6 KB instead of 37.9 KB:
+// SEVEN systems per SM, and no assembly pass).  Scratch inside the region while the panel is in flight:
+//   WB  the unscaled columns of all PT rows (pivot-row source and, rows 8.., the B operands), at the START of the region: all B
+//       fragments are taken into registers before the first block row is written over it;
+//   LB  the multipliers of rows 8..PT-1, at the END: block rows are written in ascending order and reach LB only at the last
+//       two, whose own A fragments are loaded before they are stored.
+// Returns the panel's contribution to the corner; `fail` as sym_panel_eliminate.  d[s]: diagonal entries of rows lane + 32 s
+// (the caller passes 1 for the identity padding), bsh: boundary vector b (shared memory, zero padded), N: real rows.
+template <int PT>
+__device__ __forceinline__ void packed_first_panel(double2* __restrict__ W, const double* __restrict__ That, const double* __restrict__ bsh,
+                                                   const double2 (&d)[2], const int N, const int lane, double2& cacc, int& fail) {
+    using G = PackedGeom<PT - 8>;
+    constexpr int n = PT - 8, NT = n / 8, LB_LD = 9;
+    constexpr int WB_OFF = 0, LB_OFF = G::SIZE - n * LB_LD;
+    static_assert(PT > 32 && PT <= 64, "two row slots");
+    static_assert(LB_OFF >= PT * LB_LD, "scratch of the first panel must fit the region");
+    double2 p[2][9];
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+        const int i = 32 * s + lane;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const double t = (i < N && j < N && i != j) ? __ldg(That + j * N + i) : 0.0;  // That is symmetric: coalesced across the lanes
+            p[s][j] = (i == j) ? d[s] : make_double2(t, 0.0);
+        }
+        p[s][8] = make_double2(i < PT ? bsh[i] : 0.0, 0.0);
+    }
+    sym_panel_eliminate<2>(
+        p, PT, lane, cacc, fail,
+        [&](int s, int kk, double2 v) {
+            const int i = 32 * s + lane;
+            if (i > kk && i < PT) W[WB_OFF + i * LB_LD + kk] = v;
+        },
+        [&](int kk, int j) { return W[WB_OFF + j * LB_LD + kk]; });
+    double2 ykeep[2];
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+        const int i = 32 * s + lane;
+        ykeep[s] = p[s][8];
+        if (i >= 8 && i < PT) {
+            double2* dst = W + LB_OFF + (i - 8) * LB_LD;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dst[j] = p[s][j];
+        }
+    }
+    __syncwarp();
+    // ---- Schur complement  W[r][c] = That[8+r][8+c] (+ d on the diagonal) - sum_k L[r][k] w[c][k], lower tiles only
+    const int fr = lane >> 2, fk = lane & 3;
+    const int rho = (fr >> 1) + 4 * (fr & 1);
+    const int part = fk & 1, pn = fr & 1;
+    const int bflip = (part & (pn ^ 1)) ? 0x80000000 : 0;
+    const double* Wd = reinterpret_cast<const double*>(W);
+    double b[NT][2][4];
+#pragma unroll
+    for (int q = 0; q < NT; ++q)
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+                const double v = Wd[2 * (WB_OFF + (8 + 8 * q + 4 * h + (fr >> 1)) * LB_LD + s + 4 * (fk >> 1)) + (part ^ pn)];
+                b[q][h][s] = __hiloint2double(__double2hiint(v) ^ bflip, __double2loint(v));
+            }
+    __syncwarp();  // the B fragments are in registers: WB may be overwritten
+#pragma unroll
+    for (int tr = 0; tr < NT; ++tr) {
+        const int row = 8 + 8 * tr + rho;  // row of the full system
+        // the entries of That (and the diagonal) this lane's accumulators start from: issued first, they arrive during the A loads
+        double2 c[NT][2];
+        const double2 dv = shfl2(row >= 32 ? d[1] : d[0], row & 31);  // d of this lane's accumulator row (used where row == col)
+#pragma unroll
+        for (int q = 0; q <= tr; ++q)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int col = 8 + 8 * q + 4 * h + fk;
+                const double t = (row != col && row < N && col < N) ? __ldg(That + col * N + row) : 0.0;
+                c[q][h] = (row == col) ? dv : make_double2(t, 0.0);
+            }
+        double a[4];
+#pragma unroll
+        for (int s = 0; s < 4; ++s) a[s] = dneg(Wd[2 * (LB_OFF + (8 * tr + rho) * LB_LD + s + 4 * (fk >> 1)) + part]);
+        __syncwarp();  // (the last block rows overwrite LB rows, their own included)
+#pragma unroll
+        for (int s = 0; s < 4; ++s)
+#pragma unroll
+            for (int q = 0; q <= tr; ++q) {
+                dmma884(c[q][0].x, c[q][0].y, a[s], b[q][0][s]);
+                dmma884(c[q][1].x, c[q][1].y, a[s], b[q][1][s]);
+            }
+        double2* Crow = W + G::off(tr) + rho * G::ld(tr) + fk;
+#pragma unroll
+        for (int q = 0; q <= tr; ++q) {
+            Crow[8 * q] = c[q][0];
+            Crow[8 * q + 4] = c[q][1];
+        }
+    }
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+        const int i = 32 * s + lane;
+        if (i >= 8 && i < PT) W[G::rhs(i - 8)] = ykeep[s];
+    }
+    __syncwarp();
+}
+
 // z = A^-1 b from the factors packed_ldlt leaves behind (W below the diagonal, 1/d on it, y = L^-1 b in the y slots):
 // z_i = (y_i - sum_{j > i} w_ji z_j) / d_i, column oriented -- row j of the packed storage holds w_ji for all i < j, lane i
 // (+32) accumulates its own entry, z_j is broadcast as it becomes final.  z[h] = entry lane + 32 h.  (core.py:63-82)
