@@ -62,6 +62,10 @@ class ClockSampler:
     def stop(self, t0, t1):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        for _ in range(20):  # a timed region shorter than the sampling period (config 1: 0.4 ms): wait for the next samples
+            if any(t0 <= t <= t1 for (t, _l) in self.rows) or len([1 for (t, _l) in self.rows if t > t1]) >= 2:
+                break
+            time.sleep(0.05)
         self.proc.terminate()
         sm, mx, reasons, pw = [], [], set(), []
         inside = [(t, l) for (t, l) in self.rows if t0 <= t <= t1] or self.rows[-3:]

@@ -535,7 +535,7 @@ __global__ void __launch_bounds__(SweepPlan<MODE>::kThreads, 1) elastic_sweep_ke
         if ((fellback | deferred) && A.fallback_mask && lane == 0) atomicOr(A.fallback_mask + pair, 1ULL << (2 * l + jj));
         bool pair_done = false;
         if (deferred) {  // warp-uniform: the pair is abandoned here and redone by the partial-pivoting modes
-            if (lane == 0) A.defer_list[atomicAdd(A.defer_count, 1)] = (int)pair;
+            if (lane == 0 && (!A.lsplit || atomicExch(A.lsplit_seen + pair, 1) == 0)) A.defer_list[atomicAdd(A.defer_count, 1)] = (int)pair;
             pair_done = true;
         } else {
         const double2* as = A.asym + ((size_t)e * L1 + l) * 4;  // (after the solve: fewer live registers)
@@ -645,13 +645,16 @@ int launch_sweep_mode(const SweepArgs& a, cudaStream_t st) {
         return set_cuda_error("cudaFuncSetAttribute(elastic_sweep)");
     const int sms = sm_count();
     SweepArgs args = a;
-    // small batches: fewer pairs than half the resident warps -> one work item per partial wave (fast modes only: they
-    // handle a failed threshold test inside the kernel)
+    // small batches: fewer pairs than half the resident warps -> one work item per partial wave (a packed mode defers a pair
+    // at most once: lsplit_seen)
     args.lsplit = 0;
-    if (MODE > 0 && MODE <= 40 && !a.pair_list && a.lmax > 0 && 2 * a.n_pairs < (long long)sms * warps) {
-        args.lsplit_flags = defer_buffer(a.n_pairs * (a.lmax + 1), st);
+    if (MODE > 0 && !a.pair_list && a.lmax > 0 && 2 * a.n_pairs < (long long)sms * warps) {
+        args.lsplit_flags = defer_buffer(a.n_pairs * (a.lmax + 2), st);
         if (!args.lsplit_flags) return set_cuda_error("elastic sweep: l-split scratch");
         args.lsplit_flags += 4;
+        args.lsplit_seen = args.lsplit_flags + a.n_pairs * (a.lmax + 1);
+        if (cudaMemsetAsync(args.lsplit_seen, 0, (size_t)a.n_pairs * sizeof(int), st) != cudaSuccess)
+            return set_cuda_error("elastic sweep: l-split scratch");
         args.lsplit = 1;
     }
     const long long items = args.lsplit ? a.n_pairs * (a.lmax + 1) : a.n_pairs;

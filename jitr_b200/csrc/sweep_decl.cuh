@@ -21,6 +21,7 @@ struct SweepArgs {
     // kernel; the partial waves kept (and the status) are decided afterwards from lsplit_flags[pair][l] (sweep_finalize)
     int lsplit;
     int* lsplit_flags;
+    int* lsplit_seen;  // packed modes: [n_pairs], set when a pair has been appended to the deferred list (once per pair)
     const double* That;
     const double* mesh_x;
     const double* bvec;

@@ -369,12 +369,15 @@ def test_partial_pivoting_only_option_matches(golden):
     assert L.jitr_b200_set_option(99, 0) == _cabi.ERR_BAD_ARG
 
 
-def test_symmetric_path_falls_back_to_partial_pivoting():
-    """A diagonal entry that fails the threshold test (|a_kk| < max_i |a_ik| / 16) must send the system
+@pytest.mark.parametrize("N", [40, 56])
+def test_symmetric_path_falls_back_to_partial_pivoting(N):
+    """(N = 40: in-kernel partial-pivoting re-solve; N = 56: a packed mode, in the l-split work distribution of a small batch --
+    the pair is deferred once and redone by the partial-pivoting mode.)
+    A diagonal entry that fails the threshold test (|a_kk| < max_i |a_ik| / 16) must send the system
     to the partial-pivoting path: a potential tuned so that the FIRST diagonal entry a^2 A[0][0] is tiny
     against its column at one partial wave (later diagonal entries are Schur complements and cannot be
     tuned from the potential alone)."""
-    N, lmax = 40, 6
+    lmax = 6
     rx = ElasticReaction((40, 20), (1, 0), mass_target=37214.69, mass_projectile=939.5654983938299)
     kin = rx.kinematics(20.0)
     angles = np.linspace(0.2, 3.0, 31)
