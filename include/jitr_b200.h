@@ -259,7 +259,13 @@ int jitr_b200_fp64_probe(int which, int iters, int warps_dmma, double* tflops_ou
  * reads their lower triangle only (half the HBM traffic).  0 = the upper triangle is read too and compared element by element;
  * a system that is not symmetric is solved by the partial-pivoting kernel instead. */
 #define JITR_B200_OPT_ASSUME_SYMMETRIC_KERNEL 1
-#define JITR_B200_OPT_COUNT 2
+/* JITR_B200_OPT_PACKED_FIRST_PANEL (default 0): 1 = single-channel systems with 33..64 basis functions and no coefficients eliminate
+ * their first eight columns in registers (panel columns of V by bulk-async copies) and accumulate the Schur complement straight from
+ * global memory, keeping only its lower triangle in shared memory (seven systems per SM at N = 60 instead of six).  Measured on B200 it
+ * is SLOWER than staging the whole lower triangle by bulk-async copies first (1.33e7 vs 1.70e7 solves/s on BASELINE config 4: the
+ * accumulator loads expose the HBM latency once per block row), so it is off by default and kept as a measured alternative. */
+#define JITR_B200_OPT_PACKED_FIRST_PANEL 2
+#define JITR_B200_OPT_COUNT 3
 int jitr_b200_set_option(int key, int value);
 /* systems the symmetric path handed to the partial-pivoting path since load (-1: no device) */
 long long jitr_b200_sym_fallback_count(void);

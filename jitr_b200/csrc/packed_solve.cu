@@ -27,12 +27,16 @@ namespace {
 
 constexpr int kPackedMaxSmem = 232448;
 
-template <int P>
+// FP ("first panel" mode, P > 32, no coefficients): the first eight columns are eliminated in registers and only the Schur
+// complement of order P - 8 is stored -- seven systems per SM at P = 64 instead of six, and no staging pass over the region
+template <int P, bool FP>
 struct PackedPlan {
-    using G = PackedGeom<P>;
+    using G = PackedGeom<FP ? P - 8 : P>;
     static constexpr int kTail = 2 * P * 8 + 16 * 8;  // b, wsqrt (doubles) + up to 16 mbarriers
     static constexpr int kFit = (kPackedMaxSmem - kTail) / (G::WARP_ELEMS * 16);
-    static constexpr int kWarps = kFit > 16 ? 16 : kFit;
+    // first-panel mode keeps all B fragments of the panel in registers: at most eight warps, 255 registers per thread
+    static constexpr int kCap = FP ? 8 : 16;
+    static constexpr int kWarps = kFit > kCap ? kCap : kFit;
     static constexpr int kThreads = kWarps * 32;
     static constexpr int kSmem = kWarps * G::WARP_ELEMS * 16 + kTail;
 };
@@ -149,12 +153,210 @@ __device__ __forceinline__ unsigned long long stage_system(double2* __restrict__
     return diff;
 }
 
-template <int P>
-__global__ void __launch_bounds__(PackedPlan<P>::kThreads, 1)
+// First-panel mode: A = F + (scaled V | interaction) (+ V_loc / E0) never exists as a whole.  The eight pivot columns of V arrive by
+// bulk-async copies (one 128-byte row segment per row, completion on the warp's mbarrier) into the scratch the panel is about to
+// use, are combined with F's columns in registers and eliminated there; the Schur complement is accumulated on DMMA straight from
+// global memory -- every accumulator starts from its own entries of F and V (four consecutive lanes read 64 contiguous bytes of a row)
+// -- and only its lower triangle of order P - 8 is written, into the packed region.  With CHECK every entry of V that is read is
+// compared bit for bit with its transpose.  Returns the OR of the XORs (0: symmetric); cacc / fail as packed_first_panel.
+template <int PT, bool HAS_V, bool INTER, bool CHECK>
+__device__ __forceinline__ unsigned long long first_panel_global(double2* __restrict__ W, const double2* __restrict__ F,
+                                                                 const double2* __restrict__ Vsrc, const double2* __restrict__ Vloc,
+                                                                 const double* __restrict__ ws, const double* __restrict__ bs,
+                                                                 const double nl_scale, const double E0, const int N, const int lane,
+                                                                 const unsigned bar, unsigned& parity, double2& cacc, int& fail) {
+    using G = PackedGeom<PT - 8>;
+    constexpr int n = PT - 8, NT = n / 8, LB_LD = 9;
+    constexpr int WB_OFF = 0, LB_OFF = G::SIZE - n * LB_LD;
+    static_assert(PT > 32 && PT <= 64 && LB_OFF >= PT * LB_LD, "first-panel mode: two row slots, scratch inside the region");
+    const double2 zero2 = make_double2(0.0, 0.0);
+    unsigned long long diff = 0ULL;
+    auto xorw = [](const double2 a, const double2 b) {
+        return (unsigned long long)(__double_as_longlong(a.x) ^ __double_as_longlong(b.x)) |
+               (unsigned long long)(__double_as_longlong(a.y) ^ __double_as_longlong(b.y));
+    };
+    if (HAS_V) {
+        // ---- the panel columns of V: row i, columns 0..7 = 128 contiguous bytes -> W[i * 9 .. i * 9 + 7]
+        __syncwarp();
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        if (lane == 0) {
+            const unsigned bytes = (unsigned)N * 8u * 16u;
+            asm volatile("{ .reg .b64 st; mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1; }" ::"r"(bar), "r"(bytes) : "memory");
+        }
+        __syncwarp();
+        for (int r = lane; r < N; r += 32) {
+            const unsigned dst = smem_u32(W + WB_OFF + r * LB_LD);
+            const unsigned long long src = (unsigned long long)(Vsrc + (size_t)r * N);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                         "r"(128u), "r"(bar)
+                         : "memory");
+        }
+    }
+    double2 p[2][9], d[2];
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+        const int i = 32 * s + lane;
+        const bool in = i < N;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) p[s][j] = (in && j < N) ? F[(size_t)i * N + j] : make_double2(i == j ? 1.0 : 0.0, 0.0);
+        p[s][8] = make_double2(i < PT ? bs[i] : 0.0, 0.0);
+        d[s] = make_double2(1.0, 0.0);
+        if (in) {
+            d[s] = F[(size_t)i * N + i];
+            if (Vloc) {
+                const double2 w = Vloc[i];
+                d[s].x += w.x / E0; d[s].y += w.y / E0;
+            }
+        }
+    }
+    if (HAS_V) {
+        double2 vt[2][8];
+        if (CHECK) {
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                const int i = 32 * s + lane;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) vt[s][j] = (i < N && j < N) ? Vsrc[(size_t)j * N + i] : zero2;  // V[j][i]: coalesced across the lanes
+            }
+        }
+        mbar_wait(bar, parity);
+        parity ^= 1u;
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            const int i = 32 * s + lane;
+            if (i < N) {
+                const double wi = INTER ? 1.0 : ws[i] * nl_scale;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (j < N) {
+                        const double2 v = W[WB_OFF + i * LB_LD + j];
+                        if (CHECK) diff |= xorw(v, vt[s][j]);
+                        const double sc = INTER ? 1.0 : wi * ws[j];
+                        p[s][j].x = fma(v.x, sc, p[s][j].x);
+                        p[s][j].y = fma(v.y, sc, p[s][j].y);
+                    }
+                }
+            }
+        }
+        // the diagonal entries of V (rows >= 8: their column is not in the panel)
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            const int i = 32 * s + lane;
+            if (i < N) {
+                const double2 v = i < 8 ? zero2 : Vsrc[(size_t)i * N + i];
+                const double sc = INTER ? 1.0 : ws[i] * nl_scale * ws[i];
+                if (i >= 8) {
+                    d[s].x = fma(v.x, sc, d[s].x);
+                    d[s].y = fma(v.y, sc, d[s].y);
+                }
+            }
+        }
+        __syncwarp();
+    }
+    // local potential on the diagonal of the panel block (rows < 8: their diagonal entry is p[0][lane])
+    if (Vloc && lane < 8 && lane < N) {
+        const double2 w = Vloc[lane];
+        p[0][lane].x += w.x / E0;
+        p[0][lane].y += w.y / E0;
+    }
+    sym_panel_eliminate<2>(
+        p, PT, lane, cacc, fail,
+        [&](int s, int kk, double2 v) {
+            const int i = 32 * s + lane;
+            if (i > kk && i < PT) W[WB_OFF + i * LB_LD + kk] = v;
+        },
+        [&](int kk, int j) { return W[WB_OFF + j * LB_LD + kk]; });
+    double2 ykeep[2];
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+        const int i = 32 * s + lane;
+        ykeep[s] = p[s][8];
+        if (i >= 8 && i < PT) {
+            double2* dst = W + LB_OFF + (i - 8) * LB_LD;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dst[j] = p[s][j];
+        }
+    }
+    __syncwarp();
+    // ---- Schur complement, lower tiles only; accumulators initialised from F and V in global memory
+    const int fr = lane >> 2, fk = lane & 3;
+    const int rho = (fr >> 1) + 4 * (fr & 1);
+    const int part = fk & 1, pn = fr & 1;
+    const int bflip = (part & (pn ^ 1)) ? 0x80000000 : 0;
+    const double* Wd = reinterpret_cast<const double*>(W);
+    double b[NT][2][4];
+#pragma unroll
+    for (int q = 0; q < NT; ++q)
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+                const double v = Wd[2 * (WB_OFF + (8 + 8 * q + 4 * h + (fr >> 1)) * LB_LD + s + 4 * (fk >> 1)) + (part ^ pn)];
+                b[q][h][s] = __hiloint2double(__double2hiint(v) ^ bflip, __double2loint(v));
+            }
+    __syncwarp();  // the B fragments are in registers: WB may be overwritten
+#pragma unroll
+    for (int tr = 0; tr < NT; ++tr) {
+        const int row = 8 + 8 * tr + rho;
+        const bool rin = row < N;
+        const double wr = (HAS_V && !INTER && rin) ? ws[row] * nl_scale : 1.0;
+        const double2 dv = shfl2(row >= 32 ? d[1] : d[0], row & 31);  // the assembled diagonal entry of this lane's accumulator row
+        double2 c[NT][2];
+#pragma unroll
+        for (int q = 0; q <= tr; ++q)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int col = 8 + 8 * q + 4 * h + fk;
+                double2 v = make_double2(row == col ? 1.0 : 0.0, 0.0);  // identity padding
+                if (rin && col < N) {
+                    if (row == col) {
+                        v = dv;
+                    } else {
+                        v = F[(size_t)row * N + col];
+                        if (HAS_V) {
+                            const double2 w = Vsrc[(size_t)row * N + col];
+                            if (CHECK) diff |= xorw(w, Vsrc[(size_t)col * N + row]);
+                            const double sc = INTER ? 1.0 : wr * ws[col];
+                            v.x = fma(w.x, sc, v.x);
+                            v.y = fma(w.y, sc, v.y);
+                        }
+                    }
+                }
+                c[q][h] = v;
+            }
+        double a[4];
+#pragma unroll
+        for (int s = 0; s < 4; ++s) a[s] = dneg(Wd[2 * (LB_OFF + (8 * tr + rho) * LB_LD + s + 4 * (fk >> 1)) + part]);
+        __syncwarp();  // (the last block rows overwrite LB rows, their own included)
+#pragma unroll
+        for (int s = 0; s < 4; ++s)
+#pragma unroll
+            for (int q = 0; q <= tr; ++q) {
+                dmma884(c[q][0].x, c[q][0].y, a[s], b[q][0][s]);
+                dmma884(c[q][1].x, c[q][1].y, a[s], b[q][1][s]);
+            }
+        double2* Crow = W + G::off(tr) + rho * G::ld(tr) + fk;
+#pragma unroll
+        for (int q = 0; q <= tr; ++q) {
+            Crow[8 * q] = c[q][0];
+            Crow[8 * q + 4] = c[q][1];
+        }
+    }
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+        const int i = 32 * s + lane;
+        if (i >= 8 && i < PT) W[G::rhs(i - 8)] = ykeep[s];
+    }
+    __syncwarp();
+    return diff;
+}
+
+template <int P, bool FP>
+__global__ void __launch_bounds__(PackedPlan<P, FP>::kThreads, 1)
 packed_solve_kernel(const GenArgs A, const int* __restrict__ symflag, const int check_symmetry,
                     unsigned long long* __restrict__ work_counter, int* __restrict__ defer_list, int* __restrict__ defer_count) {
-    using G = PackedGeom<P>;
-    using Plan = PackedPlan<P>;
+    using Plan = PackedPlan<P, FP>;
+    using G = typename Plan::G;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int N = A.N;
     const int warp = __shfl_sync(kFull, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
@@ -189,6 +391,34 @@ packed_solve_kernel(const GenArgs A, const int* __restrict__ symflag, const int 
         const double a = sy[0], E0 = sy[1], k0 = sy[2];
         const double nl_scale = A.interaction ? 1.0 : (a / k0) / k0 / E0;  // kernel.py:202 (x radius), rmatrix.py:175-178 (/k0, /E0)
         const double2* Vsrc = Vsrc_base ? Vsrc_base + (size_t)sysi * N * N : nullptr;
+        double2 corner = zero2;
+        if constexpr (FP) {
+            if (!defer) {
+                const double2* F = A.free_matrix + (A.free_index ? (size_t)A.free_index[sysi] * N * N : 0);
+                const double2* Vloc = (!A.interaction && A.local) ? A.local + (size_t)sysi * N : nullptr;
+                unsigned long long diff = 0ULL;
+                int fail = 0, bad = 0;
+                if (!Vsrc)
+                    diff = first_panel_global<P, false, false, false>(M, F, nullptr, Vloc, ws, bs, nl_scale, E0, N, lane, bar, parity, corner, fail);
+                else if (A.interaction)
+                    diff = check_symmetry
+                               ? first_panel_global<P, true, true, true>(M, F, Vsrc, Vloc, ws, bs, nl_scale, E0, N, lane, bar, parity, corner, fail)
+                               : first_panel_global<P, true, true, false>(M, F, Vsrc, Vloc, ws, bs, nl_scale, E0, N, lane, bar, parity, corner, fail);
+                else
+                    diff = check_symmetry
+                               ? first_panel_global<P, true, false, true>(M, F, Vsrc, Vloc, ws, bs, nl_scale, E0, N, lane, bar, parity, corner, fail)
+                               : first_panel_global<P, true, false, false>(M, F, Vsrc, Vloc, ws, bs, nl_scale, E0, N, lane, bar, parity, corner, fail);
+                defer = __any_sync(kFull, diff != 0ULL);
+                if (!defer) {
+                    const double2 rest = packed_ldlt<P - 8>(M, lane, bad);
+                    corner.x += rest.x;
+                    corner.y += rest.y;
+                    bad |= fail;
+                    defer = bad != 0;
+                    if (defer && lane == 0 && A.fallbacks) atomicAdd(A.fallbacks, 1ULL);
+                }
+            }
+        } else {
         if (!defer && Vsrc) {
             // ---- stage the lower triangle: one bulk-async copy per row, all of them in flight at once
             __syncwarp();
@@ -225,12 +455,12 @@ packed_solve_kernel(const GenArgs A, const int* __restrict__ symflag, const int 
             defer = __any_sync(kFull, asym);
             __syncwarp();
         }
-        double2 corner = zero2;
         if (!defer) {
             int bad = 0;
             corner = packed_ldlt<P>(M, lane, bad);
             defer = bad != 0;
             if (defer && lane == 0 && A.fallbacks) atomicAdd(A.fallbacks, 1ULL);
+        }
         }
         if (defer) {
             if (lane == 0) defer_list[atomicAdd(defer_count, 1)] = (int)sysi;
@@ -272,10 +502,10 @@ packed_solve_kernel(const GenArgs A, const int* __restrict__ symflag, const int 
     }
 }
 
-template <int P>
-int launch_packed(const GenArgs& a, const int* symflag, int check_symmetry, int* defer_list, int* defer_count, cudaStream_t st) {
-    using Plan = PackedPlan<P>;
-    auto kern = packed_solve_kernel<P>;
+template <int P, bool FP>
+int launch_packed_fp(const GenArgs& a, const int* symflag, int check_symmetry, int* defer_list, int* defer_count, cudaStream_t st) {
+    using Plan = PackedPlan<P, FP>;
+    auto kern = packed_solve_kernel<P, FP>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Plan::kSmem) != cudaSuccess)
         return set_cuda_error("cudaFuncSetAttribute(packed_solve)");
     long long blocks = (a.batch + Plan::kWarps - 1) / Plan::kWarps;
@@ -286,6 +516,16 @@ int launch_packed(const GenArgs& a, const int* symflag, int check_symmetry, int*
     count_launch();
     if (cudaGetLastError() != cudaSuccess) return set_cuda_error("packed_solve launch");
     return JITR_B200_OK;
+}
+
+// first-panel mode whenever it exists (P > 32) and no coefficients are wanted (their back substitution needs all columns)
+template <int P>
+int launch_packed(const GenArgs& a, const int* symflag, int check_symmetry, int* defer_list, int* defer_count, cudaStream_t st) {
+    if constexpr (P > 32) {
+        if (!a.coeffs && option(JITR_B200_OPT_PACKED_FIRST_PANEL))
+            return launch_packed_fp<P, true>(a, symflag, check_symmetry, defer_list, defer_count, st);
+    }
+    return launch_packed_fp<P, false>(a, symflag, check_symmetry, defer_list, defer_count, st);
 }
 
 }  // namespace
