@@ -265,7 +265,10 @@ int jitr_b200_fp64_probe(int which, int iters, int warps_dmma, double* tflops_ou
  * is SLOWER than staging the whole lower triangle by bulk-async copies first (1.33e7 vs 1.70e7 solves/s on BASELINE config 4: the
  * accumulator loads expose the HBM latency once per block row), so it is off by default and kept as a measured alternative. */
 #define JITR_B200_OPT_PACKED_FIRST_PANEL 2
-#define JITR_B200_OPT_COUNT 3
+/* JITR_B200_OPT_OBSERVABLES_DMMA (default 1): the Legendre sums of the elastic observables as a GEMM on the FP64 tensor path (four
+ * samples per DMMA row block); 0 = the round-1 kernel (one warp per sample, scalar FMAs), which also serves lmax > 63. */
+#define JITR_B200_OPT_OBSERVABLES_DMMA 3
+#define JITR_B200_OPT_COUNT 4
 int jitr_b200_set_option(int key, int value);
 /* systems the symmetric path handed to the partial-pivoting path since load (-1: no device) */
 long long jitr_b200_sym_fallback_count(void);

@@ -17,6 +17,7 @@ STATUS_OK, STATUS_NONFINITE, STATUS_SINGULAR = 0, 1, 2
 OPT_SYMMETRIC = 0
 OPT_ASSUME_SYMMETRIC_KERNEL = 1
 OPT_PACKED_FIRST_PANEL = 2
+OPT_OBSERVABLES_DMMA = 3
 MODEL_SHAPE, MODEL_KDUQ, MODEL_CHUQ, MODEL_LOCAL, MODEL_WLH, MODEL_SHAPE_PAIR = 0, 1, 2, 3, 4, 5
 MODEL_NPARAMS = {MODEL_SHAPE: 17, MODEL_KDUQ: 40, MODEL_CHUQ: 22, MODEL_LOCAL: 15, MODEL_WLH: 46, MODEL_SHAPE_PAIR: 18}
 # per-energy table layout (include/jitr_b200.h)

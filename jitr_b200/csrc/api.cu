@@ -42,7 +42,7 @@ int sm_count() {
     return v;
 }
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
-static std::atomic<int> g_options[JITR_B200_OPT_COUNT] = {{1}, {0}, {0}};
+static std::atomic<int> g_options[JITR_B200_OPT_COUNT] = {{1}, {0}, {0}, {1}};
 int option(int key) { return (key >= 0 && key < JITR_B200_OPT_COUNT) ? g_options[key].load() : 0; }
 unsigned long long* fallback_counter() {
     static unsigned long long* ctr[kMaxDevices] = {nullptr};

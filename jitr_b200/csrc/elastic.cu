@@ -155,6 +155,171 @@ __global__ void __launch_bounds__(kObsWarps * 32) elastic_observables_kernel(con
 
 
 // ---------------------------------------------------------------------------------------------
+// The same observables as a GEMM on the FP64 tensor path (round 2).  a(theta) = f_c + sum_l P_l(theta) ca_l and
+// b(theta) = sum_l P1_l(theta) cb_l are two real GEMMs per group of FOUR samples: rows = (sample, re | im) of the complex
+// coefficients, K = l, N = theta -- DMMA m8n8k4 with the Legendre tables as the B operand from shared memory (row stride = 4 mod 16:
+// the fragment loads are bank-conflict free) and the coefficient rows as the A operand (staged per warp, kept in registers across the
+// angle tiles).  A table entry is fetched once per four samples instead of once per sample, and the k loop stops at the largest
+// number of partial waves kept in the group.  Epilogue: the (re, im) rows of a sample sit four lanes apart -> one exchange, then
+// every lane writes one (sample, angle).  Sums run in the DMMA's order: same terms, rounding-level differences only.
+// ---------------------------------------------------------------------------------------------
+constexpr int kObsGroup = 4;  // samples per DMMA row block (8 rows = 4 samples x (re, im))
+constexpr int kObsDmmaWarps = 16;  // one CTA per SM (the tables take 92 KB): sixteen warps hide the fragment-load and DMMA latencies
+
+template <bool MISFIT>
+__global__ void __launch_bounds__(kObsDmmaWarps * 32) elastic_observables_dmma_kernel(const ObsArgs A, const int Lp, const int ts,
+                                                                                         const int chunks_per_energy) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int L1 = A.lmax + 1, NA = A.n_angles;
+    double* Ps = reinterpret_cast<double*>(smem_raw);   // [Lp][ts], rows >= L1 and columns >= NA zero
+    double* P1s = Ps + (size_t)Lp * ts;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
+    // per warp: coefficient rows [2 GEMMs][8 rows][Lp + 1]
+    const int cs = Lp + 1;
+    double* coef = P1s + (size_t)Lp * ts + (size_t)warp * 2 * 8 * cs;
+    const int fr = lane >> 2, fk = lane & 3;       // accumulator row (sample fr / 2, part fr & 1), column pair 2 fk, 2 fk + 1
+    const int my_s = fr >> 1, my_part = fr & 1;
+    // persistent CTAs over the (energy, sample chunk) items, energy-major and contiguous per CTA: a CTA reloads its tables only
+    // when its next item belongs to another energy (at most once or twice), and the grid is exactly one CTA per SM
+    const long long n_items = (long long)A.n_energies * chunks_per_energy;
+    const long long per_cta = (n_items + gridDim.x - 1) / gridDim.x;
+    long long item = (long long)blockIdx.x * per_cta;
+    const long long item_end = item + per_cta < n_items ? item + per_cta : n_items;
+    int e_loaded = -1;
+    for (; item < item_end; ++item) {
+    const int e = (int)(item / chunks_per_energy);
+    if (e != e_loaded) {
+        __syncthreads();
+        const double* Pg = A.P + (size_t)e * L1 * NA;
+        const double* P1g = A.P1 + (size_t)e * L1 * NA;
+        for (int i = threadIdx.x; i < Lp * ts; i += blockDim.x) {
+            const int l = i / ts, t = i - l * ts;
+            const bool in = l < L1 && t < NA;
+            Ps[i] = in ? Pg[l * NA + t] : 0.0;
+            P1s[i] = in ? P1g[l * NA + t] : 0.0;
+        }
+        e_loaded = e;
+        __syncthreads();
+    }
+    const double k = A.kvec[e];
+    const long long s_begin = (item - (long long)e * chunks_per_energy) * A.chunk;
+    long long s_end = s_begin + A.chunk;
+    if (s_end > A.n_samples) s_end = A.n_samples;
+    for (long long s0 = s_begin + (long long)warp * kObsGroup; s0 < s_end; s0 += (long long)kObsDmmaWarps * kObsGroup) {
+        // ---- coefficients of the four samples: lane = l (two rounds cover Lp <= 64)
+        int nlmax = 0;
+#pragma unroll
+        for (int g = 0; g < kObsGroup; ++g) {
+            const long long smp = s0 + g;
+            const bool live = smp < s_end;
+            const long long pair = (live ? smp : s_begin) * A.n_energies + e;
+            const int nl = live ? A.nl[pair] : 0;
+            nlmax = max(nlmax, nl);
+            const double2* Sp = A.S + (size_t)pair * 2 * L1;
+            const double2* Sm = Sp + L1;
+            double rx = 0.0, tt = 0.0;
+            for (int l = lane; l < Lp; l += 32) {
+                double2 wa = make_double2(0.0, 0.0), wb = wa;
+                if (l < nl) {
+                    const double2 sp = Sp[l], sm = Sm[l], ph = A.phase[(size_t)e * L1 + l];
+                    // (l+1)(S+ - 1) + l (S- - 1) ;  S+ - S-     (xs/elastic.py:357-362)
+                    wa = cmul(ph, make_double2((l + 1) * (sp.x - 1.0) + l * (sm.x - 1.0), (l + 1) * sp.y + l * sm.y));
+                    wb = cmul(ph, make_double2(sp.x - sm.x, sp.y - sm.y));
+                    rx += (l + 1) * (1.0 - (sp.x * sp.x + sp.y * sp.y)) + l * (1.0 - (sm.x * sm.x + sm.y * sm.y));
+                    tt += (l + 1) * (1.0 - sp.x) + l * (1.0 - sm.x);
+                }
+                coef[(2 * g) * cs + l] = wa.x;
+                coef[(2 * g + 1) * cs + l] = wa.y;
+                coef[(8 + 2 * g) * cs + l] = wb.x;
+                coef[(8 + 2 * g + 1) * cs + l] = wb.y;
+            }
+            for (int o = 16; o > 0; o >>= 1) {
+                rx += __shfl_down_sync(0xffffffffu, rx, o);
+                tt += __shfl_down_sync(0xffffffffu, tt, o);
+            }
+            if (lane == 0 && live) {
+                A.tot_rxn[2 * pair] = tt * (10.0 * 2.0 * M_PI / (k * k));
+                A.tot_rxn[2 * pair + 1] = rx * (10.0 * M_PI / (k * k));
+            }
+        }
+        __syncwarp();
+        const int ksteps = (nlmax + 3) >> 2;  // warp-uniform
+        // A fragments (row fr, k = fk) of both GEMMs for every k step, in registers across the angle tiles
+        double aa[16], ab[16];
+#pragma unroll
+        for (int ks = 0; ks < 16; ++ks) {
+            aa[ks] = ks < ksteps ? coef[fr * cs + 4 * ks + fk] : 0.0;
+            ab[ks] = ks < ksteps ? coef[(8 + fr) * cs + 4 * ks + fk] : 0.0;
+        }
+        const long long my_smp = s0 + my_s;
+        const bool my_live = my_smp < s_end;
+        const long long my_pair = (my_live ? my_smp : s_begin) * A.n_energies + e;
+        double mis = 0.0;
+        // four angle tiles at a time: eight independent accumulator chains per lane hide the DMMA latency
+        constexpr int TU = 4;
+        for (int tb = 0; tb < NA; tb += 8 * TU) {
+            double ca0[TU], ca1[TU], cb0[TU], cb1[TU];
+#pragma unroll
+            for (int u = 0; u < TU; ++u) {
+                const int tc = tb + 8 * u + 2 * fk;  // this lane's accumulator columns tc, tc + 1 of tile u
+                // a starts from the Coulomb amplitude (its re / im part on the re / im rows), b from zero
+                const double2 f0 = A.f_c[(size_t)e * NA + (tc < NA ? tc : NA - 1)], f1 = A.f_c[(size_t)e * NA + (tc + 1 < NA ? tc + 1 : NA - 1)];
+                ca0[u] = my_part ? f0.y : f0.x;
+                ca1[u] = my_part ? f1.y : f1.x;
+                cb0[u] = cb1[u] = 0.0;
+            }
+            const double* Pb = Ps + fk * ts + tb + fr;    // B fragment: row k = fk, column n = fr
+            const double* P1b = P1s + fk * ts + tb + fr;
+#pragma unroll
+            for (int ks = 0; ks < 16; ++ks) {
+                if (ks < ksteps) {
+#pragma unroll
+                    for (int u = 0; u < TU; ++u) {
+                        if (tb + 8 * u < NA) {  // warp-uniform
+                            dmma884(ca0[u], ca1[u], aa[ks], Pb[4 * ks * ts + 8 * u]);
+                            dmma884(cb0[u], cb1[u], ab[ks], P1b[4 * ks * ts + 8 * u]);
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < TU; ++u) {
+                if (tb + 8 * u >= NA) break;
+                const int tc = tb + 8 * u + 2 * fk;
+                // the other part (re <-> im) of the same sample and angles lives four lanes away
+                const double oa0 = __shfl_xor_sync(0xffffffffu, ca0[u], 4), oa1 = __shfl_xor_sync(0xffffffffu, ca1[u], 4);
+                const double ob0 = __shfl_xor_sync(0xffffffffu, cb0[u], 4), ob1 = __shfl_xor_sync(0xffffffffu, cb1[u], 4);
+                // the re lane writes angle tc, the im lane angle tc + 1
+                const double are = my_part ? oa1 : ca0[u], aim = my_part ? ca1[u] : oa0;
+                const double bre = my_part ? ob1 : cb0[u], bim = my_part ? cb1[u] : ob0;
+                const int t = tc + my_part;
+                if (my_live && t < NA) {
+                    const double d0 = are * are + aim * aim + bre * bre + bim * bim;
+                    const double den = fmax(d0, 1e-30);
+                    const double re = are * bre + aim * bim, im = are * bim - aim * bre;  // conj(a) b
+                    const size_t o = (size_t)my_pair * NA + t;
+                    if (!MISFIT || A.dsdo) A.dsdo[o] = d0 * 10.0;
+                    if (A.Ay) A.Ay[o] = 2.0 * im / den;
+                    if (A.Q) A.Q[o] = 2.0 * re / den;
+                    if (MISFIT) {
+                        const size_t d = (size_t)e * NA + t;
+                        const double v = d0 * 10.0 * (A.data_scale ? A.data_scale[d] : 1.0) - A.data_y[d];
+                        mis = fma(A.data_w[d] * v, v, mis);
+                    }
+                }
+            }
+        }
+        if (MISFIT) {
+            // the eight lanes 8 s .. 8 s + 7 hold the terms of sample s
+            for (int o = 4; o > 0; o >>= 1) mis += __shfl_xor_sync(0xffffffffu, mis, o);
+            if ((lane & 7) == 0 && my_live) A.misfit[my_pair] = mis;
+        }
+        __syncwarp();  // the coefficient rows are consumed before the next group overwrites them
+    }
+    }  // items
+}
+
+// ---------------------------------------------------------------------------------------------
 // stand-alone evaluation of the built-in potential forms on the mesh (same device code as the
 // fused sweep): SingleChannelOpticalModel.evaluate, omp.py:26-43 / kduq.py:541-559
 // ---------------------------------------------------------------------------------------------
@@ -284,6 +449,35 @@ extern "C" int jitr_b200_elastic_sweep_tensors(int nbasis, int lmax, long long n
 
 static int launch_observables(ObsArgs a, const char* what, cudaStream_t st) {
     const int L1 = a.lmax + 1;
+    // GEMM formulation on DMMA when the zero-padded tables fit shared memory (lmax <= 63)
+    {
+        const int Lp = (L1 + 3) & ~3;
+        int ts = (a.n_angles + 7) & ~7;
+        while ((ts & 15) != 4) ++ts;  // row stride = 4 mod 16: conflict-free fragment loads
+        const size_t smem = (size_t)2 * Lp * ts * 8 + (size_t)kObsDmmaWarps * 2 * 8 * (Lp + 1) * 8;
+        if (Lp <= 64 && smem <= 232448 && option(JITR_B200_OPT_OBSERVABLES_DMMA)) {
+            auto kern = a.misfit ? elastic_observables_dmma_kernel<true> : elastic_observables_dmma_kernel<false>;
+            if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+                return set_cuda_error("cudaFuncSetAttribute(observables)");
+            // items = (energy, chunk of samples); about sixteen items per CTA so that the contiguous split over the SMs is even
+            const int sms = sm_count();
+            const long long per = kObsDmmaWarps * kObsGroup;  // samples one pass of the CTA covers
+            long long chunks = (16LL * sms + a.n_energies - 1) / a.n_energies;
+            const long long max_chunks = (a.n_samples + per - 1) / per;
+            if (chunks > max_chunks) chunks = max_chunks;
+            if (chunks < 1) chunks = 1;
+            long long chunk = (a.n_samples + chunks - 1) / chunks;
+            chunk = (chunk + per - 1) / per * per;
+            chunks = (a.n_samples + chunk - 1) / chunk;
+            a.chunk = (int)(chunk > (1 << 30) ? (1 << 30) : chunk);
+            long long blocks = (long long)a.n_energies * chunks;
+            if (blocks > sms) blocks = sms;
+            kern<<<(unsigned)blocks, kObsDmmaWarps * 32, smem, st>>>(a, Lp, ts, (int)chunks);
+            count_launch();
+            if (cudaGetLastError() != cudaSuccess) return set_cuda_error(what);
+            return JITR_B200_OK;
+        }
+    }
     size_t smem = (size_t)2 * L1 * a.n_angles * 8 + (size_t)kObsWarps * 2 * L1 * 16;
     a.tables_in_smem = 1;
     if (smem > 232448) {  // large lmax (the Frescox regression cases reach 100): tables from global memory / L2
