@@ -39,6 +39,8 @@ extern "C" {
 #define JITR_B200_MODEL_CHUQ 2   /* 22 global Chapel-Hill numbers */
 #define JITR_B200_MODEL_LOCAL 3  /* 15 LocalOpticalPotential numbers */
 #define JITR_B200_MODEL_WLH 4    /* 46 global Whitehead-Lim-Holt numbers (optical_potentials/wlh.py) */
+#define JITR_B200_MODEL_DOM 6     /* 19 global parameters of the local dispersive optical model (optical_potentials/dom.py), mapped on the
+                                    device incl. the analytic surface-dispersion integral; needs JITR_B200_ET_EF in the energy rows */
 #define JITR_B200_MODEL_SHAPE_PAIR 5 /* 18 numbers (17 canonical + Vw, the real depth at the imaginary-volume geometry) PER
                                         (sample, energy): params is [n_samples][n_energies][n_params]; for models whose
                                         energy-dependent parameter map is evaluated on the host (optical_potentials/dom.py) */
@@ -58,6 +60,7 @@ extern "C" {
 #define JITR_B200_ET_AM13 11    /* parameter maps see bit-identical powers (kduq.py:455-507)       */
 #define JITR_B200_ET_AM23 12
 #define JITR_B200_ET_AM53 13
+#define JITR_B200_ET_EF 14      /* effective Fermi energy of the (projectile, target) pair (MeV), DOM only (reactions/reaction.py:528-538) */
 #define JITR_B200_ET_STRIDE 16
 
 const char* jitr_b200_last_error(void);

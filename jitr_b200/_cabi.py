@@ -18,11 +18,12 @@ OPT_SYMMETRIC = 0
 OPT_ASSUME_SYMMETRIC_KERNEL = 1
 OPT_PACKED_FIRST_PANEL = 2
 OPT_OBSERVABLES_DMMA = 3
-MODEL_SHAPE, MODEL_KDUQ, MODEL_CHUQ, MODEL_LOCAL, MODEL_WLH, MODEL_SHAPE_PAIR = 0, 1, 2, 3, 4, 5
-MODEL_NPARAMS = {MODEL_SHAPE: 17, MODEL_KDUQ: 40, MODEL_CHUQ: 22, MODEL_LOCAL: 15, MODEL_WLH: 46, MODEL_SHAPE_PAIR: 18}
+MODEL_SHAPE, MODEL_KDUQ, MODEL_CHUQ, MODEL_LOCAL, MODEL_WLH, MODEL_SHAPE_PAIR, MODEL_DOM = 0, 1, 2, 3, 4, 5, 6
+MODEL_NPARAMS = {MODEL_SHAPE: 17, MODEL_KDUQ: 40, MODEL_CHUQ: 22, MODEL_LOCAL: 15, MODEL_WLH: 46, MODEL_SHAPE_PAIR: 18, MODEL_DOM: 19}
 # per-energy table layout (include/jitr_b200.h)
 ET_A, ET_ECM, ET_K, ET_ELAB, ET_RCH, ET_AT, ET_ZT, ET_ZP, ET_AP, ET_RSCALE = range(10)
 ET_A13, ET_AM13, ET_AM23, ET_AM53 = 10, 11, 12, 13
+ET_EF = 14
 ET_STRIDE = 16
 
 _p = C.c_void_p

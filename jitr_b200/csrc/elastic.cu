@@ -404,8 +404,8 @@ extern "C" int jitr_b200_elastic_sweep_params(int nbasis, int lmax, int model, l
     if (lmax < 0 || n_samples < 0 || n_energies < 1 || !That || !mesh_x || !bvec || !etab || !asym || !params ||
         !S_out || !nl_out || !status)
         return set_error(JITR_B200_ERR_BAD_ARG, "elastic_sweep_params: null pointer or bad size");
-    const int need = model == JITR_B200_MODEL_KDUQ ? 40 : model == JITR_B200_MODEL_CHUQ ? 22 : model == JITR_B200_MODEL_LOCAL ? 15 : model == JITR_B200_MODEL_WLH ? 46 : model == JITR_B200_MODEL_SHAPE_PAIR ? 18 : 17;
-    if (model < 0 || model > 5 || n_params < need)
+    const int need = model == JITR_B200_MODEL_KDUQ ? 40 : model == JITR_B200_MODEL_CHUQ ? 22 : model == JITR_B200_MODEL_LOCAL ? 15 : model == JITR_B200_MODEL_WLH ? 46 : model == JITR_B200_MODEL_SHAPE_PAIR ? 18 : model == JITR_B200_MODEL_DOM ? 19 : 17;
+    if (model < 0 || model > 6 || n_params < need)
         return set_error(JITR_B200_ERR_BAD_ARG, "elastic_sweep_params: model / n_params mismatch");
     SweepArgs a{};
     a.lmax = lmax; a.model = model; a.n_energies = n_energies; a.n_params = n_params;
@@ -542,8 +542,8 @@ extern "C" int jitr_b200_eval_potentials(int nbasis, int model, long long n_samp
     if (n_samples == 0) return JITR_B200_OK;  // empty batch (its tensors have null data pointers)
     if (nbasis < 1 || n_samples < 0 || n_energies < 1 || !mesh_x || !etab || !params || !central || !spin_orbit || !coulomb)
         return set_error(JITR_B200_ERR_BAD_ARG, "eval_potentials: null pointer or bad size");
-    const int need = model == JITR_B200_MODEL_KDUQ ? 40 : model == JITR_B200_MODEL_CHUQ ? 22 : model == JITR_B200_MODEL_LOCAL ? 15 : model == JITR_B200_MODEL_WLH ? 46 : model == JITR_B200_MODEL_SHAPE_PAIR ? 18 : 17;
-    if (model < 0 || model > 5 || n_params < need) return set_error(JITR_B200_ERR_BAD_ARG, "eval_potentials: model / n_params mismatch");
+    const int need = model == JITR_B200_MODEL_KDUQ ? 40 : model == JITR_B200_MODEL_CHUQ ? 22 : model == JITR_B200_MODEL_LOCAL ? 15 : model == JITR_B200_MODEL_WLH ? 46 : model == JITR_B200_MODEL_SHAPE_PAIR ? 18 : model == JITR_B200_MODEL_DOM ? 19 : 17;
+    if (model < 0 || model > 6 || n_params < need) return set_error(JITR_B200_ERR_BAD_ARG, "eval_potentials: model / n_params mismatch");
     const long long total = n_samples * n_energies * nbasis;
     if (total == 0) return JITR_B200_OK;
     eval_potentials_kernel<<<(unsigned)((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(

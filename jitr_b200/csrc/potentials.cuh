@@ -214,6 +214,130 @@ __device__ __forceinline__ Shape shape_from_canonical_pair(const double* __restr
     return s;
 }
 
+// ---- dispersive optical model (optical_potentials/dom.py:151-283, 287-382, 399-455) --------------------------------
+// The energy dependence of the DOM depths contains the analytic surface-dispersion integral: exponential integrals of real
+// argument, and of complex argument on the rays arg z = -pi/4, -3pi/4.  Series below |z| <= 8 (x <= 1 for the real E1, whose
+// alternating series cancels beyond), continued fractions (modified Lentz) / the asymptotic series above; all in the scaled
+// forms e^{-x} Ei(x), e^{x} E1(x), e^{z} E1(z) that the formula uses, so nothing overflows.
+constexpr double kEulerGamma = 0.5772156649015329;
+
+static __device__ __noinline__ double dom_expi_scaled(double x) {  // e^{-x} Ei(x), x > 0
+    if (x <= 40.0) {
+        double term = 1.0, sum = 0.0;
+        for (int k = 1; k < 200; ++k) {
+            term *= x / k;
+            const double t = term / k;
+            sum += t;
+            if (t < 1e-17 * sum) break;
+        }
+        return exp(-x) * (kEulerGamma + log(x) + sum);
+    }
+    double term = 1.0, sum = 1.0;
+    for (int k = 1; k < 60; ++k) {
+        const double next = term * k / x;
+        if (next >= term || next < 1e-17) break;
+        term = next;
+        sum += term;
+    }
+    return sum / x;
+}
+
+static __device__ __noinline__ double2 dom_cexp1_scaled(double2 z) {  // e^{z} E1(z), z off the negative real axis
+    const double r2 = z.x * z.x + z.y * z.y;
+    if (r2 <= 64.0 && !(z.y == 0.0 && z.x > 1.0)) {
+        // E1(z) = -gamma - Log z - sum_{k>=1} (-z)^k / (k k!)
+        double2 term = make_double2(1.0, 0.0), sum = make_double2(0.0, 0.0);
+        for (int k = 1; k < 200; ++k) {
+            const double tx = -(term.x * z.x - term.y * z.y) / k, ty = -(term.x * z.y + term.y * z.x) / k;
+            term = make_double2(tx, ty);
+            sum.x += tx / k;
+            sum.y += ty / k;
+            if (fabs(tx) + fabs(ty) < 1e-17 * (fabs(sum.x) + fabs(sum.y)) * k) break;
+        }
+        const double2 e1 = make_double2(-kEulerGamma - 0.5 * log(r2) - sum.x, -atan2(z.y, z.x) - sum.y);
+        const double ex = exp(z.x);
+        const double2 ez = make_double2(ex * cos(z.y), ex * sin(z.y));
+        return make_double2(ez.x * e1.x - ez.y * e1.y, ez.x * e1.y + ez.y * e1.x);
+    }
+    // e^z E1(z) = 1 / (z + 1 - 1 / (z + 3 - 4 / (z + 5 - ...)))   (modified Lentz)
+    const double tiny = 1e-300;
+    double2 b = make_double2(z.x + 1.0, z.y);
+    double2 f = b, C = b, D = make_double2(0.0, 0.0);
+    auto cinv = [](double2 v) { const double d = v.x * v.x + v.y * v.y; return make_double2(v.x / d, -v.y / d); };
+    for (int i = 1; i < 500; ++i) {
+        const double an = -(double)i * (double)i;
+        b.x += 2.0;
+        D = make_double2(b.x + an * D.x, b.y + an * D.y);
+        if (D.x == 0.0 && D.y == 0.0) D.x = tiny;
+        const double2 Ci = cinv(C);
+        C = make_double2(b.x + an * Ci.x, b.y + an * Ci.y);
+        if (C.x == 0.0 && C.y == 0.0) C.x = tiny;
+        D = cinv(D);
+        const double2 delta = make_double2(C.x * D.x - C.y * D.y, C.x * D.y + C.y * D.x);
+        f = make_double2(f.x * delta.x - f.y * delta.y, f.x * delta.y + f.y * delta.x);
+        if (fabs(delta.x - 1.0) + fabs(delta.y) < 1e-16) break;
+    }
+    return cinv(f);
+}
+
+// delta_Vs_analytic, dom.py:399-455
+static __device__ __noinline__ double dom_delta_Vs(double x, double w0, double s1, double s2) {
+    if (x == 0.0) return 0.0;
+    const double ax = fabs(x);
+    double J1 = 0.0, J2;
+    if (s2 != 0.0) {
+        const double z1 = s2 * ax;
+        J1 = (-dom_expi_scaled(z1) - dom_cexp1_scaled(make_double2(z1, 0.0)).x) / (2.0 * ax);
+        J2 = 0.0;
+        const double c = 0.7071067811865476;
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+            // root = s1 e^{i pi/4}, s1 e^{3 i pi/4};  F = e^{z} E1(z), z = -s2 root
+            const double2 root = make_double2(m == 0 ? s1 * c : -s1 * c, s1 * c);
+            const double2 F = dom_cexp1_scaled(make_double2(-s2 * root.x, -s2 * root.y));
+            // (root^2 + x^2) / (4 root^3) * F
+            const double2 r2 = make_double2(root.x * root.x - root.y * root.y, 2.0 * root.x * root.y);
+            const double2 r3 = make_double2(r2.x * root.x - r2.y * root.y, r2.x * root.y + r2.y * root.x);
+            const double2 num = make_double2(r2.x + x * x, r2.y);
+            const double d = 4.0 * (r3.x * r3.x + r3.y * r3.y);
+            const double2 q = make_double2((num.x * r3.x + num.y * r3.y) / d, (num.y * r3.x - num.x * r3.y) / d);
+            J2 += 2.0 * (q.x * F.x - q.y * F.y);
+        }
+    } else {
+        J2 = 3.141592653589793 * (s1 * s1 + x * x) / (2.0 * 1.4142135623730951 * s1 * s1 * s1);
+    }
+    const double x4 = x * x * x * x, s4 = s1 * s1 * s1 * s1;
+    return (2.0 * w0 * x / 3.141592653589793) * (x4 / (x4 + s4) * J1 + s4 / (x4 + s4) * J2);
+}
+
+// dom.calculate_params, dom.py:287-382; p: the 19 global parameters of get_param_names(); the effective Fermi energy of the
+// (projectile, target) pair comes with the energy row (JITR_B200_ET_EF)
+static __device__ __noinline__ Shape shape_from_dom(const double* __restrict__ p, const double* __restrict__ et) {
+    const double Z = et[JITR_B200_ET_ZT], Zp = et[JITR_B200_ET_ZP], A13 = et[ET_A13];
+    const double v0 = p[0], v1 = p[1], rv = p[2], av = p[3], wv0 = p[4], wv1 = p[5], rw = p[6], aw = p[7], ws0 = p[8], ws1 = p[9],
+                 ws2 = p[10], rd = p[11], ad = p[12], vso0 = p[13], wso0 = p[14], wso1 = p[15], rso = p[16], aso = p[17], rC = p[18];
+    const double RC = rC * A13;
+    const double Ec = (Zp == 1.0) ? 6.0 * (Z * Zp) * kAlpha * kHbarc / (5.0 * RC) : 0.0;  // dom.py:385-396
+    const double dE = et[JITR_B200_ET_ECM] - Ec - et[JITR_B200_ET_EF];
+    const double dE2 = dE * dE, dE4 = dE2 * dE2;
+    Shape s;
+    s.Vv = v0 * exp(-v1 * dE);
+    s.Rv = rv * A13; s.av = av;
+    s.Wv = wv0 * dE2 / (dE2 + wv1 * wv1);
+    s.Rw = rw * A13; s.aw = aw;
+    s.Vd = dom_delta_Vs(dE, ws0, ws1, ws2);
+    s.Wd = ws0 * dE4 / (dE4 + ws1 * ws1 * ws1 * ws1) * exp(-ws2 * fabs(dE));
+    s.Rd = rd * A13; s.ad = ad;
+    s.Vso = 2.0 * (vso0 * exp(-v1 * dE) + wso0 * wso1 * dE / (dE2 + wso1 * wso1));
+    s.Rso = rso * A13; s.aso = aso;
+    s.Wso = 2.0 * (wso0 * dE2 / (dE2 + wso1 * wso1));
+    s.Rwso = s.Rso; s.awso = aso;
+    s.RC = RC;
+    s.Zz = Z * Zp;
+    s.Vw = wv0 * wv1 * dE / (dE2 + wv1 * wv1);
+    return s;
+}
+
 __device__ __forceinline__ Shape shape_from_model(int model, const double* __restrict__ p, const double* __restrict__ et) {
     switch (model) {
         case JITR_B200_MODEL_SHAPE_PAIR: return shape_from_canonical_pair(p, et);
@@ -221,6 +345,7 @@ __device__ __forceinline__ Shape shape_from_model(int model, const double* __res
         case JITR_B200_MODEL_CHUQ: return shape_from_chuq(p, et);
         case JITR_B200_MODEL_LOCAL: return shape_from_local(p, et);
         case JITR_B200_MODEL_WLH: return shape_from_wlh(p, et);
+        case JITR_B200_MODEL_DOM: return shape_from_dom(p, et);
         default: return shape_from_canonical(p, et);
     }
 }

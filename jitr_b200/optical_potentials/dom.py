@@ -131,20 +131,28 @@ def shape_rows(projectile, target, Ecm, Ef, params):
 
 
 class DOM(SingleChannelOpticalModel):
-    """dom.py:483-529.  ``evaluate`` keeps the reference's single-sample contract; in a sweep the workspace asks for
-    ``pair_rows`` and the forms are evaluated inside the fused kernel."""
+    """dom.py:483-529.  ``evaluate`` keeps the reference's single-sample contract.  In a sweep the 19 global parameters go to
+    the device as they are: the energy-dependent map -- including the analytic surface-dispersion integral with its exponential
+    integrals of real and complex argument -- runs inside the fused kernel (``JITR_B200_MODEL_DOM``, csrc/potentials.cuh), the
+    effective Fermi energy of each (projectile, target) pair comes with the per-energy table (``Reaction(..., Ef=...)``).
+    ``DOM(host_map=True)`` keeps the round-1 route: the map on the host, one canonical row per (sample, energy)."""
 
-    model_id = _cabi.MODEL_SHAPE_PAIR
-
-    def __init__(self):
+    def __init__(self, host_map=False):
         super().__init__(params=get_param_names())
+        self.host_map = bool(host_map)
+        self.model_id = _cabi.MODEL_SHAPE_PAIR if self.host_map else _cabi.MODEL_DOM
+
+    @property
+    def pair_rows(self):
+        """The sweep asks for this: a callable when the map runs on the host, None when it runs in the kernel."""
+        return self.host_pair_rows if self.host_map else None
 
     @staticmethod
     def _fermi(reaction):
         Ef = getattr(reaction, "Ef", None)
         return 0.0 if Ef is None else float(Ef)
 
-    def pair_rows(self, reaction_kinematics, params, device=None):
+    def host_pair_rows(self, reaction_kinematics, params, device=None):
         """[(reaction, kinematics)] per energy + params (B, 19) -> CUDA tensor (B, E, 18)."""
         import torch
 
@@ -163,7 +171,9 @@ class DOM(SingleChannelOpticalModel):
         return torch.tensor(np.ascontiguousarray(rows), dtype=torch.float64, device=device or "cuda")
 
     def pack(self, params, device=None):
-        raise TypeError("DOM rows depend on the energy: use pair_rows (the workspaces do)")
+        if self.host_map:
+            raise TypeError("DOM(host_map=True) rows depend on the energy: use pair_rows (the workspaces do)")
+        return super().pack(params, device)
 
     def evaluate(self, rgrid, reaction, kinematics, *params):
         if len(params) != self.n_params:
@@ -177,7 +187,10 @@ class DOM(SingleChannelOpticalModel):
         etab = energy_table_row(reaction, kinematics, kinematics.k, None)
         etab[_cabi.ET_RCH] = 1.0
         dev = torch.device("cuda", torch.cuda.current_device())
-        p = self.pair_rows([(reaction, kinematics)], np.asarray(params, dtype=np.float64)[None, :], dev)
+        if self.host_map:
+            p = self.host_pair_rows([(reaction, kinematics)], np.asarray(params, dtype=np.float64)[None, :], dev)
+        else:
+            p = self.pack(np.asarray(params, dtype=np.float64)[None, :], dev)
         rt = torch.tensor(r, dtype=torch.float64, device=dev)
         et = torch.tensor(etab[None, :], dtype=torch.float64, device=dev)
         c = torch.empty(r.shape[0], dtype=torch.complex128, device=dev)

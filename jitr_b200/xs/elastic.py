@@ -61,6 +61,8 @@ def energy_table_row(reaction, kinematics, a, radius_factor=None):
     row[_cabi.ET_AM13] = A ** (-1.0 / 3.0)
     row[_cabi.ET_AM23] = A ** (-2.0 / 3.0)
     row[_cabi.ET_AM53] = A ** (-5.0 / 3.0)
+    Ef = getattr(reaction, "Ef", None)
+    row[_cabi.ET_EF] = 0.0 if Ef is None else float(Ef)  # effective Fermi energy (dispersive model)
     return row
 
 
@@ -421,7 +423,7 @@ class ElasticSweep:
         """Built-in potentials: params (B, n_params) CUDA float64 -> S (B, E, 2, lmax+1), nl (B, E), status (B, E)."""
         import torch
 
-        if hasattr(model, "pair_rows"):
+        if getattr(model, "pair_rows", None) is not None:
             # the model maps its parameters to shape numbers per (sample, energy) on the host (DOM): rows (B, E, 18)
             params = model.pair_rows([(iw.reaction, iw.kinematics) for iw in self.integral], params, self.device)
         else:
@@ -564,7 +566,7 @@ class ElasticSweep:
             if b["done"] is not None:
                 cur.wait_event(b["done"])  # previous D2H out of this buffer set has finished
             S, nl, status = (t[:n] for t in b["S"])
-            if hasattr(model, "pair_rows"):
+            if getattr(model, "pair_rows", None) is not None:
                 # parameter map on the host (one row per sample and energy): hand it the host rows
                 self.smatrix_params(model, params_host[s0 : s0 + n], out=(S, nl, status))
             else:

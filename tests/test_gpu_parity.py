@@ -755,8 +755,11 @@ def test_blocked_solver_asymmetric_couplings_take_partial_pivoting():
 # ------------------------------------------------------------------------------------------------
 # dispersive optical model: host parameter map per (sample, energy) + device forms (MODEL_SHAPE_PAIR)
 # ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("host_map", [False, True])
 @pytest.mark.parametrize("name", ["dom_n40Ca_14MeV", "dom_p208Pb_30MeV"])
-def test_dom_sweep_vs_reference_golden(golden, name):
+def test_dom_sweep_vs_reference_golden(golden, name, host_map):
+    """host_map = False: the parameter map (incl. the exponential integrals of the surface-dispersion term) runs inside the fused
+    kernel from the 19 global parameters; True: the round-1 route, the map on the host, one canonical row per (sample, energy)."""
     from jitr_b200.optical_potentials import dom
 
     g = golden(name)
@@ -764,7 +767,7 @@ def test_dom_sweep_vs_reference_golden(golden, name):
                          mass_target=float(g["masses"][0]), mass_projectile=float(g["masses"][1]), Ef=float(g["Ef"]))
     kin = rx.kinematics(float(g["kin"][0]))
     ws = jitr_b200.DifferentialWorkspace.build_from_system(rx, kin, float(g["Rch"]), jitr_b200.Solver(int(g["N"])), int(g["lmax"]), g["angles"])
-    model = dom.DOM()
+    model = dom.DOM(host_map=host_map)
     x, status = ws._as_sweep().xs_params(model, g["params"], return_status=True)
     S, nl, _ = ws.integral_workspace.smatrix_params(model, g["params"])
     assert int(status.abs().sum()) == 0
@@ -783,7 +786,8 @@ def test_dom_sweep_vs_reference_golden(golden, name):
         model(g["rgrid"], rx, kin, *g["params"][2][:-1])
 
 
-def test_dom_multi_energy_sweep_vs_oracle():
+@pytest.mark.parametrize("host_map", [False, True])
+def test_dom_multi_energy_sweep_vs_oracle(host_map):
     """Rows differ per energy: a three-energy sweep of the same samples against the oracle energy by energy."""
     from jitr_b200.optical_potentials import dom
 
@@ -793,7 +797,7 @@ def test_dom_multi_energy_sweep_vs_oracle():
     solver = jitr_b200.Solver(32)
     wss = [jitr_b200.DifferentialWorkspace.build_from_system(rx, rx.kinematics(E), 10.5, solver, 16, ang) for E in (6.0, 14.0, 27.0)]
     sweep = jitr_b200.ElasticSweep(wss)
-    x = sweep.xs_params(dom.DOM(), g["params"][:3])
+    x = sweep.xs_params(dom.DOM(host_map=host_map), g["params"][:3])
     for e, w in enumerate(wss):
         ow = orc.ElasticWorkspace(32, 16, 10.5, tuple(w.kinematics), ang, 0)
         for b in range(3):
@@ -815,9 +819,11 @@ def test_dom_mixed_target_sweep_equals_per_workspace_results():
     rx_pb = ElasticReaction((208, 82), (1, 0), mass_target=193687.12278341982, mass_projectile=float(g["masses"][1]), Ef=-5.65)
     wss = [jitr_b200.DifferentialWorkspace.build_from_system(rx, rx.kinematics(E), R, solver, 16, ang)
            for rx, E, R in ((rx_ca, 9.0, 10.5), (rx_pb, 9.0, 13.0), (rx_ca, 21.0, 10.5), (rx_pb, 21.0, 13.0))]
-    model = dom.DOM()
     p = g["params"][:3]
+    xh = jitr_b200.ElasticSweep(wss).xs_params(dom.DOM(host_map=True), p)
+    model = dom.DOM()
     x = jitr_b200.ElasticSweep(wss).xs_params(model, p)
+    assert relerr(x.dsdo.cpu().numpy(), xh.dsdo.cpu().numpy()) < 1e-9   # device map vs host map
     for e, w in enumerate(wss):
         one = jitr_b200.ElasticSweep([w]).xs_params(model, p)
         assert torch.equal(one.dsdo[:, 0], x.dsdo[:, e]) and torch.equal(one.rxn[:, 0], x.rxn[:, e])
