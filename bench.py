@@ -495,7 +495,7 @@ def main():
     ap.add_argument("--cpu-pairs", type=int, default=None, help="CPU arm: (sample, energy) pairs (configs 1-3) or systems (4, 5) per worker")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-parity", action="store_true", help="config 2, N = 1: skip the large-sample parity gate")
+    ap.add_argument("--no-parity", action="store_true", help="N = 1: skip the parity record (config 2: the large-sample gate; configs 3-5: tools/parity_general.py)")
     ap.add_argument("--no-strong", action="store_true", help="N > 1: skip the strong-scaling sub-record (configuration size in total)")
     ap.add_argument("--chunk", type=int, default=8192)
     args = ap.parse_args()
@@ -653,6 +653,13 @@ def main():
                             "sigma_rxn_max": a_["sigma_rxn"]["max"], "fallback_systems": a_["fallback"]["systems"],
                             "fallback_S_max": a_["fallback"]["S"]["max"], "S_outliers_refereed": rep[mode]["referee"]["S_refereed"],
                             "S_outliers_explained": rep[mode]["referee"]["S_explained"]}
+
+    if args.config in (3, 4, 5) and world == 1 and not args.no_parity:
+        # the bench's own inputs (leading rows / samples of the same seeded generators), every partial wave, against the oracle
+        from tools import parity_general
+
+        parity = {3: parity_general.config3, 4: parity_general.config4, 5: parity_general.config5}[args.config]()
+        parity["tool"] = "tools/parity_general.py"
 
     pairs = wl.B * wl.nE * world
     line = {

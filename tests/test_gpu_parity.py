@@ -307,6 +307,16 @@ def test_no_early_break_and_size_independent_properties():
     assert float(S[:, 1, 0].abs().max()) == 0.0
 
 
+@pytest.mark.parametrize("config", [3, 4, 5])
+def test_benchmarked_workloads_of_configs_3_4_5_vs_oracle(config):
+    """The inputs `bench.py --config 3|4|5` times (leading rows of the same seeded generators), every partial wave, against
+    the oracle: nl exact, S to 1e-10, cross sections to 1e-8 (tools/parity_general.py, the bench's own `parity` record)."""
+    from tools import parity_general
+
+    r = {3: lambda: parity_general.config3(64), 4: lambda: parity_general.config4(8), 5: lambda: parity_general.config5(6)}[config]()
+    assert r["passed"], r
+
+
 def test_large_sample_parity_gate_on_the_benchmarked_sweep():
     """BASELINE.md section 3 / SURVEY 8(d): all 416 federal KDUQ rows + 1000 of the bench's own multivariate-normal
     rows on all 64 (target, energy) workspaces of config 2 against the oracle (host cores), with the threshold-pivoted
