@@ -306,9 +306,7 @@ struct PackedSolver {
         double2 corner = make_double2(0.0, 0.0);
         int fail = 0, bad = 0;
         packed_first_panel<PT>(M, That, b, dd, N, lane, corner, fail);
-        const double2 rest = packed_ldlt<PT - 8>(M, lane, bad);
-        corner.x += rest.x;
-        corner.y += rest.y;
+        corner = packed_ldlt<PT - 8>(M, lane, bad, corner);
         __syncwarp();
         bad |= fail;
         if (bad) {

@@ -94,14 +94,17 @@ __device__ __forceinline__ void packed_panel(double2* __restrict__ M, const int 
         }
         // the unscaled column entries, in place (rows below the pivot): W of the trailing update, and the pivot row
 #pragma unroll
+        // the pivot and the pivot row's y go through shared memory too (their own positions: the diagonal entry is replaced by
+        // 1/d after the panel, the right-hand side slot gets the same value again): 3 LSU wavefronts instead of 8 for two shuffles
         for (int s = 0; s < NS; ++s) {
             const int i = 32 * s + lane;
-            if (i > kk && i < nrows) M[rb[s] + kk] = p[s][kk];
+            if (i >= kk + (s ? 1 : 0) && i < nrows) M[rb[s] + kk] = p[s][kk];
         }
-        const double2 piv = shfl2(dmine, kk);
-        double2 u[9];
-        u[8] = shfl2(p[0][8], kk);
+        if (lane == kk) M[ry[0]] = p[0][8];
         __syncwarp();
+        const double2 piv = M[dbase + kk * ldk + kk];
+        double2 u[9];
+        u[8] = M[dbase - J0 + kk * ldk + 8 * kb + 8];
 #pragma unroll
         for (int j = kk + 1; j < 8; ++j) u[j] = M[dbase + j * ldk + kk];  // pivot row = transposed pivot column
         const double sc = __shfl_sync(kFull, mys, kk);
@@ -116,16 +119,10 @@ __device__ __forceinline__ void packed_panel(double2* __restrict__ M, const int 
             for (int j = kk + 1; j < 9; ++j) cfnma(p[s][j], l, u[j]);
         }
     }
-    // corner -= sum_k y_k^2 / d_k : one term per lane k < 8
-    double2 term = cmul(cmul(ysave, rsave), ysave);
-#pragma unroll
-    for (int o = 1; o < 8; o <<= 1) {
-        term.x += __shfl_xor_sync(kFull, term.x, o);
-        term.y += __shfl_xor_sync(kFull, term.y, o);
-    }
-    const double2 tot = shfl2(term, 0);
-    cacc.x -= tot.x;
-    cacc.y -= tot.y;
+    // corner -= sum_k y_k^2 / d_k : one term per lane k < 8, per lane across the panels (packed_ldlt sums the lanes once)
+    const double2 term = cmul(cmul(ysave, rsave), ysave);
+    cacc.x -= term.x;
+    cacc.y -= term.y;
     // 1/d_k replaces the diagonal entry (trailing update, back substitution); every row keeps its final right-hand side y
     if (lane < 8) {
         M[rb[0] + lane] = rsave;
@@ -203,9 +200,11 @@ __device__ __forceinline__ void packed_trailing(double2* __restrict__ M, const i
 // In-place elimination of a packed system (lower triangle + y slots).  Returns -y^T D^-1 y = -b^T A^-1 b on every lane;
 // bad != 0 (warp-uniform on return): a pivot failed the threshold test, the value is meaningless.
 template <int P>
-__device__ __forceinline__ double2 packed_ldlt(double2* __restrict__ M, const int lane, int& bad) {
+__device__ __forceinline__ double2 packed_ldlt(double2* __restrict__ M, const int lane, int& bad,
+                                               const double2 cacc0 = make_double2(0.0, 0.0)) {
+    // cacc0: PER-LANE corner terms of panels eliminated before the call (packed_first_panel); summed with this function's own
     using G = PackedGeom<P>;
-    double2 cacc = make_double2(0.0, 0.0);
+    double2 cacc = cacc0;
     int mybad = 0;
     JITR_PH_INIT
 #pragma unroll 1
@@ -220,7 +219,7 @@ __device__ __forceinline__ double2 packed_ldlt(double2* __restrict__ M, const in
         JITR_PH(2)
     }
     bad = __any_sync(kFull, mybad) ? 1 : 0;
-    return cacc;
+    return corner_total(cacc);
 }
 
 // First panel of  That + diag(d)  straight from That (the fused sweep: the system never exists as a whole, lu_sym.cuh), for the
@@ -231,7 +230,7 @@ __device__ __forceinline__ double2 packed_ldlt(double2* __restrict__ M, const in
 //       fragments are taken into registers before the first block row is written over it;
 //   LB  the multipliers of rows 8..PT-1, at the END: block rows are written in ascending order and reach LB only at the last
 //       two, whose own A fragments are loaded before they are stored.
-// Returns the panel's contribution to the corner; `fail` as sym_panel_eliminate.  d[s]: diagonal entries of rows lane + 32 s
+// cacc: the panel's PER-LANE corner terms are accumulated into it (hand it to packed_ldlt as cacc0); `fail` as sym_panel_eliminate.  d[s]: diagonal entries of rows lane + 32 s
 // (the caller passes 1 for the identity padding), bsh: boundary vector b (shared memory, zero padded), N: real rows.
 template <int PT>
 __device__ __forceinline__ void packed_first_panel(double2* __restrict__ W, const double* __restrict__ That, const double* __restrict__ bsh,
@@ -252,13 +251,17 @@ __device__ __forceinline__ void packed_first_panel(double2* __restrict__ W, cons
         }
         p[s][8] = make_double2(i < PT ? bsh[i] : 0.0, 0.0);
     }
-    sym_panel_eliminate<2>(
+    sym_panel_eliminate<2, true>(
         p, PT, lane, cacc, fail,
         [&](int s, int kk, double2 v) {
+            if (s < 0) {
+                W[WB_OFF + kk * LB_LD + (s == -1 ? kk : 8)] = v;
+                return;
+            }
             const int i = 32 * s + lane;
             if (i > kk && i < PT) W[WB_OFF + i * LB_LD + kk] = v;
         },
-        [&](int kk, int j) { return W[WB_OFF + j * LB_LD + kk]; });
+        [&](int kk, int j) { return j < 0 ? W[WB_OFF + kk * LB_LD + (j == -1 ? kk : 8)] : W[WB_OFF + j * LB_LD + kk]; });
     double2 ykeep[2];
 #pragma unroll
     for (int s = 0; s < 2; ++s) {

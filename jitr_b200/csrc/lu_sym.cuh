@@ -54,7 +54,10 @@ struct SymGeom {
 // broadcast: 2 SM-cycles against the 4 of a 128-bit shuffle; the store is issued anyway).  On return
 // p[s][k] are the multipliers and p[s][8] the updated RHS.  cacc accumulates the corner; fail is set when
 // a diagonal entry fails the threshold test (or is zero / not finite).
-template <int NS, class StoreW, class LoadU>
+// BC: 1/d and y of the pivot row travel through shared memory as well -- store_w(-1 / -2, kk, v) by lane kk, load_u(kk, -1 / -2)
+// by all -- instead of two 128-bit shuffles: 8 LSU wavefronts -> 4 per column; the LSU pipe is the second-busiest unit of the
+// N = 40 sweep (69 %), measured +2.1 % (profiles/r02_sweep_variants.md).
+template <int NS, bool BC = false, class StoreW, class LoadU>
 __device__ __forceinline__ void sym_panel_eliminate(double2 (&p)[NS][9], const int nrows, const int lane,
                                                     double2& cacc, int& fail, StoreW store_w, LoadU load_u) {
 #ifdef JITR_SYM_FASTCHAIN
@@ -121,10 +124,21 @@ __device__ __forceinline__ void sym_panel_eliminate(double2 (&p)[NS][9], const i
         }
 #pragma unroll
         for (int s = 0; s < NS; ++s) store_w(s, kk, p[s][kk]);
-        const double2 rinv = shfl2(myrinv, kk);
+        double2 rinv;
         double2 u[9];
-        u[8] = shfl2(p[0][8], kk);
-        __syncwarp();
+        if constexpr (BC) {
+            if (lane == kk) {
+                store_w(-1, kk, myrinv);
+                store_w(-2, kk, p[0][8]);
+            }
+            __syncwarp();
+            rinv = load_u(kk, -1);
+            u[8] = load_u(kk, -2);
+        } else {
+            rinv = shfl2(myrinv, kk);
+            u[8] = shfl2(p[0][8], kk);
+            __syncwarp();
+        }
         // pivot row = transposed pivot column: the entries the rows kk+1..7 have just stored
 #pragma unroll
         for (int j = kk + 1; j < 8; ++j) u[j] = load_u(kk, j);
@@ -137,17 +151,22 @@ __device__ __forceinline__ void sym_panel_eliminate(double2 (&p)[NS][9], const i
         }
     }
 #endif
-    // corner -= sum_k y_k^2 / d_k : one term per lane k < 8, summed over the eight lanes
-    double2 term = cmul(cmul(ysave, rsave), ysave);
+    // corner -= sum_k y_k^2 / d_k : one term per lane k < 8 (zero on the others), kept PER LANE across the panels; the owner of
+    // cacc sums the eight lanes once, after the last panel (corner_total) -- 16 shuffles per solve instead of per panel
+    const double2 term = cmul(cmul(ysave, rsave), ysave);
+    cacc.x -= term.x;
+    cacc.y -= term.y;
+    if (__any_sync(kFull, myfail)) fail = 1;
+}
+
+// Sum of the per-lane corner terms of the panels (lanes 0..7), on every lane.
+__device__ __forceinline__ double2 corner_total(double2 t) {
 #pragma unroll
     for (int o = 1; o < 8; o <<= 1) {
-        term.x += __shfl_xor_sync(kFull, term.x, o);
-        term.y += __shfl_xor_sync(kFull, term.y, o);
+        t.x += __shfl_xor_sync(kFull, t.x, o);
+        t.y += __shfl_xor_sync(kFull, t.y, o);
     }
-    const double2 tot = shfl2(term, 0);  // lanes >= 8 hold zeros: take the sum from the first group
-    cacc.x -= tot.x;
-    cacc.y -= tot.y;
-    if (__any_sync(kFull, myfail)) fail = 1;
+    return shfl2(t, 0);  // lanes >= 8 hold zeros: take the sum from the first group
 }
 
 // lower-triangle trailing update of the Schur complement in W after panel J0 (nt <= 3 tile rows)
@@ -300,7 +319,7 @@ __device__ __forceinline__ double2 sym_schur_inplace(double2* __restrict__ M, co
         __syncwarp();
         JITR_PH(2)
     }
-    return cacc;
+    return corner_total(cacc);
 }
 
 // Returns -b^T (That + diag d)^-1 b on every lane; fail != 0: a pivot failed the threshold test and the
@@ -329,13 +348,17 @@ __device__ __forceinline__ double2 sym_schur(double2* __restrict__ W, double2* _
             }
             p[s][8] = make_double2(bsh[ic], 0.0);
         }
-        sym_panel_eliminate<NS>(
+        sym_panel_eliminate<NS, true>(
             p, PT, lane, cacc, fail,
             [&](int s, int kk, double2 v) {
+                if (s < 0) {  // lane kk: 1/d in the diagonal slot, y in the pad slot of WB row kk (both otherwise unused)
+                    W[G::WB_OFF + kk * G::LB_LD + (s == -1 ? kk : 8)] = v;
+                    return;
+                }
                 const int i = 32 * s + lane;
                 if (i > kk && i < PT) W[G::WB_OFF + i * G::LB_LD + kk] = v;
             },
-            [&](int kk, int j) { return W[G::WB_OFF + j * G::LB_LD + kk]; });
+            [&](int kk, int j) { return j < 0 ? W[G::WB_OFF + kk * G::LB_LD + (j == -1 ? kk : 8)] : W[G::WB_OFF + j * G::LB_LD + kk]; });
         double2 ykeep[NS];
 #pragma unroll
         for (int s = 0; s < NS; ++s) {
@@ -416,13 +439,16 @@ __device__ __forceinline__ double2 sym_schur(double2* __restrict__ W, double2* _
             for (int j = 0; j < 8; ++j) p[0][j] = W[row * LDW + J0 + j];
             p[0][8] = W[row * LDW + n];
         }
-        sym_panel_eliminate<1>(
+        sym_panel_eliminate<1, true>(
             p, nrows, lane, cacc, fail,
-            [&](int, int kk, double2 v) {
-                // the unscaled column entry of row J0 + lane is U[kk][lane]: its natural (upper) position
+            [&](int s, int kk, double2 v) {
+                if (s < 0) {  // lane kk: 1/d on the diagonal, y in the RHS column of the pivot row (neither is read again)
+                    W[(J0 + kk) * LDW + (s == -1 ? J0 + kk : n)] = v;
+                    return;
+                }
                 if (lane > kk && lane < nrows) W[(J0 + kk) * LDW + J0 + lane] = v;
             },
-            [&](int kk, int j) { return W[(J0 + kk) * LDW + J0 + j]; });
+            [&](int kk, int j) { return j < 0 ? W[(J0 + kk) * LDW + (j == -1 ? J0 + kk : n)] : W[(J0 + kk) * LDW + J0 + j]; });
         if (nrows <= 8) {
             JITR_PH(0)
             break;
@@ -439,7 +465,7 @@ __device__ __forceinline__ double2 sym_schur(double2* __restrict__ W, double2* _
         __syncwarp();
         JITR_PH(2)
     }
-    return cacc;
+    return corner_total(cacc);
 }
 
 }  // namespace jitr

@@ -410,9 +410,7 @@ packed_solve_kernel(const GenArgs A, const int* __restrict__ symflag, const int 
                                : first_panel_global<P, true, false, false>(M, F, Vsrc, Vloc, ws, bs, nl_scale, E0, N, lane, bar, parity, corner, fail);
                 defer = __any_sync(kFull, diff != 0ULL);
                 if (!defer) {
-                    const double2 rest = packed_ldlt<P - 8>(M, lane, bad);
-                    corner.x += rest.x;
-                    corner.y += rest.y;
+                    corner = packed_ldlt<P - 8>(M, lane, bad, corner);
                     bad |= fail;
                     defer = bad != 0;
                     if (defer && lane == 0 && A.fallbacks) atomicAdd(A.fallbacks, 1ULL);

@@ -1316,3 +1316,95 @@ def test_indexed_free_matrices_equal_per_partial_wave_calls():
         for q, l in enumerate(ls):
             per = solver.solve_batch(a, E[0], k0, nch, free[q], asym[q], local_potential=loc_t)
             assert torch.equal(one["S"][q * B:(q + 1) * B], per["S"]) and torch.equal(one["R"][q * B:(q + 1) * B], per["R"])
+
+
+class _Guarded:
+    """Output / input buffers cut out of a larger allocation whose margins hold a canary pattern: a kernel that writes out of
+    bounds changes a margin, a kernel that reads out of bounds and uses the value sees NaNs (the device-side stand-in for a
+    memory checker: bounds evidence from our own guard bands, small cases and bit-for-bit comparison with an unguarded run)."""
+
+    MARGIN = 4096  # bytes on both sides
+
+    def __init__(self):
+        self.bufs = []
+
+    def empty(self, shape, dtype, fill=None):
+        n = int(np.prod(shape)) * torch.empty((), dtype=dtype).element_size()
+        pad = (-n) % 16
+        raw = torch.full((self.MARGIN + n + pad + self.MARGIN,), 0xA5, dtype=torch.uint8, device="cuda")
+        if dtype in (torch.float64, torch.complex128):  # margins that poison any value computed from them
+            raw[: self.MARGIN].view(torch.float64).fill_(float("nan"))
+            raw[self.MARGIN + n + pad:].view(torch.float64).fill_(float("nan"))
+        view = raw[self.MARGIN: self.MARGIN + n].view(dtype).reshape(shape)
+        if fill is not None:
+            view.copy_(fill)
+        self.bufs.append((raw, n + pad, raw[: self.MARGIN].clone(), raw[self.MARGIN + n + pad:].clone()))
+        return view
+
+    def check(self):
+        torch.cuda.synchronize()
+        for raw, n, lo, hi in self.bufs:
+            assert torch.equal(raw[: self.MARGIN], lo) or bool(torch.equal(raw[: self.MARGIN].view(torch.int64), lo.view(torch.int64))), "write below a buffer"
+            assert torch.equal(raw[self.MARGIN + n:].view(torch.int64), hi.view(torch.int64)), "write beyond a buffer"
+
+
+@pytest.mark.parametrize("N,lmax,B", [(12, 9, 37), (40, 30, 75), (40, 30, 3), (56, 24, 41), (64, 40, 13)])
+def test_guard_bands_around_sweep_buffers(golden, N, lmax, B):
+    """Every path of the fused sweep (small modes, the N = 40 symmetric mode incl. the partial-wave split of small batches,
+    the packed modes), odd batch sizes: inputs and outputs live between NaN / canary guard bands; the results must equal the
+    unguarded run bit for bit and the bands must be untouched."""
+    g = golden("kduq_params")
+    rows = np.zeros((B, 40))
+    rows[:, :37] = np.tile(g["federal_n"], (B // len(g["federal_n"]) + 1, 1))[:B]
+    rx = ElasticReaction((208, 82), (1, 0), mass_target=193687.12278341982, mass_projectile=939.5654983938299)
+    solver = jitr_b200.Solver(N)
+    ang = np.linspace(0.1, np.pi, 23)
+    wss = [jitr_b200.DifferentialWorkspace.build_from_system(rx, rx.kinematics(E), 12.0, solver, lmax, ang) for E in (7.0, 33.0, 61.0)]
+    sweep = jitr_b200.ElasticSweep(wss)
+    model = kduq.KDUQ((1, 0))
+    p = torch.tensor(rows, device="cuda")
+    S0, nl0, st0 = sweep.smatrix_params(model, p)
+    x0 = sweep.observables(S0, nl0)
+    G = _Guarded()
+    pg = G.empty(p.shape, torch.float64, fill=p)
+    out = (G.empty(S0.shape, torch.complex128), G.empty(nl0.shape, nl0.dtype), G.empty(st0.shape, st0.dtype))
+    S, nl, st = sweep.smatrix_params(model, pg, out=out)
+    obs = (G.empty(x0.dsdo.shape, torch.float64), G.empty(x0.dsdo.shape, torch.float64), G.empty(x0.dsdo.shape, torch.float64),
+           G.empty((B, 3, 2), torch.float64))
+    x = sweep.observables(S, nl, out=obs)
+    G.check()
+    assert torch.equal(nl, nl0) and torch.equal(st, st0)
+    assert torch.equal(torch.view_as_real(S), torch.view_as_real(S0))
+    for a, b in ((x.dsdo, x0.dsdo), (x.Ay, x0.Ay), (x.Q, x0.Q), (x.t, x0.t), (x.rxn, x0.rxn)):
+        assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("N,nch,B", [(60, 1, 19), (23, 1, 7), (50, 3, 5), (21, 2, 9)])
+def test_guard_bands_around_general_solver_buffers(N, nch, B):
+    """solve_batched (packed single-channel kernel and the blocked multi-channel kernel): every input between NaN guard bands
+    -- an over-read that reaches the arithmetic poisons the result -- compared bit for bit with the unguarded call."""
+    rng = np.random.default_rng(N * 10 + nch)
+    solver = jitr_b200.Solver(N)
+    a, k, E = 11.0, 0.9, 14.0
+    free = torch.tensor(solver.free_matrix(a, [1] * nch), device="cuda")
+    H = np.array([orc.coulomb_hankel(1, 0.0, a) for _ in range(nch)]).T
+    asym = torch.tensor(np.ascontiguousarray(H), device="cuda")
+    r = solver.radial_grid(a, k)
+    V = np.zeros((B, nch, nch, N), dtype=np.complex128)
+    for b in range(B):
+        for i in range(nch):
+            for j in range(i, nch):
+                v = (-40.0 - 5j if i == j else 3.0) * (1 + 0.1 * rng.standard_normal()) / (1 + np.exp((r - 4.0) / 0.6))
+                V[b, i, j] = V[b, j, i] = v
+    Vt = torch.tensor(V, device="cuda")
+    o0 = solver.solve_batch(a, E, k, nch, free, asym, local_potential=Vt)
+    G = _Guarded()
+    Vg = G.empty(Vt.shape, torch.complex128, fill=Vt)
+    fg = G.empty(free.shape, torch.complex128, fill=free)
+    ag = G.empty(asym.shape, torch.complex128, fill=asym)
+    o1 = solver.solve_batch(a, E, k, nch, fg, ag, local_potential=Vg)
+    G.check()
+    assert int(o0["status"].abs().sum()) == 0
+    for key in ("R", "S", "uext"):
+        if key in o0:
+            assert torch.equal(torch.view_as_real(o0[key]), torch.view_as_real(o1[key])), key
