@@ -122,6 +122,12 @@ def fp64_peak(L):
 # ====================================================================================================================
 # workloads: each provides  setup / step (device-resident inputs) / e2e_step (host buffers) / cpu runs
 # ====================================================================================================================
+def _mark(torch):
+    e = torch.cuda.Event(enable_timing=True)
+    e.record()
+    return e
+
+
 class Config2:
     """KDUQ posterior sweep (the headline).  Also configs 1 and 3 (single-workspace variants of the same fused sweep)."""
 
@@ -184,39 +190,120 @@ class Config2:
         self.Ay = torch.empty_like(self.dsdo) if self.want_Ay else None
         self.tr = torch.empty((B, self.nE, 2), dtype=torch.float64, device=dev)
         self.gather_out = None
-        if world > 1 and not self.args.no_gather_dsdo and rank == 0:
+        self.windows = None
+        if world > 1 and self.args.gather_mode == "p2p" and self.S_total == B * world:
+            # root-resident windows written by copy-engine peer copies (sharding.PeerWindow); any failure -> the NCCL gather
+            try:
+                from jitr_b200.sharding import PeerWindow
+
+                wins = [PeerWindow((self.S_total, self.nE, 2), torch.float64, dev)]
+                if not self.args.no_gather_dsdo:
+                    wins.append(PeerWindow((self.S_total, self.nE, nth), torch.float64, dev))
+                ok = torch.ones(1, dtype=torch.int32, device=dev)
+            except Exception as exc:  # noqa: BLE001
+                sys.stderr.write(f"[bench] rank {rank}: peer windows unavailable ({exc!r}); using the NCCL gather\n")
+                wins, ok = None, torch.zeros(1, dtype=torch.int32, device=dev)
+            import torch.distributed as dist
+
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            self.windows = wins if int(ok.item()) == 1 else None
+        if world > 1 and self.windows is None and not self.args.no_gather_dsdo and rank == 0:
             self.gather_out = (torch.empty((self.S_total, self.nE, nth), dtype=torch.float64, device=dev),
                                torch.empty((self.S_total, self.nE, 2), dtype=torch.float64, device=dev))
         self.ev = None
         self.kernel = f"elastic_sweep_kernel<PARAMS=true, MODE={40 if self.N == 40 else 64}> (fused potentials + {'assembly-free' if self.N == 40 else 'packed lower-triangle'} LDL^T + R->S)"
 
     def step(self, timed_events=None):
-        from jitr_b200.sharding import gather_to_root
+        """One pass of the hot path over this rank's block.  N > 1: the block is processed in `--gather-chunks` chunks of samples and
+        every chunk's observables start their way to rank 0 (one asynchronous NCCL gather per chunk, into the root's preallocated
+        slices) while the next chunk is being solved: the 9.3 GB per rank of a 10^5-sample sweep (65 GB into the root at N = 8)
+        hide behind the elimination except for the last chunk.  timed_events: a list the step appends (kind, start, end) to."""
+        from jitr_b200.sharding import gather_chunk_async
 
         torch = self.torch
         ev = timed_events
-        if ev:
-            ev[0].record()
-        self.sweep.smatrix_params(self.model, self.params_dev, out=self.Sbuf)
-        if ev:
-            ev[1].record()
-        self.sweep.observables(self.Sbuf[0], self.Sbuf[1], want_Ay=self.want_Ay, want_Q=False, out=(self.dsdo, self.Ay, None, self.tr))
-        if ev:
-            ev[2].record()
-        if self.world > 1:
-            go = self.gather_out
+        mark = (lambda: _mark(torch)) if ev is not None else (lambda: None)
+        B = self.B
+        nchunk = max(1, min(self.args.gather_chunks if self.windows is not None else self.args.nccl_gather_chunks, B)) if self.world > 1 else 1
+        equal = self.S_total == B * self.world
+        if self.world > 1 and not equal:
+            nchunk = 1
+        bounds = [(c * B // nchunk, (c + 1) * B // nchunk) for c in range(nchunk)]
+        go = self.gather_out
+        offs = [r * B for r in range(self.world)]
+        works = []
+        S, nl, st = self.Sbuf
+        t_last = None
+        for (c0, c1) in bounds:
+            t0 = mark()
+            self.sweep.smatrix_params(self.model, self.params_dev[c0:c1], out=(S[c0:c1], nl[c0:c1], st[c0:c1]))
+            t1 = mark()
+            self.sweep.observables(S[c0:c1], nl[c0:c1], want_Ay=self.want_Ay, want_Q=False,
+                                   out=(self.dsdo[c0:c1], None if self.Ay is None else self.Ay[c0:c1], None, self.tr[c0:c1]))
+            t2 = mark()
+            if ev is not None:
+                ev.append(("k1", t0, t1))
+                ev.append(("k2", t1, t2))
+            t_last = t2
+            if self.windows is not None:
+                self.windows[0].push(self.tr[c0:c1], self.rank * B + c0)
+                if len(self.windows) > 1:
+                    self.windows[1].push(self.dsdo[c0:c1], self.rank * B + c0)
+            elif self.world > 1 and equal:
+                works.append(gather_chunk_async(self.tr[c0:c1], None if go is None else go[1], offs, c0, c1))
+                if not self.args.no_gather_dsdo:
+                    works.append(gather_chunk_async(self.dsdo[c0:c1], None if go is None else go[0], offs, c0, c1))
+        if self.world > 1 and not equal:  # uneven blocks: the padded one-shot gather
+            from jitr_b200.sharding import gather_to_root
+
             gather_to_root(self.tr, self.S_total, dst=0, out=None if go is None else go[1])
             if not self.args.no_gather_dsdo:
                 gather_to_root(self.dsdo, self.S_total, dst=0, out=None if go is None else go[0])
-        if ev:
-            ev[3].record()
+        for w_ in works:
+            w_.wait()
+        if self.windows is not None:
+            for w_ in self.windows:
+                w_.flush()
+        if ev is not None:
+            ev.append(("coll", t_last, mark()))  # what is left of the transfers after the last chunk's kernels: the exposed part
+
+    def collective_check(self):
+        """Every rank's block sums against the sums of the rows the root received for it (all ranks call this)."""
+        import torch.distributed as dist
+
+        torch = self.torch
+        mine = torch.stack([self.tr.sum(), self.dsdo.sum()]).reshape(1, 2)
+        allv = torch.empty((self.world, 2), dtype=torch.float64, device=self.dev)
+        dist.all_gather_into_tensor(allv, mine)
+        if self.rank != 0:
+            return None
+        got_tr = self.windows[0].buf if self.windows is not None else (self.gather_out[1] if self.gather_out is not None else None)
+        got_ds = (self.windows[1].buf if len(self.windows) > 1 else None) if self.windows is not None else (
+            self.gather_out[0] if self.gather_out is not None else None)
+        ok = True
+        B = self.B
+        for r in range(self.world):
+            if got_tr is not None:
+                ok &= bool(torch.allclose(got_tr[r * B:(r + 1) * B].sum(), allv[r, 0], rtol=1e-12, atol=0.0))
+            if got_ds is not None:
+                ok &= bool(torch.allclose(got_ds[r * B:(r + 1) * B].sum(), allv[r, 1], rtol=1e-12, atol=0.0))
+        return ok
 
     def collective(self):
         if self.world == 1:
             return None
         per_rank = self.tr.numel() * 8 + (0 if self.args.no_gather_dsdo else self.dsdo.numel() * 8)
-        return {"op": "torch.distributed.gather (NCCL) of dsigma/dOmega [S/G, E, n_angles] + (sigma_tot, sigma_rxn) [S/G, E, 2] to rank 0, once per step",
-                "bytes_per_rank": int(per_rank), "bytes_into_root": int(per_rank * (self.world - 1))}
+        what = "dsigma/dOmega [S/G, E, n_angles] + (sigma_tot, sigma_rxn) [S/G, E, 2] to rank 0"
+        if self.windows is not None:
+            op = (f"copy-engine peer copies (CUDA IPC window on rank 0, cudaMemcpyAsync over NVLink, no SMs) of {what}, in {self.args.gather_chunks} chunks of "
+                  "samples per step, each queued behind its chunk's kernels and overlapped with the next chunk's solve, + one 4-byte NCCL all_reduce as "
+                  "the completion barrier; ms_per_step = what stays exposed after the last chunk's kernels")
+            chunks = int(self.args.gather_chunks)
+        else:
+            chunks = int(self.args.nccl_gather_chunks)
+            op = f"torch.distributed.gather (NCCL) of {what}, once per step" + ("" if chunks == 1 else f" in {chunks} asynchronous chunks")
+        return {"op": op, "mode": "p2p" if self.windows is not None else "nccl", "chunks": chunks, "bytes_per_rank": int(per_rank),
+                "bytes_into_root": int(per_rank * (self.world - 1))}
 
     def solves(self):
         return int((2 * self.Sbuf[1].to(self.torch.int64) - 1).sum().item())
@@ -379,17 +466,16 @@ class Config45:
         import torch.distributed as dist
 
         ev = timed_events
-        if ev:
-            ev[0].record()
+        mark = (lambda: _mark(self.torch)) if ev is not None else (lambda: None)
+        t0 = mark()
         self._solve_all()
-        if ev:
-            ev[1].record()
-            ev[2].record()
+        t1 = mark()
         if self.world > 1:
             # (NCCL has no complex type: the S-matrices travel as interleaved float64 pairs)
             dist.gather(self.torch.view_as_real(self.Sout), [self.torch.view_as_real(g) for g in self.gather_out.unbind(0)] if self.rank == 0 else None, dst=0)
-        if ev:
-            ev[3].record()
+        if ev is not None:
+            ev.append(("k1", t0, t1))
+            ev.append(("coll", t1, mark()))
 
     def collective(self):
         if self.world == 1:
@@ -491,6 +577,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--samples", type=int, default=None, help="samples per GPU (weak scaling); default: the configuration's own size")
     ap.add_argument("--no-gather-dsdo", action="store_true", help="N > 1: gather sigma_tot / sigma_rxn only")
+    ap.add_argument("--gather-mode", default="p2p", choices=["nccl", "p2p"],
+                    help="N > 1: how the observables reach rank 0 -- p2p: copy-engine peer copies into a CUDA-IPC window on rank 0, chunk by chunk beside "
+                         "the solve (falls back to nccl if the window cannot be set up); nccl: one torch.distributed.gather at the end of the step")
+    ap.add_argument("--gather-chunks", type=int, default=4, help="p2p mode: chunks of samples per step; a chunk's observables travel to rank 0 while the next is solved")
+    ap.add_argument("--nccl-gather-chunks", type=int, default=1, help="nccl mode: > 1 launches one asynchronous gather per chunk (measured slower: its copy kernels wait for SMs)")
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--cpu-pairs", type=int, default=None, help="CPU arm: (sample, energy) pairs (configs 1-3) or systems (4, 5) per worker")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -535,16 +626,14 @@ def main():
         per_step = []
         e_begin.record()
         for _ in range(steps):
-            evs = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-            w.step(evs)
-            per_step.append(evs)
+            w.step(per_step)
         e_end.record()
         sync_all()
         t1 = time.time()
         total = e_begin.elapsed_time(e_end)
-        t_k1 = sum(e[0].elapsed_time(e[1]) for e in per_step)
-        t_k2 = sum(e[1].elapsed_time(e[2]) for e in per_step)
-        t_coll = sum(e[2].elapsed_time(e[3]) for e in per_step)
+        t_k1 = sum(a.elapsed_time(b) for k, a, b in per_step if k == "k1")
+        t_k2 = sum(a.elapsed_time(b) for k, a, b in per_step if k == "k2")
+        t_coll = sum(a.elapsed_time(b) for k, a, b in per_step if k == "coll")
         my_solves = w.solves()
         tt = torch.tensor([total, float(my_solves), t_k1, t_k2, t_coll], dtype=torch.float64, device=dev)
         all_solves = float(my_solves)
@@ -559,6 +648,10 @@ def main():
                     clocks=clocks.stop(t0, t1) if clocks else None)
 
     main_run = timed_run(wl, args.steps, args.warmup, True)
+    collective_desc = wl.collective() if world > 1 else None
+    if world > 1 and hasattr(wl, "collective_check") and wl.S_total == wl.B * world:
+        torch.cuda.synchronize()
+        collective_desc["received_block_sums_match"] = wl.collective_check()
     ms_per_step = main_run["ms_per_step"]
     value = main_run["all_solves"] / (ms_per_step * 1e-3)
     status_bad = wl.status_bad()
@@ -592,6 +685,10 @@ def main():
         ws = make_workload(sargs)
         del wl.gather_out
         wl.gather_out = None
+        if getattr(wl, "windows", None) is not None:
+            for w_ in wl.windows:
+                w_.close()
+            wl.windows = None
         torch.cuda.empty_cache()
         ws.setup(dev, rank, world)
         r = timed_run(ws, args.steps, max(1, args.warmup), False)
@@ -599,6 +696,12 @@ def main():
                   "value": r["all_solves"] / (r["ms_per_step"] * 1e-3), "unit": "solves/s", "scaling": "strong",
                   "collective_ms_per_step": r["coll_ms"], "collective": ws.collective()}
 
+    for w_obj in (wl, locals().get("ws")):
+        wins = getattr(w_obj, "windows", None) if w_obj is not None else None
+        if wins is not None:
+            for w_ in wins:
+                w_.close()
+            w_obj.windows = None
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -674,9 +777,10 @@ def main():
         "e2e": e2e, "gpu_launches": int(main_run["launches"]), "clocks": main_run["clocks"], "roofline": roofline, "cpu_baseline": cpu_baseline,
     }
     if world > 1:
-        c = wl.collective()
+        c = collective_desc
         c["ms_per_step"] = main_run["coll_ms"]
-        c["GBps_into_root"] = c["bytes_into_root"] / (main_run["coll_ms"] * 1e-3) / 1e9 if main_run["coll_ms"] > 0 else None
+        if c.get("chunks", 1) == 1:  # not overlapped: the transfer time itself
+            c["GBps_into_root"] = c["bytes_into_root"] / (main_run["coll_ms"] * 1e-3) / 1e9 if main_run["coll_ms"] > 0 else None
         line["collective"] = c
         line["strong"] = strong
     if parity is not None:

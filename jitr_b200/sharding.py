@@ -51,3 +51,82 @@ def gather_to_root(shard, n_samples: int, dst: int = 0, group=None, out=None):
     if rank != dst:
         return None
     return torch.cat([b[: h - l] for b, (l, h) in zip(bufs, sizes)], dim=0)
+
+
+def gather_chunk_async(chunk, out, rank_offsets, c0: int, c1: int, dst: int = 0, group=None):
+    """Pipelined form of ``gather_to_root`` for a sweep processed in chunks of samples: every rank passes the rows [c0, c1) of ITS
+    block (``chunk``, contiguous) as soon as they are finished, the root receives rank r's rows in ``out[rank_offsets[r] + c0 :
+    rank_offsets[r] + c1]`` (``out`` is ignored elsewhere).  The collective is launched asynchronously (``async_op=True``: NCCL's own
+    stream, ordered after the work already queued on the current stream) so that the next chunk's kernels run beside the transfer;
+    returns the work handle -- ``handle.wait()`` orders the current stream after the transfer without blocking the host.
+    Blocks must be equal (``rank_offsets[r] = r * block``)."""
+    import torch.distributed as dist
+
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    bufs = [out[rank_offsets[r] + c0: rank_offsets[r] + c1] for r in range(world)] if rank == dst else None
+    return dist.gather(chunk.contiguous(), bufs, dst=dst, group=group, async_op=True)
+
+
+class PeerWindow:
+    """A buffer on the root rank's GPU that every rank of the node writes with COPY-ENGINE peer copies (CUDA IPC mapping of the
+    root's allocation + ``cudaMemcpyAsync`` over NVLink): no SM takes part, so a chunk of observables travels to the root while
+    the persistent sweep kernel -- which fills every SM -- solves the next chunk.  (An NCCL gather needs SMs for its copy
+    kernels on both ends; launched behind a chunk it waits for the next chunk's CTAs to drain and holds SMs meanwhile: measured
+    SLOWER than the one-shot gather)  Single node only; every rank must see the root's device.
+
+        win = PeerWindow((n_samples, E, n_angles), torch.float64, device)      # collective: all ranks
+        win.push(chunk, row0)        # after the kernels queued on the current stream, on a side stream
+        win.flush()                  # current stream waits for this rank's copies; then one tiny all_reduce = "all have landed"
+        win.buf                      # the root's tensor (on the other ranks: the IPC-mapped view of it)
+    """
+
+    def __init__(self, shape, dtype, device, dst: int = 0, group=None):
+        import torch
+        import torch.distributed as dist
+        from torch.multiprocessing.reductions import reduce_tensor
+
+        self.group, self.dst = group, dst
+        self.rank = dist.get_rank(group)
+        self.device = torch.device(device)
+        payload = [None]
+        if self.rank == dst:
+            self.buf = torch.empty(shape, dtype=dtype, device=self.device)
+            payload = [reduce_tensor(self.buf)]
+        dist.broadcast_object_list(payload, src=dst, group=group)
+        if self.rank != dst:
+            fn, args = payload[0]
+            # The IPC handle is opened in THIS rank's device context (argument 6 of rebuild_cuda_tensor is the device the handle
+            # is opened on): the mapping is then a peer pointer this GPU's copy engines write through NVLink directly.  Opened on
+            # the root's device instead (the default), the memory belongs to another context of this process and the copy is
+            # staged through the host: measured 37 GB/s and no overlap (tools/p2p_probe.py).
+            args = list(args)
+            args[6] = self.device.index
+            self.buf = fn(*args)
+        self.stream = torch.cuda.Stream(device=self.device)
+        self._flag = torch.zeros(1, dtype=torch.int32, device=self.device)
+
+    def push(self, chunk, row0: int):
+        import torch
+
+        cur = torch.cuda.current_stream(self.device)
+        self.stream.wait_stream(cur)
+        with torch.cuda.stream(self.stream):
+            self.buf[row0: row0 + chunk.shape[0]].copy_(chunk, non_blocking=True)
+
+    def flush(self):
+        import torch
+        import torch.distributed as dist
+
+        torch.cuda.current_stream(self.device).wait_stream(self.stream)
+        dist.all_reduce(self._flag, group=self.group)  # ordered after the copies on every rank: when it completes, all have landed
+
+    def close(self):
+        """Collective: the mapped views are dropped before the root releases its allocation."""
+        import torch
+        import torch.distributed as dist
+
+        torch.cuda.synchronize(self.device)
+        if self.rank != self.dst:
+            self.buf = None
+        dist.barrier(group=self.group)
+        self.buf = None

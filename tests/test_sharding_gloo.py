@@ -82,3 +82,51 @@ def test_gather_to_root_gloo(world, n_samples):
 def test_gather_single_process_is_identity():
     x = torch.arange(12.0).reshape(4, 3)
     assert gather_to_root(x, 4) is x
+
+
+def _worker_chunks(rank, world, port, block, nchunk, out):
+    """bench.py's N > 1 step: the block is processed in chunks, every chunk gathered asynchronously into the root's preallocated
+    slices (gather_chunk_async) and into `out=` (gather_to_root) -- both must reproduce the global array."""
+    import torch.distributed as dist
+
+    from jitr_b200.sharding import gather_chunk_async
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        n = block * world
+        s = torch.arange(rank * block, (rank + 1) * block, dtype=torch.float64)[:, None]
+        shard = 7.0 * s + torch.arange(4, dtype=torch.float64)[None, :]
+        full = torch.full((n, 4), -1.0, dtype=torch.float64) if rank == 0 else None
+        works = []
+        for c in range(nchunk):
+            c0, c1 = c * block // nchunk, (c + 1) * block // nchunk
+            works.append(gather_chunk_async(shard[c0:c1], full, [r * block for r in range(world)], c0, c1))
+        for w in works:
+            w.wait()
+        pre = torch.empty((n, 4), dtype=torch.float64) if rank == 0 else None
+        got = gather_to_root(shard, n, dst=0, out=pre)
+        if rank == 0:
+            want = 7.0 * torch.arange(n, dtype=torch.float64)[:, None] + torch.arange(4, dtype=torch.float64)[None, :]
+            assert torch.equal(full, want)
+            assert got is pre and torch.equal(pre, want)
+            out.put("ok")
+        else:
+            assert got is None
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,block,nchunk", [(2, 12, 4), (2, 5, 3), (3, 4, 1)])
+def test_chunked_async_gather_gloo(world, block, nchunk):
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_chunks, args=(r, world, port, block, nchunk, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
+    assert out.get(timeout=5) == "ok"
