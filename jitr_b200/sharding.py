@@ -128,5 +128,6 @@ class PeerWindow:
         torch.cuda.synchronize(self.device)
         if self.rank != self.dst:
             self.buf = None
+            torch.cuda.ipc_collect()  # give the mapping back now, not at the next allocator sweep
         dist.barrier(group=self.group)
         self.buf = None
