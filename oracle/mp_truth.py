@@ -66,7 +66,12 @@ def smatrix_element_refined(ws, central, spin_orbit, coulomb, l, jj, steps=3):
 
     if np.finfo(np.longdouble).eps > 1e-18:
         return smatrix_element_mp(ws, central, spin_orbit, coulomb, l, jj)
-    A = _oracle_matrix(ws, central, spin_orbit, coulomb, l, jj)
+    return _refined_from_matrix(ws, _oracle_matrix(ws, central, spin_orbit, coulomb, l, jj), l, steps)
+
+
+def _refined_from_matrix(ws, A, l, steps=3):
+    import scipy.linalg as sla
+
     b = np.asarray(ws.b, dtype=np.complex128)
     lu = sla.lu_factor(A)
     x = sla.lu_solve(lu, b).astype(np.clongdouble)
@@ -80,13 +85,36 @@ def smatrix_element_refined(ws, central, spin_orbit, coulomb, l, jj, steps=3):
     return complex((Hm - a * R * Hmp) / (Hp - a * R * Hpp))
 
 
+def smatrix_input_noise(ws, central, spin_orbit, coulomb, l, jj, trials=4, seed=1):
+    """What ONE ULP of uncertainty in the float64 matrix does to this S-matrix element: max over `trials` random sign patterns E of
+    |S(A o (1 + 2^-53 E)) - S(A)| / |S(A)|, every solve exact to ~1e-12 (smatrix_element_refined).  Any float64 algorithm --
+    LAPACK's explicit inverse in the reference as much as an LU or LDL^T on the GPU -- is backward stable at best: its result is the
+    exact one of a matrix perturbed by a modest multiple p(n) of that, so p(n) x this number is the accuracy to which the
+    reference's value is DEFINED.  The parity gate uses it to judge the handful of elements of a large sweep that differ by more
+    than 1e-10 (tools/parity_config2.referee_outliers)."""
+    if np.finfo(np.longdouble).eps > 1e-18:
+        return float("nan")
+    A = _oracle_matrix(ws, central, spin_orbit, coulomb, l, jj)
+    s0 = _refined_from_matrix(ws, A, l)
+    rng = np.random.default_rng(seed)
+    u = 2.0 ** -53
+    worst = 0.0
+    for _ in range(trials):
+        E = rng.choice([-1.0, 1.0], size=A.shape)
+        E = np.triu(E) + np.triu(E, 1).T  # a symmetric perturbation keeps the matrix complex symmetric
+        s1 = _refined_from_matrix(ws, A * (1.0 + u * E), l)
+        worst = max(worst, abs(s1 - s0) / abs(s0))
+    return float(worst)
+
+
 def _referee_chunk(args):
     return referee(*args, procs=1)
 
 
 def referee(energy_table, rows, items, N=40, lmax=30, projectile=(1, 0), dps=40, procs=None):
     """items: list of (row index, energy index, l, jj).  Returns the list of exact-to-1e-12 S values (complex128):
-    dps > 0 -> mpmath at `dps` digits, dps = 0 -> float64 LU + 80-bit iterative refinement."""
+    dps > 0 -> mpmath at `dps` digits, dps = 0 -> float64 LU + 80-bit iterative refinement; dps < 0 -> not S but its sensitivity to
+    one ulp of input uncertainty (smatrix_input_noise)."""
     from oracle import jitr_oracle as orc
 
     import os
@@ -113,5 +141,8 @@ def referee(energy_table, rows, items, N=40, lmax=30, projectile=(1, 0), dps=40,
         ws, tgt, Elab = cache[e]
         with np.errstate(over="ignore"):
             c, so, co = orc.kduq_potentials(ws.rgrid, projectile, tgt, Elab, rows[i])
-        out.append(smatrix_element_mp(ws, c, so, co, l, jj, dps) if dps > 0 else smatrix_element_refined(ws, c, so, co, l, jj))
+        if dps < 0:
+            out.append(smatrix_input_noise(ws, c, so, co, l, jj))
+        else:
+            out.append(smatrix_element_mp(ws, c, so, co, l, jj, dps) if dps > 0 else smatrix_element_refined(ws, c, so, co, l, jj))
     return out

@@ -284,3 +284,26 @@ def test_refinement_referee_matches_40_digit_solve():
     fast = mp_truth.referee(tab, rows, items, dps=0, procs=2)
     for a, b in zip(exact, fast):
         assert abs(a - b) / abs(a) < 1e-13
+
+
+def test_one_ulp_input_noise_of_the_referee():
+    """oracle/mp_truth.smatrix_input_noise: the change one ulp of uncertainty in the matrix entries makes to an S-matrix element.
+    It must be a small multiple of machine epsilon for well-conditioned elements, it must reproduce (seeded), and the float64
+    oracle itself must sit within a few of these 'input ulps' of the exact value -- the yardstick the large-sample gate uses
+    for the handful of elements of 10^7 that no float64 algorithm pins to 1e-10."""
+    from jitr_b200 import workloads
+    from oracle import mp_truth, parity_sweep
+
+    tab = workloads.energy_table()
+    rows = workloads.synthetic_kduq_samples(8)
+    items = [(0, 5, 3, 0), (1, 40, 7, 1), (5, 0, 0, 0), (7, 63, 12, 1)]
+    noise = mp_truth.referee(tab, rows, items, dps=-1, procs=2)
+    again = mp_truth.referee(tab, rows, items, dps=-1, procs=1)
+    assert noise == again
+    exact = mp_truth.referee(tab, rows, items, dps=0, procs=2)
+    o = parity_sweep.run([tab[e] for e in sorted({e for _, e, _, _ in items})], rows, procs=2)
+    emap = {e: k for k, e in enumerate(sorted({e for _, e, _, _ in items}))}
+    for (i, e, l, jj), nz, st in zip(items, noise, exact):
+        assert 1e-17 < nz < 1e-9
+        so_ = (o["splus"] if jj == 0 else o["sminus"])[i, emap[e], l]
+        assert abs(so_ - st) / abs(st) < max(1e-12, 16 * nz)

@@ -25,6 +25,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 RTOL_S, RTOL_XS = 1e-10, 1e-8
+ULP_FACTOR = 8.0  # an outlier may sit this many input-ulps from the exact S (a backward error of 8 ulp in an n = 40 elimination)
 
 
 def parity_rows(n_synthetic=1000, pool=100000):
@@ -139,7 +140,10 @@ def referee_outliers(g, o, rows, tab, max_systems=4000, max_pairs=16, procs=None
     float64 matrix (oracle/mp_truth.py: float64 LU + iterative refinement with 80-bit residuals, exact to ~1e-12; the eight
     worst systems also by mpmath at 40 digits as a cross-check of the referee itself) decides: the reference obtains R through an explicit inverse at cond(A) up to 1e7,
     so its own S carries ~1e-10 .. 1e-9 of rounding noise on a handful of systems of a large sweep.  An outlier is
-    EXPLAINED when the CUDA value is inside the tolerance of the exact value, or at least as close to it as the oracle's."""
+    EXPLAINED when the CUDA value is inside the tolerance of the exact value, or at least as close to it as the oracle's, or
+    within ULP_FACTOR x the change ONE ulp of uncertainty in the matrix entries makes to that element (on 6 416 rows x 64
+    workspaces = 1.5e7 systems: 37 elements beyond 1e-10, all with |S| < 2e-3, 1-ulp noise 0.7 .. 4.9e-10; CUDA at most 3.5,
+    the float64 reference at most 3.2 input-ulps from the exact value: both are as accurate as float64 permits)."""
     from oracle import jitr_oracle as orc
     from oracle import mp_truth
 
@@ -157,16 +161,25 @@ def referee_outliers(g, o, rows, tab, max_systems=4000, max_pairs=16, procs=None
         truth = mp_truth.referee(tab, rows, items, dps=0, procs=procs)
         truth40 = mp_truth.referee(tab, rows, items[:8], dps=40, procs=procs)
         rep["referee_vs_mp40_max"] = float(max(abs(a - b) / abs(b) for a, b in zip(truth[:8], truth40)))
-        for (i, e, l, jj), st in zip(items, truth):
+        # what ONE ULP of uncertainty in the float64 matrix does to each of these elements (mp_truth.smatrix_input_noise): a
+        # backward-stable float64 solve -- the reference's included -- is the exact solve of a matrix perturbed by a few ulps
+        noise = mp_truth.referee(tab, rows, items, dps=-1, procs=procs)
+        rep["ulp_factor_allowed"] = ULP_FACTOR
+        rep["gpu_error_in_input_ulps_max"] = 0.0
+        rep["oracle_error_in_input_ulps_max"] = 0.0
+        for (i, e, l, jj), st, nz in zip(items, truth, noise):
             sg = g["S"][i, e, jj, l]
             so_ = (o["splus"] if jj == 0 else o["sminus"])[i, e, l]
             eg, eo = abs(sg - st) / abs(st), abs(so_ - st) / abs(st)
-            ok = eg < RTOL_S or eg <= eo
+            ok = eg < RTOL_S or eg <= eo or eg <= ULP_FACTOR * nz
             rep["S_refereed"] += 1
             rep["S_explained"] += int(ok)
+            if nz == nz and nz > 0:
+                rep["gpu_error_in_input_ulps_max"] = max(rep["gpu_error_in_input_ulps_max"], float(eg / nz))
+                rep["oracle_error_in_input_ulps_max"] = max(rep["oracle_error_in_input_ulps_max"], float(eo / nz))
             if len(rep["S_worst"]) < 8:
                 rep["S_worst"].append({"row": i, "energy": e, "l": l, "jj": jj, "abs_S": abs(st), "gpu_vs_oracle": float((ep if jj == 0 else em)[i, e, l]),
-                                       "gpu_vs_mp40": float(eg), "oracle_vs_mp40": float(eo)})
+                                       "gpu_vs_mp40": float(eg), "oracle_vs_mp40": float(eo), "one_ulp_of_input_noise": float(nz)})
     # cross sections: pairs with an angle beyond the gate -> every kept partial wave of the pair solved in 40 digits
     ed = np.abs(g["dsdo"] - o["dsdo"]) / o["dsdo"]
     bad_pairs = np.argwhere(ed.max(axis=-1) >= RTOL_XS)
