@@ -225,6 +225,7 @@ class Config2:
         mark = (lambda: _mark(torch)) if ev is not None else (lambda: None)
         B = self.B
         nchunk = max(1, min(self.args.gather_chunks if self.windows is not None else self.args.nccl_gather_chunks, B)) if self.world > 1 else 1
+        nchunk = min(nchunk, max(1, (B * self.nE) // 100000))  # a chunk keeps >= 1e5 (sample, energy) pairs: ~100 per resident warp
         equal = self.S_total == B * self.world
         if self.world > 1 and not equal:
             nchunk = 1
@@ -295,10 +296,10 @@ class Config2:
         per_rank = self.tr.numel() * 8 + (0 if self.args.no_gather_dsdo else self.dsdo.numel() * 8)
         what = "dsigma/dOmega [S/G, E, n_angles] + (sigma_tot, sigma_rxn) [S/G, E, 2] to rank 0"
         if self.windows is not None:
-            op = (f"copy-engine peer copies (CUDA IPC window on rank 0, cudaMemcpyAsync over NVLink, no SMs) of {what}, in {self.args.gather_chunks} chunks of "
-                  "samples per step, each queued behind its chunk's kernels and overlapped with the next chunk's solve, + one 4-byte NCCL all_reduce as "
+            op = (f"copy-engine peer copies (CUDA IPC window on rank 0, cudaMemcpyAsync over NVLink, no SMs) of {what}, in up to {self.args.gather_chunks} chunks of "
+                  "samples per step (>= 1e5 pairs each), each queued behind its chunk's kernels and overlapped with the next chunk's solve, + one 4-byte NCCL all_reduce as "
                   "the completion barrier; ms_per_step = what stays exposed after the last chunk's kernels")
-            chunks = int(self.args.gather_chunks)
+            chunks = min(int(self.args.gather_chunks), max(1, (self.B * self.nE) // 100000))
         else:
             chunks = int(self.args.nccl_gather_chunks)
             op = f"torch.distributed.gather (NCCL) of {what}, once per step" + ("" if chunks == 1 else f" in {chunks} asynchronous chunks")
