@@ -434,6 +434,20 @@ packed_solve_kernel(const GenArgs A, const int* __restrict__ symflag, const int 
                              "r"(bytes), "r"(bar)
                              : "memory");
             }
+#ifndef JITR_PACKED_NO_UPPER_PREFETCH
+            // the symmetry check reads the UPPER triangle from global memory block row by block row (stage_system): ask the L2 for
+            // those lines now, while the bulk copies of the lower triangle are in flight -- the check then waits for L2 hits instead
+            // of eight DRAM round trips in sequence.  Every line is still read from DRAM once (this system's data, used within
+            // microseconds; unlike a prefetch of the NEXT system, which doubled the DRAM reads and was removed).
+            if (check_symmetry) {
+                for (int r = lane; r < N - 1; r += 32) {
+                    const char* p0 = reinterpret_cast<const char*>(Vsrc + (size_t)r * N + r + 1);
+                    const char* p1 = reinterpret_cast<const char*>(Vsrc + (size_t)r * N + N) - 1;
+                    for (const char* q = p0; q <= p1; q += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(p1));
+                }
+            }
+#endif
             mbar_wait(bar, parity);
             parity ^= 1u;
         }
