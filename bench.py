@@ -581,7 +581,7 @@ def main():
     ap.add_argument("--gather-mode", default="p2p", choices=["nccl", "p2p"],
                     help="N > 1: how the observables reach rank 0 -- p2p: copy-engine peer copies into a CUDA-IPC window on rank 0, chunk by chunk beside "
                          "the solve (falls back to nccl if the window cannot be set up); nccl: one torch.distributed.gather at the end of the step")
-    ap.add_argument("--gather-chunks", type=int, default=8, help="p2p mode: chunks of samples per step; a chunk's observables travel to rank 0 while the next is solved")
+    ap.add_argument("--gather-chunks", type=int, default=4, help="p2p mode: chunks of samples per step; a chunk's observables travel to rank 0 while the next is solved")
     ap.add_argument("--nccl-gather-chunks", type=int, default=1, help="nccl mode: > 1 launches one asynchronous gather per chunk (measured slower: its copy kernels wait for SMs)")
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--cpu-pairs", type=int, default=None, help="CPU arm: (sample, energy) pairs (configs 1-3) or systems (4, 5) per worker")
