@@ -104,6 +104,30 @@ class PeerWindow:
             self.buf = fn(*args)
         self.stream = torch.cuda.Stream(device=self.device)
         self._flag = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._self_check(dist.get_world_size(group))
+
+    def _self_check(self, world):
+        """Every rank writes a marker through its mapping, the root reads them back: a mapping that does not reach the root's
+        memory (an IPC handle rebuilt on a different layout of torch's reduction tuple, say) raises here on EVERY rank, and the
+        caller falls back to the collective."""
+        import torch
+        import torch.distributed as dist
+
+        flat = self.buf.view(-1)
+        ok = torch.ones(1, dtype=torch.int32, device=self.device)
+        if flat.numel() >= world:
+            saved = flat[:world].clone() if self.rank == self.dst else None
+            dist.barrier(group=self.group)
+            flat[self.rank: self.rank + 1].copy_(torch.full((1,), float(self.rank + 1), dtype=flat.dtype, device=self.device))
+            torch.cuda.synchronize(self.device)
+            dist.barrier(group=self.group)
+            if self.rank == self.dst:
+                want = torch.arange(1, world + 1, dtype=flat.dtype, device=self.device)
+                ok[0] = int(torch.equal(flat[:world], want))
+                flat[:world].copy_(saved)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+        if int(ok.item()) != 1:
+            raise RuntimeError("PeerWindow: the peers' writes did not reach the root's buffer")
 
     def push(self, chunk, row0: int):
         import torch
