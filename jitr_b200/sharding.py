@@ -155,3 +155,5 @@ class PeerWindow:
             torch.cuda.ipc_collect()  # give the mapping back now, not at the next allocator sweep
         dist.barrier(group=self.group)
         self.buf = None
+        if self.rank == self.dst:
+            torch.cuda.ipc_collect()
