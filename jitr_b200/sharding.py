@@ -88,20 +88,39 @@ class PeerWindow:
         self.group, self.dst = group, dst
         self.rank = dist.get_rank(group)
         self.device = torch.device(device)
+        # every step that can fail on ONE rank is followed by a vote before the next collective, so that a failure raises on all
+        # ranks (the caller falls back to the gather) instead of leaving the others waiting
+        err = None
         payload = [None]
         if self.rank == dst:
-            self.buf = torch.empty(shape, dtype=dtype, device=self.device)
-            payload = [reduce_tensor(self.buf)]
+            try:
+                self.buf = torch.empty(shape, dtype=dtype, device=self.device)
+                payload = [reduce_tensor(self.buf)]
+            except Exception as exc:  # noqa: BLE001
+                err = exc
         dist.broadcast_object_list(payload, src=dst, group=group)
         if self.rank != dst:
-            fn, args = payload[0]
-            # The IPC handle is opened in THIS rank's device context (argument 6 of rebuild_cuda_tensor is the device the handle
-            # is opened on): the mapping is then a peer pointer this GPU's copy engines write through NVLink directly.  Opened on
-            # the root's device instead (the default), the memory belongs to another context of this process and the copy is
-            # staged through the host: measured 37 GB/s and no overlap (tools/p2p_probe.py).
-            args = list(args)
-            args[6] = self.device.index
-            self.buf = fn(*args)
+            if payload[0] is None:
+                err = RuntimeError("the root could not export its buffer")
+            else:
+                try:
+                    fn, args = payload[0]
+                    # The IPC handle is opened in THIS rank's device context (argument 6 of rebuild_cuda_tensor is the device the
+                    # handle is opened on): the mapping is then a peer pointer this GPU's copy engines write through NVLink directly.
+                    # Opened on the root's device instead (the default), the memory belongs to another context of this process and
+                    # the copy is staged through the host: measured 37 GB/s and no overlap (tools/p2p_probe.py).
+                    args = list(args)
+                    if not isinstance(args[6], int):
+                        raise RuntimeError("unexpected layout of torch's CUDA tensor reduction")
+                    args[6] = self.device.index
+                    self.buf = fn(*args)
+                except Exception as exc:  # noqa: BLE001
+                    err = exc
+        ok = torch.tensor([0 if err is not None else 1], dtype=torch.int32, device=self.device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if int(ok.item()) != 1:
+            self.buf = None
+            raise RuntimeError(f"PeerWindow unavailable on this node: {err!r}")
         self.stream = torch.cuda.Stream(device=self.device)
         self._flag = torch.zeros(1, dtype=torch.int32, device=self.device)
         self._self_check(dist.get_world_size(group))
